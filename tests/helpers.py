@@ -1,0 +1,40 @@
+"""Shared comparison helpers for the parity tests."""
+import numpy as np
+
+SAMPLE_STRIDE = 997  # must match tests/golden/make_golden.py
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|: the 'relative' error the north_star tolerances are stated in
+    (normalised by the tensor's largest magnitude; element-wise ratios are meaningless
+    for entries that are ~0)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    denom = max(float(np.abs(b).max()) if b.size else 0.0, 1e-30)
+    return float(np.abs(a - b).max() / denom) if b.size else 0.0
+
+
+def check_summary(golden, prefix, name, x, tol, atol=0.0):
+    """Compare tensor x with what make_golden.summarize stored under prefix/name."""
+    x = np.asarray(x)
+    kf, ks = f"{prefix}/{name}/full", f"{prefix}/{name}/sample"
+    if kf in golden:
+        ref = golden[kf]
+        got = x.reshape(ref.shape)
+    else:
+        ref = golden[ks]
+        got = x.reshape(-1)[::SAMPLE_STRIDE]
+    if ref.dtype.kind in "iu":
+        assert np.array_equal(got, ref), f"{prefix}/{name}: integer mismatch"
+        return 0.0
+    n = float(golden[f"{prefix}/{name}/norm"])
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err = float(np.abs(got.astype(np.float64) - ref).max() / scale)
+    assert err <= tol + atol / scale, f"{prefix}/{name}: rel err {err:.3e} > {tol:.1e}"
+    gn = float(np.sqrt((x.astype(np.float64) ** 2).sum()))
+    assert abs(gn - n) <= tol * max(n, 1e-30) * 10 + atol * np.sqrt(x.size) + 1e-30, f"{prefix}/{name}: norm {gn} vs {n}"
+    return err
+
+
+def unpack_mask(bits, shape):
+    return np.unpackbits(bits)[: int(np.prod(shape))].reshape(shape)
