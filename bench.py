@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- FiBiNET train-step throughput on synthetic MicroLens_1M_x1-shaped batches.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+One "step" = zero_grad -> forward -> BCELoss -> backward -> clip_grad_norm_(10) -> Adam(wd 1e-5) ->
+OneCycleLR (reference src/train_fibinet.py:113-122) over one batch.  Prints ONE JSON line (rank 0).
+  value : whole-job samples/s with the batch already resident in HBM (CUDA-event timed, max over ranks)
+  e2e   : same through the public API from pinned HOST buffers, H2D copy and loss read-back inside the
+          timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train samples/sec FiBiNET MicroLens-shape"
+UNIT = "samples/s"
+L_HIST = 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("FBN_BENCH_BATCH", "16384")), help="per-GPU batch")
+    ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "fp32"))
+    ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), tf=float(p["bf16_tflops"]), tf_sus=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_pool(args, rank, n):
+    """n synthetic batches as pinned host tensors in the reference loader's dtypes
+    (float64 scalars, int64 item_seq, fp32 item_emb_d128, fp32 labels)."""
+    from oracle import synth
+    table = synth.make_item_mm_table(seed=11)
+    pool = []
+    for i in range(n):
+        b, y = synth.make_batch(seed=2025 + 1000 * rank + i, batch=args.batch, max_len=L_HIST, id_dist=args.id_dist,
+                                index_dtype=np.float64, mm_table=table, edge_cases=False)
+        b.pop("user_id")
+        host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items()}
+        pool.append((host, torch.from_numpy(y).pin_memory()))
+    return pool
+
+
+def run_ours(args):
+    from ctr_recommendation_b200 import build_model, FusedAdam, clip_grad_norm_, _lib
+    from ctr_recommendation_b200 import dist as fdist
+    import torch.distributed as dist
+    rank, local, world = fdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    _lib.check(lib.fbn_check_device(local), "fbn_check_device")
+    torch.manual_seed(2025)
+    model = build_model({"precision": args.precision}, {"embedding_dim": 128}).to(dev).train()
+    if world > 1:
+        fdist.broadcast_parameters(model)
+    opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+    total_steps = max(10, 2 * (args.steps + args.warmup) * 2 + 10)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=total_steps, pct_start=0.3, div_factor=25.0,
+                                                final_div_factor=1000.0)
+    loss_fn = torch.nn.BCELoss()
+    pool = make_pool(args, rank, args.pool)
+    dev_pool = [({k: v.to(dev) for k, v in b.items()}, y.to(dev)) for b, y in pool]
+    stage = ({k: torch.empty_like(v, device=dev) for k, v in pool[0][0].items()}, torch.empty_like(pool[0][1], device=dev))
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pool[0][0].values()) + pool[0][1].numel() * 4
+
+    def step(batch, labels):
+        opt.zero_grad()
+        y = model(batch)
+        loss = loss_fn(y, labels)
+        loss.backward()
+        if world > 1:
+            fdist.sync_gradients(model)
+        clip_grad_norm_(model, 10.0)
+        opt.step()
+        sched.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            fn(k)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def resident(k):
+        b, y = dev_pool[k % len(dev_pool)]
+        step(b, y)
+
+    def e2e(k):
+        hb, hy = pool[k % len(pool)]
+        for name, t in hb.items():
+            stage[0][name].copy_(t, non_blocking=True)
+        stage[1].copy_(hy, non_blocking=True)
+        loss = step(stage[0], stage[1])
+        return loss.item()      # D2H read of the step's result, like the reference loop (:124)
+
+    for k in range(args.warmup):
+        resident(k)
+    launches0 = lib.fbn_launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(resident, args.steps)
+    launches = lib.fbn_launch_count() - launches0
+    for k in range(max(1, args.warmup // 2)):
+        e2e(k)
+    with ClockSampler(local) as clk2:
+        ms_e2e = timed(e2e, args.steps)
+
+    global_batch = args.batch * world
+    value = global_batch * args.steps / (ms / 1e3)
+    e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
+    peaks = load_peaks()
+    kernels = kernel_rooflines(args, model, dev_pool[0], peaks, lib) if rank == 0 else {}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "config": {"workload": f"FiBiNET train step (config/fibinet_config.yaml model: D=128, 6 fields, bilinear all, MLP 2688-512-256-1), "
+                               f"per-GPU batch {args.batch}, history L={L_HIST}, item ids {args.id_dist}, replicated tables",
+                   "global_batch": global_batch, "per_gpu_batch": args.batch, "parallelism": f"dp{world}",
+                   "precision": args.precision,
+                   "l2": "working set per step (table p/m/v/grad 188 MB + activations) exceeds the 126 MB L2; inputs cycle over "
+                         f"{args.pool} distinct batches"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "clocks_e2e": clk2.summary(),
+    }
+    if rank == 0:
+        out.update(kernels)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, steps=3, warmup=1)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(args, model, dev_batch, peaks, lib):
+    """Stand-alone CUDA-event timings of the kernels the step is made of, against their rooflines.
+    Algorithmic bytes / FLOPs per unit are the figures of SURVEY 8(d) (restated in DESIGN.md)."""
+    import ctypes as C
+    from ctr_recommendation_b200 import _lib
+    B = args.batch
+    st = _lib.stream_ptr()
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def time_kernel(fn, iters=10):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.fill_(1.0)               # evict L2 between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    out = {}
+    # (1) dense-exact table Adam: 6 streams (p,m,v in/out) + gradient rows read
+    opt = model._fused_optimizer
+    rows = model.item_emb.weight.shape[0]
+    h = _lib.AdamHyper(1e-3, 0.9, 0.999, 1e-8, 1e-5, 10)
+    w = model.item_emb.weight.data
+
+    def adam():
+        _lib.check(lib.fbn_adam_table(_lib.ptr(w), _lib.ptr(opt._m_item), _lib.ptr(opt._v_item), _lib.ptr(model._item_grad),
+                                      _lib.ptr(model._row_touched), rows, None, C.byref(h), None, st))
+    ms = time_kernel(adam)
+    touched = int((model._row_touched > 0).sum().item())
+    adam_bytes = 6 * rows * 512 + touched * 512 + rows * 4
+    out["adam_table"] = {"ms": ms, "bytes": adam_bytes, "GBps": adam_bytes / ms / 1e6, "frac": adam_bytes / ms / 1e6 / peaks["hbm"]}
+    # (2) fused gather + pooling + projection + SENET
+    model.eval()
+    bs, keep, Bq, L = model._batch_struct(dev_batch[0])
+    ws = model._workspace(Bq, L)
+    P = model._params_struct()
+
+    def gather():
+        _lib.check(lib.fbn_embed_forward(C.byref(P), C.byref(bs), _lib.ptr(ws), ws.numel(), 1, st))
+    ms = time_kernel(gather)
+    nvalid = int((dev_batch[0]["item_seq"] != 0).sum().item())
+    # idx 184 B + 2 cate rows + item row + mm vector + history rows + V out (2560) + saved X5/xhat (3072 + 32)
+    g_bytes = B * (184 + 2 * 512 + 512 + 512 + 2560 + 2560 + 512 + 48) + nvalid * 512
+    out["gather_senet_fwd"] = {"ms": ms, "bytes": g_bytes, "GBps": g_bytes / ms / 1e6, "frac": g_bytes / ms / 1e6 / peaks["hbm"]}
+    model.train()
+    # (3) the MLP-1 GEMM (B x 2688 x 512; 1920 live K columns)
+    A = torch.randn(B, 2688, device="cuda")
+    Wt = torch.randn(512, 2688, device="cuda")
+    Cc = torch.empty(B, 512, device="cuda")
+
+    def gemm():
+        _lib.check(lib.fbn_gemm(_lib.ptr(A), _lib.ptr(Wt), None, _lib.ptr(Cc), B, 512, 2688, 2688, 2688, 512, 0, 1,
+                                _lib.PRECISIONS[args.precision], None, 0, st))
+    ms = time_kernel(gemm, iters=5)
+    flops = 2.0 * B * 2688 * 512
+    out["mlp1_gemm"] = {"ms": ms, "flops": flops, "TFLOPs": flops / ms / 1e9, "frac_of_bf16_peak": flops / ms / 1e9 / peaks["tf"]}
+    dom = max(("adam_table", "gather_senet_fwd"), key=lambda k: out[k]["ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": out[dom]["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": out[dom]["frac"], "traffic": None, "peak_source": peaks["src"]}
+    return {"roofline": roof, "kernels": out}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(args, steps, warmup):
+    """The reference's CPU train step (oracle/fibinet_torch_port.py: same ATen op stream), all host cores,
+    on a bounded sample of the workload."""
+    from oracle import fibinet_torch_port as port
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = min(args.cpu_sample, args.batch)
+    W = synth.make_weights(seed=7)
+    tr = port.Trainer(port.tensors_from_numpy(W), lr=1e-3, weight_decay=1e-5)
+    table = synth.make_item_mm_table(seed=11)
+    batches = []
+    for i in range(2):
+        b, y = synth.make_batch(seed=2025 + i, batch=B, id_dist=args.id_dist, index_dtype=np.float64, mm_table=table, edge_cases=False)
+        b.pop("user_id")
+        batches.append(({k: torch.from_numpy(v) for k, v in b.items()}, torch.from_numpy(y)))
+    for k in range(warmup):
+        tr.step(*batches[k % 2])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        tr.step(*batches[k % 2])
+    dt = time.perf_counter() - t0
+    return {"value": B * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} train steps of {B} rows (of the {args.batch}-row workload batch), torch {torch.__version__} CPU fp32, "
+                      f"{cores} host cores", "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    warmup = max(1, min(args.warmup, 2))
+    cb = cpu_baseline(args, steps=steps, warmup=warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"FiBiNET train step, reference op stream on host CPU, {min(args.cpu_sample, args.batch)}-row sample of the "
+                                  f"per-GPU batch {args.batch} workload", "parallelism": "cpu"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,449 @@
+// extern "C" surface of libfibinet_b200.so: argument validation + the launch sequence of one
+// forward / backward pass.  All orchestration is native so that a training step costs one FFI call
+// per phase (and can be captured into a CUDA graph by the host).
+#include <algorithm>
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "tower.h"
+
+namespace fbn {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sms = v;
+    else {
+      cudaGetLastError();
+      sms = 148;  // B200
+    }
+  }
+  return sms;
+}
+
+static int pick_splits(long long tiles, long long K) {
+  const long long ktiles = std::max<long long>(1, cdiv(K, 16));
+  long long s = cdiv(2LL * 148, std::max<long long>(tiles, 1));
+  s = std::min<long long>(s, 32);
+  s = std::min<long long>(s, ktiles);
+  return (int)std::max<long long>(s, 1);
+}
+
+// K blocks of the MLP input that can be non-zero: fields 1..5 and pairs (i>=1, j)
+static unsigned long long active_mask() {
+  unsigned long long m = 0;
+  for (int f = 1; f < NF; ++f) m |= 1ull << f;
+  for (int blk = NF + (NF - 1); blk < NF + FBN_PAIRS; ++blk) m |= 1ull << blk;
+  return m;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t rows) {
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = base ? p + off : nullptr;
+    off += align_up(bytes);
+    return r;
+  };
+  const size_t f = sizeof(float);
+  const int64_t Bp = std::max<int64_t>(B, 1);
+  const int64_t Lp = std::max<int64_t>(L, 1);
+  w.B = B; w.L = L;
+  w.ids = (int32_t*)take(Bp * 4 * 4);
+  w.seq = (int32_t*)take(Bp * Lp * 4);
+  w.X5 = (float*)take(Bp * NA * D * f);
+  w.sgate = (float*)take(Bp * 8 * f);
+  w.xhat = (float*)take(Bp * D * f);
+  w.xmm = (float*)take(Bp * D * f);
+  w.rstd = (float*)take(Bp * f);
+  w.cnt = (float*)take(Bp * f);
+  w.C = (float*)take(Bp * K1 * f);
+  w.T = (float*)take(Bp * 10 * D * f);
+  w.Hd1 = (float*)take(Bp * H1 * f);
+  w.A1 = (float*)take(Bp * H1 * f);
+  w.Hd2 = (float*)take(Bp * H2 * f);
+  w.A2 = (float*)take(Bp * H2 * f);
+  w.logit = (float*)take(Bp * f);
+  w.prob = (float*)take(Bp * f);
+  w.bn = (float*)take((2 * H1 + 2 * H2) * f);
+  w.dlogit = (float*)take(Bp * f);
+  w.dH2 = (float*)take(Bp * H2 * f);
+  w.dH1 = (float*)take(Bp * H1 * f);
+  w.dC = (float*)take(Bp * K1 * f);
+  w.dT = (float*)take(Bp * 10 * D * f);
+  w.dV = (float*)take(Bp * NA * D * f);
+  w.dXitem = (float*)take(Bp * D * f);
+  w.dXhist = (float*)take(Bp * D * f);
+  w.dln = (float*)take(Bp * D * f);
+  w.dy = (float*)take(Bp * D * f);
+  w.sestat = (float*)take(Bp * 24 * f);
+  size_t pf = 0;
+  pf = std::max<size_t>(pf, (size_t)pick_splits(4 * 21, Bp) * H1 * K1);
+  pf = std::max<size_t>(pf, (size_t)pick_splits(2 * 4, Bp) * H2 * H1);
+  pf = std::max<size_t>(pf, (size_t)10 * 32 * D * D);
+  pf = std::max<size_t>(pf, (size_t)2 * 148 * 4 * MAX_CATE * D);
+  pf = std::max<size_t>(pf, (size_t)4 * 148 * 3 * H1);
+  pf = std::max<size_t>(pf, (size_t)cdiv(rows, 8) + 1024);
+  pf = std::max<size_t>(pf, (size_t)1024 * 48);
+  w.partial_floats = pf;
+  w.partial = (float*)take(pf * f);
+  const int64_t nocc = Bp * (1 + Lp);
+  w.keys_in = (int32_t*)take(nocc * 4);
+  w.keys_out = (int32_t*)take(nocc * 4);
+  w.vals_in = (int32_t*)take(nocc * 4);
+  w.vals_out = (int32_t*)take(nocc * 4);
+  w.row_off = (int32_t*)take((rows + 1) * 4);
+  w.row_cnt = (int32_t*)take((rows + 1) * 4);
+  w.cub_bytes = emb_sort_temp_bytes(nocc, rows);
+  w.cub_tmp = take(w.cub_bytes);
+  w.total_bytes = off;
+}
+
+int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (precision == FBN_PREC_FP32) return gemm_simt(g, st);
+  return gemm_tc(g, precision, scratch, scratch_bytes, st);
+}
+
+// launchers defined in embed.cu
+struct EmbedFwdArgs;
+struct EmbedBwdArgs;
+
+}  // namespace fbn
+
+#include "embed_args.h"
+
+using namespace fbn;
+
+#define RC(x)            \
+  do {                   \
+    int _rc = (x);       \
+    if (_rc) return _rc; \
+  } while (0)
+
+static int check_common(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes) {
+  FBN_REQUIRE(p && b && ws, FBN_ERR_ARG, "null params / batch / workspace");
+  FBN_REQUIRE(b->batch >= 1, FBN_ERR_SHAPE, "batch must be >= 1");
+  FBN_REQUIRE(b->seq_len >= 0 && b->seq_len <= MAX_L, FBN_ERR_SHAPE, "seq_len must be in [0,%d]", MAX_L);
+  FBN_REQUIRE(p->cate_rows >= 1 && p->cate_rows <= MAX_CATE, FBN_ERR_SHAPE, "cate_rows must be in [1,%d]", MAX_CATE);
+  FBN_REQUIRE(p->item_rows >= 2, FBN_ERR_SHAPE, "item_rows must be >= 2");
+  FBN_REQUIRE(b->item_id && b->likes_level && b->views_level, FBN_ERR_ARG, "missing index columns");
+  FBN_REQUIRE(b->item_mm || b->mm_table, FBN_ERR_ARG, "item_emb_d128 (item_mm) or mm_table is required");
+  FBN_REQUIRE(b->idx_dtype >= FBN_IDX_I32 && b->idx_dtype <= FBN_IDX_F32, FBN_ERR_DTYPE, "bad idx_dtype");
+  FBN_REQUIRE(b->seq_dtype == FBN_IDX_I32 || b->seq_dtype == FBN_IDX_I64, FBN_ERR_DTYPE, "item_seq must be int32 or int64");
+  FBN_REQUIRE(p->bilinear_type >= FBN_BILINEAR_ALL && p->bilinear_type <= FBN_BILINEAR_INTERACTION, FBN_ERR_ARG, "bad bilinear_type");
+  FBN_REQUIRE(p->precision >= FBN_PREC_FP32 && p->precision <= FBN_PREC_BF16, FBN_ERR_ARG, "bad precision");
+  const void* ptrs[] = {p->item_emb, p->cate_emb, p->mm_w, p->mm_b, p->ln_g, p->ln_b, p->bil_w, p->w1, p->b1, p->bn1_g, p->bn1_b,
+                        p->bn1_mean, p->bn1_var, p->w2, p->b2, p->bn2_g, p->bn2_b, p->bn2_mean, p->bn2_var, p->w3, ws,
+                        b->item_mm, b->mm_table};
+  for (const void* q : ptrs) FBN_REQUIRE(aligned16(q), FBN_ERR_ALIGN, "a tensor pointer is not 16-byte aligned");
+  FBN_REQUIRE(p->se_w1 && p->se_b1 && p->se_w2 && p->se_b2 && p->b3, FBN_ERR_ARG, "null parameter pointer");
+  Workspace w;
+  carve_workspace(w, nullptr, b->batch, b->seq_len, p->item_rows);
+  FBN_REQUIRE(ws_bytes >= w.total_bytes, FBN_ERR_ARG, "workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
+  return FBN_OK;
+}
+
+extern "C" size_t fbn_workspace_bytes(int64_t batch, int64_t seq_len, int64_t item_rows) {
+  Workspace w;
+  carve_workspace(w, nullptr, batch, seq_len, item_rows);
+  return w.total_bytes;
+}
+
+extern "C" size_t fbn_workspace_offset(int64_t batch, int64_t seq_len, int64_t item_rows, const char* name) {
+  Workspace w;
+  char* base = reinterpret_cast<char*>(uintptr_t(4096));
+  carve_workspace(w, base, batch, seq_len, item_rows);
+  struct { const char* n; void* p; } tab[] = {
+      {"ids", w.ids}, {"seq", w.seq}, {"X5", w.X5}, {"sgate", w.sgate}, {"xhat", w.xhat}, {"rstd", w.rstd}, {"cnt", w.cnt},
+      {"C", w.C}, {"T", w.T}, {"H1", w.Hd1}, {"A1", w.A1}, {"H2", w.Hd2}, {"A2", w.A2}, {"logit", w.logit}, {"prob", w.prob},
+      {"bn", w.bn}, {"dlogit", w.dlogit}, {"dH2", w.dH2}, {"dH1", w.dH1}, {"dC", w.dC}, {"dT", w.dT}, {"dV", w.dV},
+      {"dXitem", w.dXitem}, {"dXhist", w.dXhist}, {"dln", w.dln}, {"dy", w.dy}, {"row_off", w.row_off}, {"row_cnt", w.row_cnt},
+      {"vals_out", w.vals_out}, {"keys_out", w.keys_out}};
+  for (auto& t : tab)
+    if (strcmp(t.n, name) == 0) return (size_t)((char*)t.p - base);
+  return (size_t)-1;
+}
+
+// ---- bilinear transforms T = V_src * W_idx ---------------------------------------------------
+static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStream_t st) {
+  const int type = p->bilinear_type;
+  const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
+  GemmArgs g;
+  g.M = w.B; g.N = D; g.K = D; g.lda = K1; g.ldb = D; g.ldc = nT * D; g.a_t = 0; g.b_t = 0;
+  if (type == FBN_BILINEAR_ALL) {           // T_t = V_{t+2} W
+    g.A = w.C + 2 * D; g.strideA = D; g.B = p->bil_w; g.strideB = 0; g.C = w.T; g.strideC = D; g.batch = 4;
+    return gemm(g, p->precision, nullptr, 0, st);
+  }
+  if (type == FBN_BILINEAR_EACH) {          // T_t = V_{t+1} W_{t+1}
+    g.A = w.C + 1 * D; g.strideA = D; g.B = p->bil_w + 1 * D * D; g.strideB = D * D; g.C = w.T; g.strideC = D; g.batch = 4;
+    return gemm(g, p->precision, nullptr, 0, st);
+  }
+  int q0 = 0;                               // T_q = V_i W_(i,j), grouped by i
+  for (int i = 1; i < NF - 1; ++i) {
+    const int nj = NF - 1 - i;
+    const int pidx = i * (2 * NF - i - 1) / 2;  // pair index of (i, i+1) in the full enumeration
+    g.A = w.C + i * D; g.strideA = 0; g.B = p->bil_w + (long long)pidx * D * D; g.strideB = D * D;
+    g.C = w.T + q0 * D; g.strideC = D; g.batch = nj;
+    RC(gemm(g, p->precision, nullptr, 0, st));
+    q0 += nj;
+  }
+  return FBN_OK;
+}
+
+static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace& w, int save, cudaStream_t st) {
+  const long long B = b->batch;
+  EmbedFwdArgs e{};
+  e.item_emb = p->item_emb; e.cate_emb = p->cate_emb; e.mm_w = p->mm_w; e.mm_b = p->mm_b; e.ln_g = p->ln_g; e.ln_b = p->ln_b;
+  e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.se_b2 = p->se_b2;
+  e.item_id = b->item_id; e.likes = b->likes_level; e.views = b->views_level;
+  e.seq = b->seq_len > 0 ? b->item_seq : nullptr;
+  e.item_mm = b->item_mm; e.mm_table = b->mm_table; e.idx_dtype = b->idx_dtype; e.seq_dtype = b->seq_dtype;
+  e.B = B; e.L = (int)b->seq_len; e.item_rows = p->item_rows; e.cate_rows = (int)p->cate_rows; e.save = save;
+  e.ids = w.ids; e.seq32 = w.seq; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.xmm = w.xmm; e.rstd = w.rstd; e.cnt = w.cnt;
+  e.C = w.C;
+  return launch_embed_senet_fwd(e, st);
+}
+
+// G1+S1 alone: gather + pooling + projection + SENET -> C[:, 128:768] (and the saved tensors if save != 0)
+extern "C" int fbn_embed_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int save, fbn_stream_t stream) {
+  RC(check_common(p, b, ws, ws_bytes));
+  Workspace w;
+  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  return run_embed_fwd(p, b, w, save, (cudaStream_t)stream);
+}
+
+extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
+                           const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset, float* prob_out,
+                           fbn_stream_t stream) {
+  RC(check_common(p, b, ws, ws_bytes));
+  FBN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FBN_ERR_ARG, "dropout_p must be in [0,1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  const long long B = b->batch;
+
+  RC(run_embed_fwd(p, b, w, 1, st));
+
+  RC(bilinear_transform_fwd(p, w, st));
+  RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, st));
+
+  float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
+  GemmArgs g1;
+  g1.A = w.C; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = K1; g1.lda = K1; g1.ldb = K1; g1.ldc = H1;
+  g1.b_t = 1; g1.kmask = active_mask();
+  RC(gemm(g1, p->precision, nullptr, 0, st));
+  if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
+  else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
+  DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1;
+  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, st));
+
+  GemmArgs g2;
+  g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2;
+  g2.b_t = 1;
+  RC(gemm(g2, p->precision, nullptr, 0, st));
+  if (train) RC(bn_train_stats(w.Hd2, B, H2, w.partial, mean2, rstd2, p->bn2_mean, p->bn2_var, st));
+  else RC(bn_eval_stats(p->bn2_mean, p->bn2_var, H2, mean2, rstd2, st));
+  DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2;
+  RC(head_fwd(w.Hd2, mean2, rstd2, p->bn2_g, p->bn2_b, p->w3, p->b3, B, d2, w.A2, w.logit, w.prob, st));
+  if (prob_out) FBN_CHECK_CUDA(cudaMemcpyAsync(prob_out, w.prob, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  return FBN_OK;
+}
+
+static int wgrad(const float* dOut, long long ldo, const float* In, long long ldi, long long B, long long M, long long N,
+                 unsigned long long nmask, int precision, Workspace& w, float* out, cudaStream_t st) {
+  // out[M,N] = dOut[B,M]^T * In[B,N]
+  GemmArgs g;
+  g.A = dOut; g.lda = ldo; g.a_t = 1; g.B = In; g.ldb = ldi; g.b_t = 0; g.M = M; g.N = N; g.K = B; g.ldc = N;
+  g.splits = pick_splits(cdiv(M, 128) * cdiv(N, 128), B);
+  g.nmask = nmask;
+  FBN_REQUIRE((size_t)g.splits * M * N <= w.partial_floats, FBN_ERR_ARG, "internal: split-K scratch too small");
+  g.C = w.partial; g.strideSplit = M * N;
+  RC(gemm(g, precision, nullptr, 0, st));
+  return reduce_splits(w.partial, g.splits, M, N, M * N, nmask, out, st);
+}
+
+extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
+                            const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat, int64_t dense_grad_n,
+                            float* item_grad, int32_t* row_touched, int zero_fill, float* grad_sumsq, fbn_stream_t stream) {
+  RC(check_common(p, b, ws, ws_bytes));
+  FBN_REQUIRE(dprob && g && item_grad && grad_sumsq, FBN_ERR_ARG, "fbn_backward: null pointer");
+  FBN_REQUIRE(aligned16(item_grad), FBN_ERR_ALIGN, "item_grad is not 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  const long long B = b->batch;
+  const int prec = p->precision;
+  const float scale = (train && dropout_p > 0.f) ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
+  const unsigned long long amask = active_mask();
+
+  // ---- head + layer 2 ----
+  RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
+                    st));
+  RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2, st));
+  RC(colsum(w.dH2, B, H2, w.partial, g->b2, st));
+  RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, st));
+  {
+    GemmArgs d;  // dA1 = dH2 * w2
+    d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
+    RC(gemm(d, prec, nullptr, 0, st));
+  }
+  // ---- layer 1 ----
+  RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
+  RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1, st));
+  RC(colsum(w.dH1, B, H1, w.partial, g->b1, st));
+  RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, st));
+  {
+    GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
+    d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
+    RC(gemm(d, prec, nullptr, 0, st));
+  }
+  // ---- bilinear ----
+  const int type = p->bilinear_type;
+  const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
+  RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, st));
+  {
+    GemmArgs d;  // dV[src] += dT_t * W^T
+    d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
+    if (type == FBN_BILINEAR_ALL) {
+      d.A = w.dT; d.strideA = D; d.B = p->bil_w; d.strideB = 0; d.C = w.dV + 1 * D; d.strideC = D; d.batch = 4;
+      RC(gemm(d, prec, nullptr, 0, st));
+    } else if (type == FBN_BILINEAR_EACH) {
+      d.A = w.dT; d.strideA = D; d.B = p->bil_w + D * D; d.strideB = D * D; d.C = w.dV; d.strideC = D; d.batch = 4;
+      RC(gemm(d, prec, nullptr, 0, st));
+    } else {
+      int q = 0;
+      for (int i = 1; i < NF - 1; ++i)
+        for (int j = i + 1; j < NF; ++j, ++q) {
+          const int pidx = i * (2 * NF - i - 1) / 2 + (j - i - 1);
+          d.A = w.dT + q * D; d.B = p->bil_w + (long long)pidx * D * D; d.C = w.dV + (i - 1) * D; d.batch = 1;
+          RC(gemm(d, prec, nullptr, 0, st));
+        }
+    }
+  }
+  {
+    // dW[idx] = sum_t V_src^T dT_t  (split-K over the batch, fixed-order reduction)
+    GemmArgs d;
+    d.a_t = 1; d.lda = K1; d.b_t = 0; d.ldb = nT * D; d.M = D; d.N = D; d.K = B; d.ldc = D;
+    const int S = pick_splits(nT, B);
+    d.splits = S; d.strideSplit = (long long)D * D; d.strideC = (long long)S * D * D; d.C = w.partial;
+    FBN_REQUIRE((size_t)nT * S * D * D <= w.partial_floats, FBN_ERR_ARG, "internal: bilinear scratch too small");
+    if (type == FBN_BILINEAR_ALL) {
+      d.A = w.C + 2 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
+      RC(gemm(d, prec, nullptr, 0, st));
+      RC(reduce_splits(w.partial, 4 * S, D, D, (long long)D * D, ~0ull, g->bil_w, st));
+    } else if (type == FBN_BILINEAR_EACH) {
+      d.A = w.C + 1 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
+      RC(gemm(d, prec, nullptr, 0, st));
+      FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * D * D, st));  // W_0 multiplies the zero field
+      for (int t = 0; t < 4; ++t)
+        RC(reduce_splits(w.partial + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull, g->bil_w + (long long)(t + 1) * D * D, st));
+    } else {
+      FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * (NF - 1) * D * D, st));  // pairs (0,j)
+      int q = 0;
+      for (int i = 1; i < NF - 1; ++i) {
+        const int nj = NF - 1 - i;
+        d.A = w.C + i * D; d.strideA = 0; d.B = w.dT + q * D; d.strideB = D; d.batch = nj; d.C = w.partial + (long long)q * S * D * D;
+        RC(gemm(d, prec, nullptr, 0, st));
+        q += nj;
+      }
+      for (int t = 0; t < 10; ++t)
+        RC(reduce_splits(w.partial + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull,
+                         g->bil_w + (long long)(NF - 1 + t) * D * D, st));
+    }
+  }
+  // ---- SENET + field stack + projection ----
+  EmbedBwdArgs e{};
+  e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
+  e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.ln_g = p->ln_g; e.B = B; e.cate_rows = (int)p->cate_rows;
+  e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial;
+  const int eb = embed_bwd_blocks(B);
+  FBN_REQUIRE((size_t)eb * p->cate_rows * D <= w.partial_floats, FBN_ERR_ARG, "internal: cate scratch too small");
+  RC(launch_embed_senet_bwd(e, eb, st));
+  RC(launch_reduce_partials(w.partial, g->cate_emb, eb, p->cate_rows * D, 0, st));
+  RC(launch_senet_param_grads(w.sestat, B, w.partial, g->se_w1, g->se_b1, g->se_w2, g->se_b2, st));
+  RC(colprod2(w.dln, w.xhat, B, D, w.partial, g->ln_g, g->ln_b, st));
+  RC(colsum(w.dy, B, D, w.partial, g->mm_b, st));
+  RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, st));
+  // ---- embedding table rows ----
+  EmbGradArgs eg{};
+  eg.ids = w.ids; eg.seq = (b->seq_len > 0 && b->item_seq) ? w.seq : nullptr; eg.B = B; eg.L = (int)b->seq_len; eg.rows = p->item_rows;
+  eg.dXitem = w.dXitem; eg.dXhist = w.dXhist; eg.keys_in = w.keys_in; eg.keys_out = w.keys_out; eg.vals_in = w.vals_in;
+  eg.vals_out = w.vals_out; eg.row_count = row_touched ? row_touched : w.row_cnt; eg.row_off = w.row_off; eg.cub_tmp = w.cub_tmp;
+  eg.cub_bytes = w.cub_bytes; eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_partial = w.partial; eg.sumsq_out = grad_sumsq + 1;
+  RC(emb_grad_rows(eg, st));
+  if (dense_grad_flat) {
+    FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");
+    RC(sumsq(dense_grad_flat, dense_grad_n, w.partial, grad_sumsq, st));
+  }
+  return FBN_OK;
+}
+
+// ---- BCELoss ---------------------------------------------------------------------------------
+namespace fbn {
+__global__ void bce_kernel(const float* __restrict__ prob, const float* __restrict__ y, long long B, float scale, float* loss_out,
+                           float* __restrict__ dprob) {
+  // single block: B <= a few 100k, fixed-order double accumulation
+  __shared__ double s[256];
+  double t = 0.0;
+  const float invB = 1.0f / (float)B;
+  for (long long i = threadIdx.x; i < B; i += 256) {
+    const float p = prob[i], yy = y[i];
+    const float lp = fmaxf(logf(p), -100.0f), l1p = fmaxf(log1pf(-p), -100.0f);
+    t += (double)(-(yy * lp + (1.0f - yy) * l1p));
+    if (dprob) dprob[i] = scale * ((p - yy) / fmaxf((1.0f - p) * p, 1e-12f)) * invB;
+  }
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && loss_out) loss_out[0] = (float)(s[0] / (double)B);
+}
+}  // namespace fbn
+
+extern "C" int fbn_bce_loss(const float* prob, const float* labels, int64_t batch, float loss_scale, float* loss_out, float* dprob_out,
+                            fbn_stream_t stream) {
+  FBN_REQUIRE(prob && labels && batch >= 1, FBN_ERR_ARG, "fbn_bce_loss: bad arguments");
+  bce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(prob, labels, batch, loss_scale, loss_out, dprob_out);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+extern "C" int fbn_gemm(const float* A, const float* Bm, const float* bias, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                        int64_t ldb, int64_t ldc, int a_t, int b_t, int precision, void* scratch, size_t scratch_bytes,
+                        fbn_stream_t stream) {
+  FBN_REQUIRE(A && Bm && C, FBN_ERR_ARG, "fbn_gemm: null pointer");
+  FBN_REQUIRE(aligned16(A) && aligned16(Bm) && aligned16(C) && aligned16(bias), FBN_ERR_ALIGN, "fbn_gemm: unaligned pointer");
+  GemmArgs g;
+  g.A = A; g.B = Bm; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.a_t = a_t; g.b_t = b_t;
+  return gemm(g, precision, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" const char* fbn_last_error(void) { return g_err; }
+extern "C" uint64_t fbn_launch_count(void) { return g_launches; }
+extern "C" const char* fbn_version(void) { return "fibinet_b200 0.1 (sm_100a)"; }
+
+extern "C" int fbn_check_device(int dev) {
+  int major = 0;
+  FBN_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  FBN_REQUIRE(major == 10, FBN_ERR_ARCH, "device %d has compute capability %d.x; this library is sm_100a only", dev, major);
+  return FBN_OK;
+}

@@ -1,0 +1,34 @@
+// Argument blocks of the fused embedding kernels (embed.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fbn {
+
+struct EmbedFwdArgs {
+  const float* item_emb; const float* cate_emb;
+  const float* mm_w; const float* mm_b; const float* ln_g; const float* ln_b;
+  const float* se_w1; const float* se_b1; const float* se_w2; const float* se_b2;
+  const void* item_id; const void* likes; const void* views; const void* seq;
+  const float* item_mm; const float* mm_table;
+  int idx_dtype, seq_dtype;
+  long long B; int L; long long item_rows; int cate_rows;
+  int save;            // write the tensors backward needs
+  int32_t* ids; int32_t* seq32;
+  float* X5; float* sgate; float* xhat; float* xmm; float* rstd; float* cnt; float* C;
+};
+
+struct EmbedBwdArgs {
+  const float* dV;      // (B,5,128) gradient w.r.t. SENET output fields 1..5
+  const float* X5; const float* sgate; const float* xhat; const float* rstd; const float* cnt;
+  const int32_t* ids;
+  const float* se_w1; const float* se_b1; const float* se_w2; const float* ln_g;
+  long long B; int cate_rows;
+  float* dXitem; float* dXhist; float* dln; float* dy; float* sestat;
+  float* cate_partial;  // (gridDim.x, cate_rows, 128)
+};
+
+int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st);
+int launch_embed_senet_bwd(const EmbedBwdArgs& a, int blocks, cudaStream_t st);
+
+}  // namespace fbn

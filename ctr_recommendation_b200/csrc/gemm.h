@@ -1,0 +1,35 @@
+// Internal GEMM descriptor shared by the SIMT (fp32) and tcgen05 (tf32x3 / bf16) back ends.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fbn {
+
+// C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N])
+//   a_t == 0: A stored (M,K) row-major, lda ; a_t != 0: A stored (K,M) row-major, lda
+//   b_t == 0: B stored (K,N) row-major, ldb ; b_t != 0: B stored (N,K) row-major, ldb
+// blockIdx.z enumerates batch x splits: batch index advances A/B/C by stride{A,B,C}; split s covers
+// a contiguous range of K tiles and writes to C + s*strideSplit (reduce afterwards).
+struct GemmArgs {
+  const float* A = nullptr;
+  const float* B = nullptr;
+  const float* bias = nullptr;
+  float* C = nullptr;
+  long long M = 0, N = 0, K = 0;
+  long long lda = 0, ldb = 0, ldc = 0;
+  int a_t = 0, b_t = 0;
+  int batch = 1, splits = 1;
+  long long strideA = 0, strideB = 0, strideC = 0, strideSplit = 0;
+  unsigned long long kmask = ~0ull;  // bit i: 128-wide K block i is non-zero
+  unsigned long long nmask = ~0ull;  // bit i: 128-wide N block i is needed
+  int accumulate = 0;
+};
+
+int gemm_simt(const GemmArgs& g, cudaStream_t st);
+// tcgen05 back end; returns FBN_ERR_SHAPE if the shape/layout is not covered (caller falls back is NOT
+// allowed silently: the dispatcher reports the error).
+int gemm_tc(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
+bool gemm_tc_supported(const GemmArgs& g, int precision);
+int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+}  // namespace fbn

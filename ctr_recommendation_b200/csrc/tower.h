@@ -1,0 +1,67 @@
+// Internal launchers (see tower.cu / embed.cu / embbwd.cu / optim.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fbn {
+
+struct DropArgs {
+  float p = 0.f;                 // 0 -> no dropout
+  const uint8_t* mask = nullptr; // optional explicit keep-mask (B,N) uint8
+  uint64_t seed = 0, offset = 0, stream = 0;
+};
+
+int col_chunks(long long B, int N);
+int colsum(const float* X, long long B, int N, float* partial, float* out, cudaStream_t st);
+int colprod2(const float* X, const float* Y, long long B, int N, float* partial, float* out_xy, float* out_x, cudaStream_t st);
+int bn_train_stats(const float* H, long long B, int N, float* partial, float* mean, float* rstd, float* run_mean, float* run_var,
+                   cudaStream_t st);
+int bn_eval_stats(const float* run_mean, const float* run_var, int N, float* mean, float* rstd, cudaStream_t st);
+int bn_act(const float* H, const float* mean, const float* rstd, const float* g, const float* b, long long B, int N,
+           const DropArgs& d, float* A, cudaStream_t st);
+int head_fwd(const float* H, const float* mean, const float* rstd, const float* g, const float* b, const float* w3, const float* b3,
+             long long B, const DropArgs& d, float* A, float* logit, float* prob, cudaStream_t st);
+int head_bwd_stats(const float* dprob, const float* prob, const float* A2, const float* Hd2, const float* mean, const float* rstd,
+                   const float* w3, long long B, float scale, float* partial, float* dlogit, float* dgamma, float* dbeta, float* dw3,
+                   float* db3, cudaStream_t st);
+int bn_bwd_stats(const float* dA, const float* A, const float* Hd, const float* mean, const float* rstd, long long B, int N,
+                 float scale, float* partial, float* dgamma, float* dbeta, cudaStream_t st);
+int bn_bwd_apply(const float* dA, const float* dlogit, const float* w3, const float* A, const float* Hd, const float* mean,
+                 const float* rstd, const float* g, const float* dgamma, const float* dbeta, long long B, int N, float scale,
+                 int train, float* dH, cudaStream_t st);
+int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, cudaStream_t st);
+int bilinear_pairs_bwd(int type, const float* C, const float* T, const float* dC, long long B, float* dT, float* dV, cudaStream_t st);
+int reduce_splits(const float* partial, int parts, long long M, long long N, long long part_stride, unsigned long long nmask, float* out,
+                  cudaStream_t st);
+
+// embed.cu
+int launch_reduce_partials(const float* partial, float* out, int parts, long long n, int accumulate, cudaStream_t st);
+int launch_senet_param_grads(const float* sestat, long long B, float* partial, float* dw1, float* db1, float* dw2, float* db2,
+                             cudaStream_t st);
+int embed_bwd_blocks(long long B);
+
+// embbwd.cu : deterministic sorted-segment embedding backward
+struct EmbGradArgs {
+  const int32_t* ids;      // (B,4) canonical item_id in .x
+  const int32_t* seq;      // (B,L) or nullptr
+  long long B; int L; long long rows;
+  const float* dXitem;     // (B,128)
+  const float* dXhist;     // (B,128), already divided by the history count
+  int32_t* keys_in; int32_t* keys_out; int32_t* vals_in; int32_t* vals_out;
+  int32_t* row_count;      // (rows) occurrences per table row (output)
+  int32_t* row_off;        // (rows+1) exclusive scan (output)
+  void* cub_tmp; size_t cub_bytes;
+  float* grad;             // (rows,128) table gradient rows
+  int zero_fill;           // write zeros to untouched rows (dense .grad contract)
+  float* sumsq_partial;    // per-CTA partial sums of squares
+  float* sumsq_out;        // (1)
+};
+int emb_grad_rows(const EmbGradArgs& a, cudaStream_t st);
+size_t emb_sort_temp_bytes(long long n, long long rows);
+int emb_grad_partial_count(long long rows);
+
+// optim.cu
+int sumsq(const float* x, long long n, float* partial, float* out, cudaStream_t st);
+int sumsq_partial_count(long long n);
+
+}  // namespace fbn

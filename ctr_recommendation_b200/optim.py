@@ -1,0 +1,128 @@
+"""FusedAdam: the reference's optimizer step (src/train_fibinet.py:78,119,121) on the CUDA path.
+
+torch.optim.Adam(lr, weight_decay) -- L2-coupled, NOT AdamW -- preceded by clip_grad_norm_(10.0), with
+OneCycleLR rewriting ``lr`` and ``betas[0]`` in ``param_groups`` before every step (SURVEY facts 6,7,9).
+The embedding table is updated dense-exactly: every row gets g = (segment-sum or 0)*coef + wd*p.
+
+Usage mirrors the reference loop:
+
+    optimizer = FusedAdam(model, lr=lr, weight_decay=wd)        # instead of torch.optim.Adam(model.parameters(), ...)
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, ...)   # unchanged
+    loss.backward(); clip_grad_norm_(model, 10.0); optimizer.step(); scheduler.step()
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        from .model import MM_FiBiNET
+        inner = model.module if hasattr(model, "module") else model
+        if not isinstance(inner, MM_FiBiNET):
+            raise TypeError("FusedAdam drives a ctr_recommendation_b200 MM_FiBiNET (pass the model, not parameters())")
+        params = [p for n, p in inner.named_parameters() if not n.startswith("user_emb.")]
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.model = inner
+        inner._fused_optimizer = self
+        self._step = 0
+        self._max_norm = None
+        self._clip = None
+        self._m_flat = self._v_flat = self._m_item = self._v_item = None
+
+    # ---- state -------------------------------------------------------------------------------
+    def _ensure_state(self):
+        m = self.model
+        m._ensure_flat()
+        dev = m._flat.device
+        if self._m_flat is None or self._m_flat.device != dev or self._m_flat.numel() != m._flat.numel():
+            self._m_flat = torch.zeros_like(m._flat)
+            self._v_flat = torch.zeros_like(m._flat)
+            self._m_item = torch.zeros_like(m.item_emb.weight.data)
+            self._v_item = torch.zeros_like(m.item_emb.weight.data)
+            self._clip = torch.ones(2, dtype=torch.float32, device=dev)
+
+    def moments(self):
+        """{state_dict key: (exp_avg, exp_avg_sq)} views, for parity tests and checkpoints."""
+        m = self.model
+        out = {"item_emb.weight": (self._m_item, self._v_item)}
+        names = {id(p): n for n, p in m.named_parameters()}
+        for (field, plist), (off, _) in zip(m._dense_params(), m._layout):
+            o = off
+            for p in plist:
+                n = p.numel()
+                out[names[id(p)]] = (self._m_flat[o:o + n].view(p.shape), self._v_flat[o:o + n].view(p.shape))
+                o += (n + 3) // 4 * 4
+        return out
+
+    def state_dict(self):
+        self._ensure_state()
+        return {"step": self._step, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+                "m_flat": self._m_flat, "v_flat": self._v_flat, "m_item": self._m_item, "v_item": self._v_item}
+
+    def load_state_dict(self, sd):
+        self._ensure_state()
+        self._step = int(sd["step"])
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)
+        for k in ("m_flat", "v_flat", "m_item", "v_item"):
+            getattr(self, "_" + k).copy_(sd[k])
+
+    # ---- clip + step -------------------------------------------------------------------------
+    def clip_grad_norm_(self, max_norm: float):
+        """Global L2-norm clip over all gradients (embedding rows included); the scaling itself is
+        folded into the Adam kernels.  Returns the total norm as a 0-d device tensor (no host sync)."""
+        lib = _lib.load()
+        self._ensure_state()
+        m = self.model
+        if m._grad_sumsq is None:
+            raise RuntimeError("clip_grad_norm_ called before backward()")
+        _lib.check(lib.fbn_clip_coef(_lib.ptr(m._grad_sumsq), 2, float(max_norm), _lib.ptr(self._clip), _lib.stream_ptr()),
+                   "fbn_clip_coef")
+        self._max_norm = max_norm
+        return self._clip[0]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedAdam does not support closures")
+        lib = _lib.load()
+        self._ensure_state()
+        m = self.model
+        if m._item_grad is None:
+            raise RuntimeError("FusedAdam.step() called before backward()")
+        g = self.param_groups[0]
+        self._step += 1
+        h = _lib.AdamHyper(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                           float(g["weight_decay"]), self._step)
+        clip = _lib.ptr(self._clip) if self._max_norm is not None else None
+        st = _lib.stream_ptr()
+        w = m.item_emb.weight.data
+        _lib.check(lib.fbn_adam_table(_lib.ptr(w), _lib.ptr(self._m_item), _lib.ptr(self._v_item), _lib.ptr(m._item_grad),
+                                      None if m._dense_table_grad else _lib.ptr(m._row_touched), w.shape[0], clip, C.byref(h), None, st), "fbn_adam_table")
+        _lib.check(lib.fbn_adam_dense(_lib.ptr(m._flat), _lib.ptr(self._m_flat), _lib.ptr(self._v_flat), _lib.ptr(m._gflat),
+                                      m._flat.numel(), clip, C.byref(h), None, st), "fbn_adam_dense")
+        self._max_norm = None
+        return None
+
+    def zero_grad(self, set_to_none: bool = True):
+        # gradients are overwritten (not accumulated) by every backward in fused mode
+        for p in self.param_groups[0]["params"]:
+            p.grad = None
+
+
+def clip_grad_norm_(model_or_params, max_norm: float):
+    """Drop-in for torch.nn.utils.clip_grad_norm_ in the training script: with a FusedAdam-driven
+    model the clip is recorded on the device and applied inside the fused Adam kernels; anything
+    else is forwarded to torch."""
+    from .model import MM_FiBiNET
+    inner = getattr(model_or_params, "module", model_or_params)
+    if isinstance(inner, MM_FiBiNET) and inner._fused_optimizer is not None:
+        return inner._fused_optimizer.clip_grad_norm_(max_norm)
+    params = inner.parameters() if isinstance(inner, torch.nn.Module) else model_or_params
+    return torch.nn.utils.clip_grad_norm_(params, max_norm=max_norm)

@@ -1,0 +1,227 @@
+/*
+ * fibinet_b200.h -- C ABI of libfibinet_b200.so
+ *
+ * Hand-written sm_100a CUDA implementation of the FiBiNET training / inference hot path of
+ * YOUNESELBOUKNIFY/Ctr_recommendation (reference file: src/model_fibinet.py and the step body of
+ * src/train_fibinet.py:113-122).  The reference has no FFI of its own (it is pure PyTorch); these
+ * entry points sit *beneath* its Python module contract (build_model / forward / state_dict) and are
+ * what a ctypes binding in the reference's model file would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the library never allocates, frees or
+ *     retains memory, never synchronises, and launches only on the given stream (CUDA-graph safe);
+ *   - all floating point tensors are fp32, row-major, 16-byte aligned;
+ *   - return value: 0 on success, negative FBN_ERR_* otherwise; fbn_last_error() gives the text;
+ *   - no CPU / torch fallback exists: on a non-sm_100 device FBN_ERR_ARCH is returned.
+ */
+#ifndef FIBINET_B200_H_
+#define FIBINET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fbn_stream_t; /* cudaStream_t */
+
+enum {
+  FBN_OK = 0,
+  FBN_ERR_ARCH = -1,   /* device is not compute capability 10.x */
+  FBN_ERR_SHAPE = -2,  /* unsupported sizes */
+  FBN_ERR_ALIGN = -3,  /* pointer not 16-byte aligned */
+  FBN_ERR_DTYPE = -4,  /* unknown index dtype */
+  FBN_ERR_CUDA = -5,   /* a CUDA runtime call failed */
+  FBN_ERR_ARG = -6     /* null pointer / inconsistent arguments */
+};
+
+/* dtype of the scalar index columns as the reference loader delivers them (src/dataloader.py:21-48
+ * yields float64 for train/valid, int64 for test; src/model_fibinet.py:140-143 casts with .long()). */
+enum { FBN_IDX_I32 = 0, FBN_IDX_I64 = 1, FBN_IDX_F64 = 2, FBN_IDX_F32 = 3 };
+
+/* arithmetic mode of the dense contractions (bilinear + DNN tower) */
+enum {
+  FBN_PREC_FP32 = 0,   /* fp32 FMA (SIMT) -- exact-order reference mode */
+  FBN_PREC_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass split operands, fp32 accumulate in TMEM */
+  FBN_PREC_BF16 = 2    /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM */
+};
+
+enum { FBN_BILINEAR_ALL = 0, FBN_BILINEAR_EACH = 1, FBN_BILINEAR_INTERACTION = 2 };
+
+/* Fixed architecture of MM_FiBiNET (src/model_fibinet.py:92-136). */
+#define FBN_D 128          /* embedding_dim == mm_input_dim */
+#define FBN_F 6            /* fields [User, Like, View, ID, Image, Hist] (:112,179-182) */
+#define FBN_PAIRS 15
+#define FBN_K1 2688        /* (F + PAIRS) * D, MLP input (:122-123) */
+#define FBN_H1 512
+#define FBN_H2 256
+#define FBN_SE_R 3         /* max(1, F // 2) (:13,114) */
+
+/* Parameters of the model, in the reference's state_dict naming. */
+typedef struct {
+  float* item_emb;   int64_t item_rows;   /* item_emb.weight (91718,128), row 0 = padding */
+  float* cate_emb;   int64_t cate_rows;   /* cate_emb.weight (11,128) */
+  float* mm_w;       /* mm_proj.0.weight (128,128)  [out,in] */
+  float* mm_b;       /* mm_proj.0.bias   (128) */
+  float* ln_g;       /* mm_proj.1.weight (128) */
+  float* ln_b;       /* mm_proj.1.bias   (128) */
+  float* se_w1;      /* senet.excitation.0.weight (3,6) */
+  float* se_b1;      /* senet.excitation.0.bias (3) */
+  float* se_w2;      /* senet.excitation.2.weight (6,3) */
+  float* se_b2;      /* senet.excitation.2.bias (6) */
+  float* bil_w;      /* bilinear.W (128,128); for EACH: 5 matrices contiguous; INTERACTION: 15 */
+  float* w1;         /* mlp.0.weight (512,2688) */
+  float* b1;         /* mlp.0.bias (512) */
+  float* bn1_g;      /* mlp.1.weight */
+  float* bn1_b;      /* mlp.1.bias */
+  float* bn1_mean;   /* mlp.1.running_mean */
+  float* bn1_var;    /* mlp.1.running_var */
+  float* w2;         /* mlp.4.weight (256,512) */
+  float* b2;         /* mlp.4.bias */
+  float* bn2_g;      /* mlp.5.weight */
+  float* bn2_b;      /* mlp.5.bias */
+  float* bn2_mean;   /* mlp.5.running_mean */
+  float* bn2_var;    /* mlp.5.running_var */
+  float* w3;         /* mlp.8.weight (1,256) */
+  float* b3;         /* mlp.8.bias (1) */
+  int32_t bilinear_type; /* FBN_BILINEAR_* */
+  int32_t precision;     /* FBN_PREC_* */
+} fbn_params_t;
+
+/* Gradients of the dense parameters, same naming (item_emb's gradient is handled separately). */
+typedef struct {
+  float* cate_emb; float* mm_w; float* mm_b; float* ln_g; float* ln_b;
+  float* se_w1; float* se_b1; float* se_w2; float* se_b2; float* bil_w;
+  float* w1; float* b1; float* bn1_g; float* bn1_b;
+  float* w2; float* b2; float* bn2_g; float* bn2_b; float* w3; float* b3;
+} fbn_grads_t;
+
+/* One collated batch (forward(batch_dict), src/model_fibinet.py:138-146). */
+typedef struct {
+  int64_t batch;            /* B */
+  int64_t seq_len;          /* L (<= 64); 0 or item_seq == NULL -> history field is zero (:175-176) */
+  const void* item_id;      /* (B,) idx_dtype */
+  const void* likes_level;  /* (B,) idx_dtype */
+  const void* views_level;  /* (B,) idx_dtype */
+  const void* item_seq;     /* (B,L) seq_dtype or NULL */
+  const float* item_mm;     /* (B,128) fp32 item_emb_d128, or NULL when mm_table is given */
+  const float* mm_table;    /* optional frozen (item_rows,128) table gathered by item_id */
+  int32_t idx_dtype;        /* FBN_IDX_* of item_id / likes_level / views_level */
+  int32_t seq_dtype;        /* FBN_IDX_I32 or FBN_IDX_I64 */
+} fbn_batch_t;
+
+/* Bytes of scratch the forward/backward pair needs for a batch of B rows, history length L and an
+ * item table of item_rows rows.  The block must be zero-initialised once by the caller. */
+size_t fbn_workspace_bytes(int64_t batch, int64_t seq_len, int64_t item_rows);
+
+/* Byte offset of a named activation inside the workspace (for tests / debugging):
+ * "X5" (B,5,128) fields 1..5 before SENET, "sgate" (B,8), "C" (B,2688) MLP input, "H1","A1" (B,512),
+ * "H2","A2" (B,256), "prob","logit" (B), "ids" (B,4) int32 {item_id,likes,views,n_valid}, "seq" (B,L)
+ * int32, "dV" (B,5,128), "dC" (B,2688) ...  Returns (size_t)-1 for an unknown name. */
+size_t fbn_workspace_offset(int64_t batch, int64_t seq_len, int64_t item_rows, const char* name);
+
+/* MM_FiBiNET.forward (src/model_fibinet.py:138-199).
+ * train != 0: BatchNorm uses batch statistics and updates running_mean/var (momentum 0.1, unbiased
+ * var), dropout p = dropout_p with either the given keep-masks (uint8 (B,512) / (B,256), test hook)
+ * or an in-kernel Philox stream keyed by (seed, offset).  prob_out: (B,) fp32 (may be NULL). */
+int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train,
+                float dropout_p, const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed,
+                uint64_t offset, float* prob_out, fbn_stream_t stream);
+
+/* The first stage of fbn_forward alone (src/model_fibinet.py:140-185): multi-field gather, history mean
+ * pooling, item_emb_d128 projection + LayerNorm + ReLU, field stack and SENET; writes the re-weighted
+ * fields into the "C" workspace tensor (columns 128..767) and, if save != 0, the tensors backward needs. */
+int fbn_embed_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int save,
+                      fbn_stream_t stream);
+
+/* Backward of the forward above given dL/dprob (B,) (what autograd hands over after
+ * torch.nn.BCELoss, src/train_fibinet.py:115-116).  Dense-parameter gradients are WRITTEN to g.
+ * The item_emb gradient is produced as a dense (item_rows,128) table in item_grad:
+ *   zero_fill != 0 : every row written (untouched rows = 0) -- the nn.Embedding(sparse=False) contract;
+ *   zero_fill == 0 : only touched rows written; row_touched (item_rows,) int32 (optional) receives the
+ *                    occurrence count per row (consumed by fbn_adam_table).
+ * grad_sumsq (2,) receives sum(g^2) of [dense grads (if dense_grad_flat != NULL: the n floats at that
+ * address, normally the flat buffer all pointers of g point into), item_emb grad] for the global clip. */
+int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train,
+                 float dropout_p, const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat,
+                 int64_t dense_grad_n, float* item_grad, int32_t* row_touched, int zero_fill,
+                 float* grad_sumsq, fbn_stream_t stream);
+
+/* Fused BCELoss(mean) forward + loss_scale * d(loss)/d(prob) (torch semantics: log clamped at -100,
+ * backward divides by max(p(1-p),1e-12)); loss_out (1,) / dprob_out (B,) may be NULL. */
+int fbn_bce_loss(const float* prob, const float* labels, int64_t batch, float loss_scale, float* loss_out,
+                 float* dprob_out, fbn_stream_t stream);
+
+/* clip_grad_norm_ coefficient (src/train_fibinet.py:119): coef = min(1, max_norm/(sqrt(sum)+1e-6)),
+ * sum = sumsq[0] + ... + sumsq[n-1].  out (2,) = {total_norm, coef}. */
+int fbn_clip_coef(const float* sumsq, int n, float max_norm, float* out, fbn_stream_t stream);
+
+/* Hyper-parameters of torch.optim.Adam as the reference builds it (src/train_fibinet.py:78):
+ * L2 weight decay folded into the gradient, bias corrections from the current beta1 (OneCycleLR
+ * cycles it, :84-92).  step is the 1-based step count.  Every Adam entry point takes either this
+ * struct (host values) or hyper_dev, a device array {lr, beta1, beta2, eps, wd, lr/(1-beta1^t),
+ * sqrt(1-beta2^t), t} (CUDA-graph replay; filled by fbn_onecycle_hyper or by the host). */
+typedef struct { float lr, beta1, beta2, eps, weight_decay; int32_t step; } fbn_adam_t;
+
+/* Dense-exact Adam over the whole embedding table, consuming the gradient rows produced by
+ * fbn_backward: g = (touched ? grad[row] : 0) * coef + wd*p, then the Adam update, for EVERY row
+ * (SURVEY fact 6).  coef is read from device memory clip[1] (clip == NULL -> 1).
+ * row_touched == NULL -> grad is read for every row. */
+int fbn_adam_table(float* p, float* m, float* v, const float* grad, const int32_t* row_touched,
+                   int64_t rows, const float* clip, const fbn_adam_t* h, const float* hyper_dev,
+                   fbn_stream_t stream);
+
+/* Flat dense Adam over n contiguous fp32 elements (all dense parameters live in one buffer; n % 4 == 0). */
+int fbn_adam_dense(float* p, float* m, float* v, const float* grad, int64_t n, const float* clip,
+                   const fbn_adam_t* h, const float* hyper_dev, fbn_stream_t stream);
+
+/* OneCycleLR(cos, two phases, cycle_momentum=True) as built at src/train_fibinet.py:84-92, evaluated on
+ * the device: reads *step_counter (optimizer steps taken so far), writes hyper_dev[0..7] for the next
+ * step and increments the counter. */
+int fbn_onecycle_hyper(int32_t* step_counter, int total_steps, float max_lr, float pct_start,
+                       float div_factor, float final_div_factor, float base_momentum, float max_momentum,
+                       float beta2, float eps, float weight_decay, float* hyper_dev, fbn_stream_t stream);
+
+/* sum of squares of n floats, deterministic; partial needs fbn_sumsq_partial_floats(n) floats;
+ * out (1,) overwritten. */
+int fbn_sumsq(const float* x, int64_t n, float* partial, float* out, fbn_stream_t stream);
+size_t fbn_sumsq_partial_floats(int64_t n);
+
+/* Stand-alone SENetLayer (src/model_fibinet.py:5-35): x (B,F,D) -> y (B,F,D), gate (B,F).
+ * F <= 32, hidden <= 32, D % 4 == 0. */
+int fbn_senet_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                  int64_t batch, int fields, int dim, int hidden, float* y, float* gate, fbn_stream_t stream);
+/* scratch: fbn_senet_scratch_bytes(batch, fields, hidden) bytes */
+int fbn_senet_bwd(const float* x, const float* gate, const float* w1, const float* b1, const float* w2,
+                  const float* dy, int64_t batch, int fields, int dim, int hidden, float* dx, float* dw1,
+                  float* db1, float* dw2, float* db2, void* scratch, size_t scratch_bytes, fbn_stream_t stream);
+size_t fbn_senet_scratch_bytes(int64_t batch, int fields, int hidden);
+
+/* Stand-alone BilinearInteraction (src/model_fibinet.py:37-89): v (B,F,D) -> p (B,F(F-1)/2,D).
+ * w: ALL (D,D); EACH (F-1,D,D); INTERACTION (F(F-1)/2,D,D).  D % 4 == 0. */
+int fbn_bilinear_fwd(const float* v, const float* w, int type, int64_t batch, int fields, int dim,
+                     float* p, void* scratch, size_t scratch_bytes, int precision, fbn_stream_t stream);
+int fbn_bilinear_bwd(const float* v, const float* w, const float* dp, int type, int64_t batch, int fields,
+                     int dim, float* dv, float* dw, void* scratch, size_t scratch_bytes, int precision,
+                     fbn_stream_t stream);
+size_t fbn_bilinear_scratch_bytes(int64_t batch, int fields, int dim, int type);
+
+/* C[M,N] = op(A) * op(B) (+ bias[N]) in the given precision -- exposed for tests and benches.
+ * a_t == 0: A is (M,K) row-major lda; a_t != 0: A is stored (K,M) row-major lda.
+ * b_t == 0: B is (K,N) row-major ldb; b_t != 0: B is stored (N,K) row-major ldb (nn.Linear weight). */
+int fbn_gemm(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+             int64_t lda, int64_t ldb, int64_t ldc, int a_t, int b_t, int precision, void* scratch,
+             size_t scratch_bytes, fbn_stream_t stream);
+
+/* number of kernels this library has launched so far in this process (host-side counter) */
+uint64_t fbn_launch_count(void);
+const char* fbn_last_error(void);
+const char* fbn_version(void);
+/* 0 if device `dev` can run the library (compute capability 10.x), FBN_ERR_ARCH otherwise. */
+int fbn_check_device(int dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIBINET_B200_H_ */
