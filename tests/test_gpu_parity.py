@@ -116,8 +116,10 @@ def _run_steps(gpu, golden, tag, id_dist, fused):
         total = clip_grad_norm_(model, 10.0) if fused else torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
         opt.step()
         sched.step()
-        assert rel_err(y.detach().cpu().numpy(), golden[f"{tag}/step{s}/prob"]) <= TOL * (1 + 4 * s)
-        assert abs(loss.item() - float(golden[f"{tag}/step{s}/loss"])) <= 2e-5
+        # step 0 starts from identical weights: strict.  Later steps inherit the chaotic O(lr) differences on a few
+        # elements (see helpers.check_summary): a ReLU flip for one sample moves its probability by ~1e-4.
+        assert rel_err(y.detach().cpu().numpy(), golden[f"{tag}/step{s}/prob"]) <= (TOL if s == 0 else 1e-3)
+        assert abs(loss.item() - float(golden[f"{tag}/step{s}/loss"])) <= (2e-5 if s == 0 else 1e-4)
         assert abs(float(total) - float(golden[f"{tag}/step{s}/total_norm"])) <= 1e-4 * float(total)
     sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     init = synth.make_weights(seed=7)
@@ -126,21 +128,65 @@ def _run_steps(gpu, golden, tag, id_dist, fused):
         if k in NOISE_DRIVEN:
             assert np.abs(v - init[k]).max() <= steps * 1e-2
             continue
-        check_summary(golden, f"{tag}/final", k, v, DRIFT_TOL, atol=2e-4 if k.endswith("running_mean") else 0.0)
+        check_summary(golden, f"{tag}/final", k, v, DRIFT_TOL, atol=2e-4 if k.endswith("running_mean") else 0.0, robust=True)
     assert np.array_equal(sd["user_emb.weight"], init["user_emb.weight"])   # never touched
     assert np.all(sd["item_emb.weight"][0] == 0)
     if fused:
         for k, (m, v) in opt.moments().items():
             if k in NOISE_DRIVEN:
                 continue
-            check_summary(golden, f"{tag}/final_m", k, m.cpu().numpy(), 4 * DRIFT_TOL, atol=1e-9)
-            check_summary(golden, f"{tag}/final_v", k, v.cpu().numpy(), 4 * DRIFT_TOL, atol=1e-12)
+            check_summary(golden, f"{tag}/final_m", k, m.cpu().numpy(), 4 * DRIFT_TOL, atol=1e-9, robust=True)
+            check_summary(golden, f"{tag}/final_v", k, v.cpu().numpy(), 4 * DRIFT_TOL, atol=1e-12, robust=True)
     model.eval()
     model._test_masks = None
     batch, _ = synth.make_batch(seed=900, batch=300, id_dist=id_dist, index_dtype=np.int64)
     with torch.no_grad():
         prob = model(gpu["to_dev"](batch)).cpu().numpy()
-    assert rel_err(prob, golden[f"{tag}/eval_prob"]) <= 5e-5
+    assert rel_err(prob, golden[f"{tag}/eval_prob"]) <= 1e-3
+
+
+def test_fused_adam_step_exact_given_same_gradients(gpu):
+    """Optimizer parity isolated from gradient rounding: feed the GPU's OWN gradients to the oracle's Adam
+    (torch single-tensor math incl. L2 decay, cycled beta1, clip coefficient) from the same starting weights;
+    FusedAdam must then agree element-wise to fp32 rounding -- including untouched table rows."""
+    from ctr_recommendation_b200 import FusedAdam, clip_grad_norm_
+    B, total = 300, 12
+    model = gpu["make_model"](train=True)
+    opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=total, pct_start=0.3, div_factor=25.0,
+                                                final_div_factor=1000.0)
+    osched = orc.OneCycle(1e-2, total)
+    oopt = orc.Adam(lr=1e-3, weight_decay=1e-5)
+    P = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    for s in range(5):
+        lr, b1 = osched.at(s)
+        assert abs(opt.param_groups[0]["lr"] - lr) <= 1e-12 and abs(opt.param_groups[0]["betas"][0] - b1) <= 1e-12
+        oopt.lr, oopt.betas = lr, (b1, 0.999)
+        batch, labels = synth.make_batch(seed=300 + s, batch=B, id_dist="zipf", index_dtype=np.float64)
+        y = model(gpu["to_dev"](batch))
+        (torch.nn.BCELoss()(y, torch.from_numpy(labels).cuda()) * (40.0 if s == 3 else 1.0)).backward()   # step 3 really clips
+        G = gpu["named_grads"](model)
+        G["item_emb.weight"] = (model._item_grad * (model._row_touched > 0).unsqueeze(1)).cpu().numpy()
+        total_norm = float(clip_grad_norm_(model, 10.0))
+        opt.step()
+        sched.step()
+        ototal = orc.clip_grad_norm_(G, 10.0)
+        assert abs(total_norm - ototal) <= 1e-5 * ototal
+        if s == 3:
+            assert ototal > 10.0
+        oopt.step(P, G)
+        sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        for k in G:
+            d = np.abs(sd[k].astype(np.float64) - P[k])
+            # identical inputs: only fp32 rounding of the update itself (a few ulp of lr-sized steps)
+            assert d.max() <= 2e-3 * lr + 1e-7, f"step {s} {k}: {d.max():.3e} ({d.max() / lr:.3e} lr)"
+            assert d.mean() <= 1e-5 * lr + 1e-9, f"step {s} {k}: mean {d.mean():.3e}"
+        for k in G:                                   # continue from the GPU state so errors cannot accumulate
+            P[k] = sd[k].copy()
+        mom = opt.moments()
+        for k in G:
+            oopt.state[k]["m"] = mom[k][0].cpu().numpy().copy()
+            oopt.state[k]["v"] = mom[k][1].cpu().numpy().copy()
 
 
 @pytest.mark.parametrize("tag,id_dist", [("train_u", "uniform"), ("train_z", "zipf")])
