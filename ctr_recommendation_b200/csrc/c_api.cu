@@ -112,6 +112,13 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   w.row_cnt = (int32_t*)take((rows + 1) * 4);
   w.cub_bytes = emb_sort_temp_bytes(nocc, rows);
   w.cub_tmp = take(w.cub_bytes);
+  // operand scratch of the tcgen05 path: the largest call is the MLP-1 weight gradient (512 + 2688) x B
+  size_t gs = 0;
+  gs = std::max(gs, gemm_tc_scratch_bytes(H1, K1, Bp, FBN_PREC_TF32X3));
+  gs = std::max(gs, gemm_tc_scratch_bytes(Bp, H1, K1, FBN_PREC_TF32X3));
+  gs = std::max(gs, gemm_tc_scratch_bytes(Bp, K1, H1, FBN_PREC_TF32X3));
+  w.gemm_scratch_bytes = gs;
+  w.gemm_scratch = take(gs);
   w.total_bytes = off;
 }
 
@@ -188,11 +195,11 @@ static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStrea
   g.M = w.B; g.N = D; g.K = D; g.lda = K1; g.ldb = D; g.ldc = nT * D; g.a_t = 0; g.b_t = 0;
   if (type == FBN_BILINEAR_ALL) {           // T_t = V_{t+2} W
     g.A = w.C + 2 * D; g.strideA = D; g.B = p->bil_w; g.strideB = 0; g.C = w.T; g.strideC = D; g.batch = 4;
-    return gemm(g, p->precision, nullptr, 0, st);
+    return gemm(g, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st);
   }
   if (type == FBN_BILINEAR_EACH) {          // T_t = V_{t+1} W_{t+1}
     g.A = w.C + 1 * D; g.strideA = D; g.B = p->bil_w + 1 * D * D; g.strideB = D * D; g.C = w.T; g.strideC = D; g.batch = 4;
-    return gemm(g, p->precision, nullptr, 0, st);
+    return gemm(g, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st);
   }
   int q0 = 0;                               // T_q = V_i W_(i,j), grouped by i
   for (int i = 1; i < NF - 1; ++i) {
@@ -200,7 +207,7 @@ static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStrea
     const int pidx = i * (2 * NF - i - 1) / 2;  // pair index of (i, i+1) in the full enumeration
     g.A = w.C + i * D; g.strideA = 0; g.B = p->bil_w + (long long)pidx * D * D; g.strideB = D * D;
     g.C = w.T + q0 * D; g.strideC = D; g.batch = nj;
-    RC(gemm(g, p->precision, nullptr, 0, st));
+    RC(gemm(g, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
     q0 += nj;
   }
   return FBN_OK;
@@ -247,7 +254,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   GemmArgs g1;
   g1.A = w.C; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = K1; g1.lda = K1; g1.ldb = K1; g1.ldc = H1;
   g1.b_t = 1; g1.kmask = active_mask();
-  RC(gemm(g1, p->precision, nullptr, 0, st));
+  RC(gemm(g1, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
   DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1;
@@ -256,7 +263,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   GemmArgs g2;
   g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2;
   g2.b_t = 1;
-  RC(gemm(g2, p->precision, nullptr, 0, st));
+  RC(gemm(g2, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
   if (train) RC(bn_train_stats(w.Hd2, B, H2, w.partial, mean2, rstd2, p->bn2_mean, p->bn2_var, st));
   else RC(bn_eval_stats(p->bn2_mean, p->bn2_var, H2, mean2, rstd2, st));
   DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2;
@@ -274,7 +281,7 @@ static int wgrad(const float* dOut, long long ldo, const float* In, long long ld
   g.nmask = nmask;
   FBN_REQUIRE((size_t)g.splits * M * N <= w.partial_floats, FBN_ERR_ARG, "internal: split-K scratch too small");
   g.C = w.partial; g.strideSplit = M * N;
-  RC(gemm(g, precision, nullptr, 0, st));
+  RC(gemm(g, precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
   return reduce_splits(w.partial, g.splits, M, N, M * N, nmask, out, st);
 }
 
@@ -302,7 +309,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   {
     GemmArgs d;  // dA1 = dH2 * w2
     d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
-    RC(gemm(d, prec, nullptr, 0, st));
+    RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
   }
   // ---- layer 1 ----
   RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
@@ -312,7 +319,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   {
     GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
     d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
-    RC(gemm(d, prec, nullptr, 0, st));
+    RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
   }
   // ---- bilinear ----
   const int type = p->bilinear_type;
@@ -323,17 +330,17 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
     if (type == FBN_BILINEAR_ALL) {
       d.A = w.dT; d.strideA = D; d.B = p->bil_w; d.strideB = 0; d.C = w.dV + 1 * D; d.strideC = D; d.batch = 4;
-      RC(gemm(d, prec, nullptr, 0, st));
+      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
     } else if (type == FBN_BILINEAR_EACH) {
       d.A = w.dT; d.strideA = D; d.B = p->bil_w + D * D; d.strideB = D * D; d.C = w.dV; d.strideC = D; d.batch = 4;
-      RC(gemm(d, prec, nullptr, 0, st));
+      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
     } else {
       int q = 0;
       for (int i = 1; i < NF - 1; ++i)
         for (int j = i + 1; j < NF; ++j, ++q) {
           const int pidx = i * (2 * NF - i - 1) / 2 + (j - i - 1);
           d.A = w.dT + q * D; d.B = p->bil_w + (long long)pidx * D * D; d.C = w.dV + (i - 1) * D; d.batch = 1;
-          RC(gemm(d, prec, nullptr, 0, st));
+          RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
         }
     }
   }
@@ -346,11 +353,11 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     FBN_REQUIRE((size_t)nT * S * D * D <= w.partial_floats, FBN_ERR_ARG, "internal: bilinear scratch too small");
     if (type == FBN_BILINEAR_ALL) {
       d.A = w.C + 2 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
-      RC(gemm(d, prec, nullptr, 0, st));
+      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
       RC(reduce_splits(w.partial, 4 * S, D, D, (long long)D * D, ~0ull, g->bil_w, st));
     } else if (type == FBN_BILINEAR_EACH) {
       d.A = w.C + 1 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
-      RC(gemm(d, prec, nullptr, 0, st));
+      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
       FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * D * D, st));  // W_0 multiplies the zero field
       for (int t = 0; t < 4; ++t)
         RC(reduce_splits(w.partial + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull, g->bil_w + (long long)(t + 1) * D * D, st));
@@ -360,7 +367,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
       for (int i = 1; i < NF - 1; ++i) {
         const int nj = NF - 1 - i;
         d.A = w.C + i * D; d.strideA = 0; d.B = w.dT + q * D; d.strideB = D; d.batch = nj; d.C = w.partial + (long long)q * S * D * D;
-        RC(gemm(d, prec, nullptr, 0, st));
+        RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
         q += nj;
       }
       for (int t = 0; t < 10; ++t)
@@ -435,6 +442,10 @@ extern "C" int fbn_gemm(const float* A, const float* Bm, const float* bias, floa
   GemmArgs g;
   g.A = A; g.B = Bm; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.a_t = a_t; g.b_t = b_t;
   return gemm(g, precision, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int precision) {
+  return precision == FBN_PREC_FP32 ? 0 : gemm_tc_scratch_bytes(M, N, K, precision);
 }
 
 extern "C" const char* fbn_last_error(void) { return g_err; }

@@ -164,6 +164,8 @@ struct Workspace {
   int32_t* row_cnt;  // (item_rows + 1)
   void* cub_tmp;
   size_t cub_bytes;
+  void* gemm_scratch;   // packed tcgen05 operands (hi|lo or bf16)
+  size_t gemm_scratch_bytes;
   size_t total_bytes;
 };
 

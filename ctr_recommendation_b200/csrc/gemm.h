@@ -30,6 +30,7 @@ int gemm_simt(const GemmArgs& g, cudaStream_t st);
 // allowed silently: the dispatcher reports the error).
 int gemm_tc(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& g, int precision);
+size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precision);
 int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 }  // namespace fbn

@@ -213,6 +213,8 @@ size_t fbn_bilinear_scratch_bytes(int64_t batch, int fields, int dim, int type);
 int fbn_gemm(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int a_t, int b_t, int precision, void* scratch,
              size_t scratch_bytes, fbn_stream_t stream);
+/* scratch the tcgen05 precisions need for their packed operands (0 for FBN_PREC_FP32) */
+size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int precision);
 
 /* number of kernels this library has launched so far in this process (host-side counter) */
 uint64_t fbn_launch_count(void);
