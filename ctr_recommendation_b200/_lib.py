@@ -48,7 +48,7 @@ class AdamHyper(C.Structure):
 _SIGNATURES = {
     "fbn_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "fbn_workspace_offset": (_sz, [_i64, _i64, _i64, C.c_char_p]),
-    "fbn_forward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, _vp, _u64, _u64, _vp, _vp]),
+    "fbn_forward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "fbn_embed_forward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _vp]),
     "fbn_backward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, C.POINTER(Grads), _vp, _i64,
                                _vp, _vp, C.c_int, _vp, _vp]),

@@ -236,7 +236,8 @@ extern "C" int fbn_embed_forward(const fbn_params_t* p, const fbn_batch_t* b, vo
 }
 
 extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
-                           const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset, float* prob_out,
+                           const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset,
+                           const int32_t* step_counter_dev, float* prob_out,
                            fbn_stream_t stream) {
   RC(check_common(p, b, ws, ws_bytes));
   FBN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FBN_ERR_ARG, "dropout_p must be in [0,1)");
@@ -257,7 +258,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   RC(gemm(g1, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
-  DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1;
+  DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
   RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, st));
 
   GemmArgs g2;
@@ -266,7 +267,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   RC(gemm(g2, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
   if (train) RC(bn_train_stats(w.Hd2, B, H2, w.partial, mean2, rstd2, p->bn2_mean, p->bn2_var, st));
   else RC(bn_eval_stats(p->bn2_mean, p->bn2_var, H2, mean2, rstd2, st));
-  DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2;
+  DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2; d2.step_dev = step_counter_dev;
   RC(head_fwd(w.Hd2, mean2, rstd2, p->bn2_g, p->bn2_b, p->w3, p->b3, B, d2, w.A2, w.logit, w.prob, st));
   if (prob_out) FBN_CHECK_CUDA(cudaMemcpyAsync(prob_out, w.prob, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
   return FBN_OK;

@@ -395,25 +395,30 @@ __global__ void senet_param_partial_kernel(const float* __restrict__ sestat, lon
   partial[(long long)blockIdx.x * 48 + t] = acc;
 }
 
-__global__ void senet_param_final_kernel(const float* __restrict__ partial, int parts, float* dw1, float* db1, float* dw2, float* db2) {
-  const int t = threadIdx.x;
+__global__ void __launch_bounds__(256) senet_param_final_kernel(const float* __restrict__ partial, int parts, float* dw1, float* db1,
+                                                                float* dw2, float* db2) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);   // warp per output, lanes over the partials (fixed xor tree)
   if (t >= 45) return;
-  float acc = 0.f;
-  for (int p = 0; p < parts; ++p) acc += partial[(long long)p * 48 + t];
-  if (t < 18) dw1[t] = acc;
-  else if (t < 21) db1[t - 18] = acc;
-  else if (t < 39) dw2[t - 21] = acc;
-  else db2[t - 39] = acc;
+  double acc = 0.0;
+  for (int p = lane; p < parts; p += 32) acc += (double)partial[(long long)p * 48 + t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane != 0) return;
+  if (t < 18) dw1[t] = (float)acc;
+  else if (t < 21) db1[t - 18] = (float)acc;
+  else if (t < 39) dw2[t - 21] = (float)acc;
+  else db2[t - 39] = (float)acc;
 }
 
 int launch_senet_param_grads(const float* sestat, long long B, float* partial, float* dw1, float* db1, float* dw2, float* db2,
                              cudaStream_t st) {
-  int parts = (int)std::min<long long>((B + 255) / 256, 1024);
+  int parts = (int)std::min<long long>((B + 31) / 32, 1024);
   if (parts < 1) parts = 1;
   long long per = (B + parts - 1) / parts;
   senet_param_partial_kernel<<<parts, 64, 0, st>>>(sestat, B, per, partial);
   FBN_CHECK_LAUNCH();
-  senet_param_final_kernel<<<1, 64, 0, st>>>(partial, parts, dw1, db1, dw2, db2);
+  senet_param_final_kernel<<<6, 256, 0, st>>>(partial, parts, dw1, db1, dw2, db2);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }

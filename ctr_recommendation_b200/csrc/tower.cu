@@ -89,21 +89,31 @@ static int launch_colreduce(ColArgs a, int chunks, cudaStream_t st) {
   return FBN_OK;
 }
 
-// out_q[c] = scale * sum_chunks partial[chunk][q][c]   (fixed order, double accumulation)
-__global__ void colfinal_kernel(const float* __restrict__ partial, int chunks, int N, int nq, float scale, float* o0, float* o1,
-                                float* o2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// out_q[c] = scale * sum_chunks partial[chunk][q][c].  One warp per output: lanes stride over the chunks and a
+// fixed xor-tree combines them (double accumulation, run-to-run deterministic), so the latency is
+// ceil(chunks/32) dependent loads instead of `chunks`.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) colfinal_kernel(const float* __restrict__ partial, int chunks, int N, int nq, float scale,
+                                                       float* o0, float* o1, float* o2) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= N * nq) return;
   const int q = i / N, c = i % N;
   double t = 0.0;
-  for (int k = 0; k < chunks; ++k) t += (double)partial[((long long)k * nq + q) * N + c];
+  for (int k = lane; k < chunks; k += 32) t += (double)partial[((long long)k * nq + q) * N + c];
+  t = warp_sum_d(t);
   float* o = q == 0 ? o0 : (q == 1 ? o1 : o2);
-  if (o) o[c] = (float)(t * scale);
+  if (lane == 0 && o) o[c] = (float)(t * scale);
 }
 
 static int launch_colfinal(const float* partial, int chunks, int N, int nq, float scale, float* o0, float* o1, float* o2,
                            cudaStream_t st) {
-  colfinal_kernel<<<(N * nq + 255) / 256, 256, 0, st>>>(partial, chunks, N, nq, scale, o0, o1, o2);
+  colfinal_kernel<<<(N * nq + 7) / 8, 256, 0, st>>>(partial, chunks, N, nq, scale, o0, o1, o2);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -125,12 +135,15 @@ int colprod2(const float* X, const float* Y, long long B, int N, float* partial,
 }
 
 // var finalize: rstd + running statistics update (momentum 0.1, unbiased variance), nn.BatchNorm1d
-__global__ void bn_var_final_kernel(const float* __restrict__ partial, int chunks, int N, long long B, const float* mean,
-                                    float* rstd, float* run_mean, float* run_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_var_final_kernel(const float* __restrict__ partial, int chunks, int N, long long B,
+                                                           const float* mean, float* rstd, float* run_mean, float* run_var) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= N) return;
   double t = 0.0;
-  for (int k = 0; k < chunks; ++k) t += (double)partial[(long long)k * N + c];
+  for (int k = lane; k < chunks; k += 32) t += (double)partial[(long long)k * N + c];
+  t = warp_sum_d(t);
+  if (lane != 0) return;
   const float var = (float)(t / (double)B);
   rstd[c] = 1.0f / sqrtf(var + 1e-5f);
   if (run_mean) {
@@ -151,7 +164,7 @@ int bn_train_stats(const float* H, long long B, int N, float* partial, float* me
   a.v0 = mean;
   rc = launch_colreduce<OP_SQDEV, 1>(a, ch, st);
   if (rc) return rc;
-  bn_var_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, ch, N, B, mean, rstd, run_mean, run_var);
+  bn_var_final_kernel<<<(N + 7) / 8, 256, 0, st>>>(partial, ch, N, B, mean, rstd, run_mean, run_var);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -182,7 +195,8 @@ __device__ __forceinline__ float4 bn_relu_drop4(float4 h, float4 mean, float4 rs
       const uchar4 m = *reinterpret_cast<const uchar4*>(mask + elem);
       k0 = m.x ? 1.f : 0.f; k1 = m.y ? 1.f : 0.f; k2 = m.z ? 1.f : 0.f; k3 = m.w ? 1.f : 0.f;
     } else {
-      const uint4 r = philox4x32(d.seed, d.offset + (uint64_t)(elem >> 2), d.stream);
+      const uint64_t off = d.offset + (d.step_dev ? ((uint64_t)(uint32_t)__ldg(d.step_dev) << 36) : 0ull);
+      const uint4 r = philox4x32(d.seed, off + (uint64_t)(elem >> 2), d.stream);
       k0 = u01(r.x) >= d.p ? 1.f : 0.f; k1 = u01(r.y) >= d.p ? 1.f : 0.f;
       k2 = u01(r.z) >= d.p ? 1.f : 0.f; k3 = u01(r.w) >= d.p ? 1.f : 0.f;
     }

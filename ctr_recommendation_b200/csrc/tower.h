@@ -9,6 +9,7 @@ struct DropArgs {
   float p = 0.f;                 // 0 -> no dropout
   const uint8_t* mask = nullptr; // optional explicit keep-mask (B,N) uint8
   uint64_t seed = 0, offset = 0, stream = 0;
+  const int32_t* step_dev = nullptr;  // optional device step counter mixed into the offset (CUDA-graph replay)
 };
 
 int col_chunks(long long B, int N);

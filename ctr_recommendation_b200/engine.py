@@ -1,0 +1,249 @@
+"""TrainStep / Scorer: the reference loop bodies as CUDA-graph replays.
+
+``TrainStep`` is the body of the reference's training loop (src/train_fibinet.py:113-122)
+
+    zero_grad -> forward -> BCELoss -> backward -> clip_grad_norm_(10) -> Adam.step -> (scheduler.step)
+
+captured once into CUDA graphs over static device buffers: a step is then one host->device copy of the batch,
+one 32-byte copy of the optimizer hyper-parameters (so any torch LR scheduler, e.g. the reference's
+OneCycleLR which rewrites lr AND betas[0], keeps working unchanged) and a graph launch -- no per-kernel launch
+cost, no host synchronisation (the loss stays on the device until the caller reads it).
+
+With more than one rank (process per GPU) the step is split into two graphs around the NCCL all-reduce of the
+gradients:  [forward+loss+backward]  ->  all-reduce  ->  [clip+Adam].
+
+``Scorer`` is the inference loop body (src/Prediction.py:108-113): eval-mode forward as one graph replay.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from . import dist as fdist
+from .model import MM_FiBiNET, D, _IDX_DTYPES
+from .optim import FusedAdam
+
+
+class _StaticBatch:
+    """Device-resident input buffers with fixed addresses (what the captured kernels read)."""
+
+    def __init__(self, B, L, idx_dtype, seq_dtype, device, with_mm=True, with_labels=True):
+        self.B, self.L = B, L
+        z = dict(device=device)
+        self.t = {"item_id": torch.zeros(B, dtype=idx_dtype, **z), "likes_level": torch.zeros(B, dtype=idx_dtype, **z),
+                  "views_level": torch.zeros(B, dtype=idx_dtype, **z)}
+        if L > 0:
+            self.t["item_seq"] = torch.zeros(B, L, dtype=seq_dtype, **z)
+        if with_mm:
+            self.t["item_emb_d128"] = torch.zeros(B, D, dtype=torch.float32, **z)
+        self.labels = torch.zeros(B, dtype=torch.float32, **z) if with_labels else None
+
+    def load(self, batch: dict, labels=None):
+        for k, dst in self.t.items():
+            src = batch[k]
+            if src.shape != dst.shape:
+                src = src.reshape(dst.shape)
+            dst.copy_(src, non_blocking=True)     # dtype conversion (if any) happens in the copy
+        if labels is not None and self.labels is not None:
+            self.labels.copy_(labels.reshape(-1), non_blocking=True)
+
+    def nbytes(self):
+        n = sum(t.numel() * t.element_size() for t in self.t.values())
+        return n + (self.labels.numel() * 4 if self.labels is not None else 0)
+
+
+class TrainStep:
+    def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
+                 seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True):
+        if not isinstance(model, MM_FiBiNET) or not isinstance(optimizer, FusedAdam):
+            raise TypeError("TrainStep needs a ctr_recommendation_b200 MM_FiBiNET and its FusedAdam")
+        self.model, self.opt, self.max_norm = model, optimizer, max_norm
+        self.lib = _lib.load()
+        model._ensure_flat()
+        optimizer._ensure_state()
+        dev = model._flat.device
+        self.dev = dev
+        self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        if self.world > 1:
+            model._dense_table_grad = True
+        self.inp = _StaticBatch(batch_size, seq_len, idx_dtype, seq_dtype, dev, with_mm=not use_mm_table)
+        if use_mm_table and model._mm_table is None:
+            raise ValueError("use_mm_table=True needs model.attach_mm_table(...)")
+        self.B, self.L = batch_size, seq_len
+        rows = model.item_emb.weight.shape[0]
+        self.ws = model._workspace(batch_size, seq_len)
+        if model._item_grad is None or model._item_grad.device != dev:
+            model._item_grad = torch.zeros(rows, D, dtype=torch.float32, device=dev)
+            model._row_touched = torch.zeros(rows, dtype=torch.int32, device=dev)
+            model._grad_sumsq = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.prob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        self.dprob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hyper_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(model._item_grad.numel()), 16), dtype=torch.float32,
+                                         device=dev)
+        self.loss_weight = 1.0 / self.world
+        self._bs = self._batch_struct()
+        self._graphs = None
+        self._use_graph = graph
+        self._steps = 0
+        self.kernels_per_step = 0
+
+    # ------------------------------------------------------------------
+    def _batch_struct(self):
+        t = self.inp.t
+        bs = _lib.Batch()
+        bs.batch, bs.seq_len = self.B, self.L
+        bs.item_id, bs.likes_level, bs.views_level = t["item_id"].data_ptr(), t["likes_level"].data_ptr(), t["views_level"].data_ptr()
+        bs.idx_dtype = _IDX_DTYPES[t["item_id"].dtype]
+        bs.seq_dtype = _lib.IDX_I64
+        if self.L > 0:
+            bs.item_seq = t["item_seq"].data_ptr()
+            bs.seq_dtype = _IDX_DTYPES[t["item_seq"].dtype]
+        if "item_emb_d128" in t:
+            bs.item_mm = t["item_emb_d128"].data_ptr()
+        else:
+            bs.mm_table = self.model._mm_table.data_ptr()
+        return bs
+
+    def _fwd_bwd(self):
+        m, lib, st = self.model, self.lib, _lib.stream_ptr()
+        P, G = m._params_struct(), m._grads_struct()
+        ws = self.ws
+        _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
+                                   _lib.ptr(self.step_counter), _lib.ptr(self.prob), st), "fbn_forward")
+        _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
+                                    _lib.ptr(self.dprob), st), "fbn_bce_loss")
+        dense_table = m._dense_table_grad
+        _lib.check(lib.fbn_backward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, _lib.ptr(self.dprob),
+                                    C.byref(G), _lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(m._item_grad),
+                                    _lib.ptr(m._row_touched), 1 if dense_table else 0, _lib.ptr(m._grad_sumsq), st), "fbn_backward")
+
+    def _update(self):
+        m, o, lib, st = self.model, self.opt, self.lib, _lib.stream_ptr()
+        if self.world > 1:   # norms of the all-reduced gradients
+            _lib.check(lib.fbn_sumsq(_lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(self.sumsq_scratch), _lib.ptr(m._grad_sumsq), st))
+            _lib.check(lib.fbn_sumsq(_lib.ptr(m._item_grad), m._item_grad.numel(), _lib.ptr(self.sumsq_scratch),
+                                     fdist.C_ptr_offset(m._grad_sumsq, 1), st))
+        clip = None
+        if self.max_norm is not None:
+            _lib.check(lib.fbn_clip_coef(_lib.ptr(m._grad_sumsq), 2, float(self.max_norm), _lib.ptr(o._clip), st), "fbn_clip_coef")
+            clip = _lib.ptr(o._clip)
+        w = m.item_emb.weight.data
+        _lib.check(lib.fbn_adam_table(_lib.ptr(w), _lib.ptr(o._m_item), _lib.ptr(o._v_item), _lib.ptr(m._item_grad),
+                                      None if m._dense_table_grad else _lib.ptr(m._row_touched), w.shape[0], clip, None,
+                                      _lib.ptr(self.hyper_dev), st), "fbn_adam_table")
+        _lib.check(lib.fbn_adam_dense(_lib.ptr(m._flat), _lib.ptr(o._m_flat), _lib.ptr(o._v_flat), _lib.ptr(m._gflat), m._flat.numel(),
+                                      clip, None, _lib.ptr(self.hyper_dev), st), "fbn_adam_dense")
+        self.step_counter += 1
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up outside capture (lazy inits: func attributes, workspaces)
+            self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.step_counter.zero_()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = self.lib.fbn_launch_count()
+        if self.world == 1:
+            with torch.cuda.graph(g1):
+                self._fwd_bwd()
+                self._update()
+            self._graphs = (g1, None)
+        else:
+            with torch.cuda.graph(g1):
+                self._fwd_bwd()
+            with torch.cuda.graph(g2):
+                self._update()
+            self._graphs = (g1, g2)
+        self.kernels_per_step = int(self.lib.fbn_launch_count() - n0)   # library kernels inside the captured step
+
+    def _write_hyper(self):
+        g = self.opt.param_groups[0]
+        self.opt._step += 1
+        t = self.opt._step
+        lr, b1, b2 = float(g["lr"]), float(g["betas"][0]), float(g["betas"][1])
+        h = self.hyper_host
+        h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, float(g["eps"]), float(g["weight_decay"])
+        h[5] = lr / (1.0 - b1 ** t)
+        h[6] = math.sqrt(1.0 - b2 ** t)
+        h[7] = float(t)
+        self.hyper_dev.copy_(h, non_blocking=True)
+
+    # ------------------------------------------------------------------
+    def __call__(self, batch: dict, labels: torch.Tensor) -> torch.Tensor:
+        """One optimizer step on ``batch`` (host-pinned or device tensors).  Returns the mean BCE loss of this rank's
+        shard as a 1-element device tensor (read it with .item() only when you need it)."""
+        m = self.model
+        if not m.training:
+            raise RuntimeError("TrainStep needs model.train()")
+        self.inp.load(batch, labels)
+        self._write_hyper()
+        if self._use_graph and self._graphs is None:
+            self._capture()
+        if self._use_graph:
+            g1, g2 = self._graphs
+            g1.replay()
+            if g2 is not None:
+                self._allreduce()
+                g2.replay()
+        else:
+            self._fwd_bwd()
+            if self.world > 1:
+                self._allreduce()
+            self._update()
+        m.mlp[1].num_batches_tracked += 1
+        m.mlp[5].num_batches_tracked += 1
+        self._steps += 1
+        return self.loss
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        m = self.model
+        dist.all_reduce(m._gflat, op=dist.ReduceOp.SUM)
+        dist.all_reduce(m._item_grad, op=dist.ReduceOp.SUM)
+
+
+class Scorer:
+    """Eval-mode forward (the Prediction.py loop body) over static buffers, one CUDA-graph replay per batch."""
+
+    def __init__(self, model: MM_FiBiNET, batch_size: int, seq_len: int = 20, idx_dtype=torch.int64, seq_dtype=torch.int64,
+                 use_mm_table: bool = False, graph: bool = True):
+        self.model, self.lib = model, _lib.load()
+        model._ensure_flat()
+        dev = model._flat.device
+        self.inp = _StaticBatch(batch_size, seq_len, idx_dtype, seq_dtype, dev, with_mm=not use_mm_table, with_labels=False)
+        self.B, self.L = batch_size, seq_len
+        self.ws = model._workspace(batch_size, seq_len)
+        self.prob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        self._bs = TrainStep._batch_struct(self)
+        self._graph, self._use_graph = None, graph
+
+    def _fwd(self):
+        m = self.model
+        P = m._params_struct()
+        _lib.check(self.lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(self.ws), self.ws.numel(), 0, 0.0, None, None, 0, 0, None,
+                                        _lib.ptr(self.prob), _lib.stream_ptr()), "fbn_forward")
+
+    def __call__(self, batch: dict) -> torch.Tensor:
+        if self.model.training:
+            raise RuntimeError("Scorer needs model.eval()")
+        self.inp.load(batch)
+        if not self._use_graph:
+            self._fwd()
+            return self.prob
+        if self._graph is None:
+            self._fwd()
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._fwd()
+        self._graph.replay()
+        return self.prob

@@ -334,7 +334,7 @@ class MM_FiBiNET(nn.Module):
         p_drop = self.dropout_p if train else 0.0
         self._offset += 1
         rc = lib.fbn_forward(C.byref(P), C.byref(bs), _lib.ptr(ws), ws.numel(), int(train), p_drop, _lib.ptr(m1), _lib.ptr(m2),
-                             self._seed, self._offset << 32, _lib.ptr(prob), _lib.stream_ptr())
+                             self._seed, self._offset << 32, None, _lib.ptr(prob), _lib.stream_ptr())
         _lib.check(rc, "fbn_forward")
         if train:
             with torch.no_grad():

@@ -124,10 +124,11 @@ size_t fbn_workspace_offset(int64_t batch, int64_t seq_len, int64_t item_rows, c
 /* MM_FiBiNET.forward (src/model_fibinet.py:138-199).
  * train != 0: BatchNorm uses batch statistics and updates running_mean/var (momentum 0.1, unbiased
  * var), dropout p = dropout_p with either the given keep-masks (uint8 (B,512) / (B,256), test hook)
- * or an in-kernel Philox stream keyed by (seed, offset).  prob_out: (B,) fp32 (may be NULL). */
+ * or an in-kernel Philox stream keyed by (seed, offset [+ *step_counter_dev << 36 when that device
+ * counter is given, so a CUDA-graph replay draws fresh masks]).  prob_out: (B,) fp32 (may be NULL). */
 int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train,
                 float dropout_p, const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed,
-                uint64_t offset, float* prob_out, fbn_stream_t stream);
+                uint64_t offset, const int32_t* step_counter_dev, float* prob_out, fbn_stream_t stream);
 
 /* The first stage of fbn_forward alone (src/model_fibinet.py:140-185): multi-field gather, history mean
  * pooling, item_emb_d128 projection + LayerNorm + ReLU, field stack and SENET; writes the re-weighted
