@@ -143,12 +143,16 @@ class TrainStep:
         self.step_counter += 1
 
     def _capture(self):
+        m = self.model
+        keep = [b.clone() for b in (m.mlp[1].running_mean, m.mlp[1].running_var, m.mlp[5].running_mean, m.mlp[5].running_var)]
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up outside capture (lazy inits: func attributes, workspaces)
             self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        for b, k in zip((m.mlp[1].running_mean, m.mlp[1].running_var, m.mlp[5].running_mean, m.mlp[5].running_var), keep):
+            b.copy_(k)                         # the warm-up forward must not count as a training step
         self.step_counter.zero_()
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         n0 = self.lib.fbn_launch_count()

@@ -1,0 +1,74 @@
+"""Inference entry point with the reference's surface (src/Prediction.py): rebuild the model, load
+../checkpoints/FiBiNET_best.pth (stripping a DataParallel "module." prefix), score test.parquet in batches of 8192
+and write prediction_fibinet.csv (ID, Task2) + submission_fibinet.zip.  The eval forward is one CUDA-graph replay
+of the sm_100a kernels per batch; there is no CPU path."""
+import os
+import sys
+import zipfile
+
+import numpy as np
+import pandas as pd
+import torch
+import yaml
+from torch.utils.data import DataLoader
+
+sys.path.append(os.path.dirname(os.path.abspath(__file__)))
+
+from dataloader import BatchCollator, ParquetDataset  # noqa: E402
+from model_fibinet import build_model  # noqa: E402
+
+from ctr_recommendation_b200.engine import Scorer  # noqa: E402
+
+
+class InferenceCollator(BatchCollator):
+    """Label-less collation; unknown item ids get an all-zero item_emb_d128 instead of raising."""
+
+    def __init__(self, max_len, column_index, item_info_path):
+        super().__init__(None, max_len, column_index, item_info_path, strict=False)
+
+
+def main():
+    path = "../config/fibinet_config.yaml"
+    if not os.path.exists(path):
+        path = "config/fibinet_config.yaml"
+    with open(path, "r") as fh:
+        cfg = yaml.safe_load(fh)
+    dataset_cfg = cfg["dataset_config"][cfg["dataset_id"]]
+    model_cfg = cfg[cfg["base_expid"]]
+    if not torch.cuda.is_available():
+        raise SystemExit("Prediction.py: no CUDA device -- this implementation has no CPU path (sm_100a kernels only)")
+    device = "cuda"
+
+    model = build_model({"precision": model_cfg.get("precision", "tf32x3")}, model_cfg)
+    ckpt = "../checkpoints/FiBiNET_best.pth"
+    if not os.path.exists(ckpt):
+        ckpt = "checkpoints/FiBiNET_best.pth"
+    print(f"[ckpt] {ckpt}")
+    state = torch.load(ckpt, map_location="cpu")
+    model.load_state_dict({k.replace("module.", ""): v for k, v in state.items()})
+    model.to(device)
+    model.eval()
+
+    test_dataset = ParquetDataset(dataset_cfg["test_data"])
+    collator = InferenceCollator(int(model_cfg.get("max_len", 20)), test_dataset.column_index, dataset_cfg["item_info"])
+    loader = DataLoader(test_dataset, batch_size=8192, shuffle=False, num_workers=int(os.environ.get("FBN_NUM_WORKERS", "4")),
+                        collate_fn=collator)
+    scorers, preds = {}, []
+    for batch in loader:
+        rows = batch["item_id"].shape[0]
+        seq = batch.get("item_seq")
+        key = (rows, 0 if seq is None else seq.shape[1], batch["item_id"].dtype)
+        if key not in scorers:
+            scorers[key] = Scorer(model, key[0], key[1], idx_dtype=key[2])
+        preds.append(scorers[key](batch).cpu().numpy())
+    predictions = np.concatenate(preds)
+
+    sub = pd.DataFrame({"ID": range(len(predictions)), "Task2": predictions})
+    sub.to_csv("prediction_fibinet.csv", index=False)
+    with zipfile.ZipFile("submission_fibinet.zip", "w", zipfile.ZIP_DEFLATED) as zf:
+        zf.write("prediction_fibinet.csv")
+    print("wrote submission_fibinet.zip")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""Training entry point with the reference's surface (src/train_fibinet.py): run it from src/ (or the repo
+root), it reads config/fibinet_config.yaml, trains MM_FiBiNET with Adam(lr, weight_decay) + OneCycleLR + grad-norm
+clip 10, validates every epoch with AUC and saves the best state_dict to ../checkpoints/FiBiNET_best.pth.
+
+What differs from the reference is only *how* the loop body runs: the model, the backward pass and the optimizer
+step are hand-written sm_100a CUDA (ctr_recommendation_b200), the step is replayed from a CUDA graph, and more
+than one GPU means one process per GPU under torchrun (NCCL all-reduce) instead of nn.DataParallel.  There is no
+CPU path: without a CUDA device the script stops with an error.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+sys.path.append(os.path.dirname(os.path.abspath(__file__)))
+
+from dataloader import MMCTRDataLoader  # noqa: E402
+from model_fibinet import build_model  # noqa: E402
+from utils import compute_auc, set_seed  # noqa: E402
+
+from ctr_recommendation_b200 import FusedAdam  # noqa: E402
+from ctr_recommendation_b200 import dist as fdist  # noqa: E402
+from ctr_recommendation_b200.engine import Scorer, TrainStep  # noqa: E402
+
+
+def load_config():
+    path = "../config/fibinet_config.yaml"
+    if not os.path.exists(path):
+        path = "config/fibinet_config.yaml"
+    print(f"[config] {path}")
+    with open(path, "r") as fh:
+        cfg = yaml.safe_load(fh)
+    return cfg["dataset_config"][cfg["dataset_id"]], cfg[cfg["base_expid"]]
+
+
+def main():
+    dataset_cfg, model_cfg = load_config()
+    set_seed(model_cfg.get("seed", 2025))
+    if not torch.cuda.is_available():
+        raise SystemExit("train_fibinet.py: no CUDA device -- this implementation has no CPU path (sm_100a kernels only)")
+    rank, local, world = fdist.init_from_env()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    log = print if rank == 0 else (lambda *a, **k: None)
+    log(f"[setup] FiBiNET on {torch.cuda.get_device_name(local)} x{world}")
+
+    batch_size = int(model_cfg.get("batch_size", 4096))
+    max_len = int(model_cfg.get("max_len", 20))
+    workers = int(os.environ.get("FBN_NUM_WORKERS", "4"))
+    train_loader = MMCTRDataLoader(None, dataset_cfg["train_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=True,
+                                   num_workers=workers, max_len=max_len)
+    valid_loader = MMCTRDataLoader(None, dataset_cfg["valid_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=False,
+                                   num_workers=workers, max_len=max_len)
+
+    model = build_model({"precision": model_cfg.get("precision", "tf32x3")}, model_cfg).to(device)
+    if world > 1:
+        fdist.broadcast_parameters(model)
+    lr = float(model_cfg.get("learning_rate", 1e-3))
+    weight_decay = float(model_cfg.get("weight_decay", 1e-5))
+    epochs = int(model_cfg.get("epochs", 30))
+    optimizer = FusedAdam(model, lr=lr, weight_decay=weight_decay)     # torch.optim.Adam semantics (L2-coupled)
+    steps_per_epoch = len(train_loader)
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=lr * 10, epochs=epochs, steps_per_epoch=steps_per_epoch,
+                                                    pct_start=0.3, div_factor=25.0, final_div_factor=1000.0)
+    engines = {}
+
+    def train_engine(rows, L, dtype):
+        key = ("t", rows, L, dtype)
+        if key not in engines:
+            engines[key] = TrainStep(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0)
+        return engines[key]
+
+    def score_engine(rows, L, dtype):
+        key = ("s", rows, L, dtype)
+        if key not in engines:
+            engines[key] = Scorer(model, rows, L, idx_dtype=dtype)
+        return engines[key]
+
+    best_auc = 0.0
+    os.makedirs("../checkpoints", exist_ok=True)
+    best_path = "../checkpoints/FiBiNET_best.pth"
+    log("[train] start")
+    for epoch in range(epochs):
+        model.train()
+        total_loss = torch.zeros(1, device=device)
+        steps = 0
+        for batch_dict, labels in train_loader:
+            shard, ylab, _ = fdist.shard_batch(batch_dict, labels, rank, world)     # DataParallel-style split on dim 0
+            rows = ylab.shape[0]
+            seq = shard.get("item_seq")
+            step = train_engine(rows, 0 if seq is None else seq.shape[1], shard["item_id"].dtype)
+            loss = step(shard, ylab)                       # fwd + BCE + bwd + clip(10) + Adam, one graph replay
+            scheduler.step()
+            total_loss += loss                             # stays on the device: no per-step host sync
+            steps += 1
+            if steps % 200 == 0:
+                log(f"Epoch {epoch + 1} | Step {steps} | Loss: {loss.item():.4f} | LR: {scheduler.get_last_lr()[0]:.6f}")
+        avg_loss = (total_loss.item() / steps) if steps else 0.0
+
+        model.eval()
+        y_trues, y_preds = [], []
+        for batch_dict, labels in valid_loader:
+            shard, ylab, _ = fdist.shard_batch(batch_dict, labels, rank, world)
+            seq = shard.get("item_seq")
+            sc = score_engine(ylab.shape[0], 0 if seq is None else seq.shape[1], shard["item_id"].dtype)
+            pred = fdist.gather_predictions(sc(shard).clone())
+            y_trues.append(labels.numpy())
+            y_preds.append(pred.cpu().numpy())
+        if y_trues:
+            auc = compute_auc(np.concatenate(y_trues), np.concatenate(y_preds))
+            log(f"Epoch {epoch + 1} | Train Loss: {avg_loss:.4f} | Valid AUC: {auc:.4f}")
+            if auc > best_auc:
+                best_auc = auc
+                if rank == 0:
+                    torch.save(model.state_dict(), best_path)
+                    log(f"[ckpt] new best -> {best_path}")
+    log(f"Done. Best AUC: {best_auc:.4f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+"""CPU, world_size 2, gloo: the data-parallel host logic (sharding, gradient all-reduce + weights, prediction gather)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _FakeModel:
+    def __init__(self, rank):
+        g = torch.Generator().manual_seed(10 + rank)
+        self._gflat = torch.randn(1000, generator=g)
+        self._item_grad = torch.randn(50, 128, generator=g)
+        self._grad_sumsq = torch.zeros(2)
+        self._dense_table_grad = False
+
+    def parameters(self):
+        return []
+
+    def buffers(self):
+        return []
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from ctr_recommendation_b200 import dist as fdist
+    r, l, w = fdist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    m = _FakeModel(rank)
+    ref = [_FakeModel(i) for i in range(world)]
+    fdist.broadcast_parameters(m)
+    assert m._dense_table_grad is True
+    # unequal shards: weights B_r / B as in the DataParallel-equivalence oracle
+    n = 10
+    lo, hi = fdist.shard_bounds(n, rank, world)
+    weight = (hi - lo) / n
+    fdist.sync_gradients(m, weight=weight)
+    exp_flat = sum(((fdist.shard_bounds(n, i, world)[1] - fdist.shard_bounds(n, i, world)[0]) / n) * ref[i]._gflat for i in range(world))
+    assert torch.allclose(m._gflat, exp_flat, atol=1e-6)
+    batch = {"item_id": torch.arange(n), "item_seq": torch.arange(n * 3).reshape(n, 3)}
+    shard, lab, wgt = fdist.shard_batch(batch, torch.arange(n).float(), rank, world)
+    assert abs(wgt - weight) < 1e-12 and shard["item_seq"].shape == (hi - lo, 3)
+    pred = fdist.gather_predictions(lab * 2)
+    assert torch.equal(pred, torch.arange(n).float() * 2)            # rank order == original row order
+    if rank == 0:
+        out.put("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29610 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == "ok"
+
+
+def test_shard_bounds_match_torch_chunking():
+    from ctr_recommendation_b200.dist import shard_bounds
+    for n in (1, 7, 8, 4096, 4097):
+        for world in (1, 2, 3, 8):
+            chunks = torch.arange(n).chunk(world)       # what DataParallel's scatter does on dim 0
+            for r in range(world):
+                lo, hi = shard_bounds(n, r, world)
+                exp = chunks[r] if r < len(chunks) else torch.arange(0)
+                assert hi - lo == exp.numel()
+                if exp.numel():
+                    assert lo == int(exp[0])

@@ -1,0 +1,127 @@
+"""CPU: host-side logic -- C-ABI surface, module/state_dict contract, optimizer plumbing, loader parity."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from ctr_recommendation_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fibinet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fbn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _lib.load()                      # builds with nvcc if the .so is missing; no compute calls here
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fibinet_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in lib.fbn_version()
+    assert lib.fbn_workspace_bytes(4096, 20, 91718) > 4096 * 2688 * 4
+    assert lib.fbn_workspace_offset(64, 20, 91718, b"C") % 256 == 0
+    assert lib.fbn_workspace_offset(64, 20, 91718, b"nope") == 2 ** 64 - 1
+
+
+def test_state_dict_contract_and_no_cpu_path():
+    from ctr_recommendation_b200 import build_model
+    model = build_model(None, {"embedding_dim": 128})
+    shapes = synth.state_dict_shapes()
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())                    # same 28 keys, same order
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    assert sd["mlp.1.num_batches_tracked"].dtype == torch.int64
+    assert torch.all(sd["item_emb.weight"][0] == 0)                  # padding_idx=0
+    W = synth.make_weights(seed=7)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in W.items()}, strict=True)
+    model._ensure_flat()                                             # dense params re-homed into one buffer
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), W[k]), k
+    p = model.mlp[0].weight
+    assert model._flat.data_ptr() <= p.data_ptr() < model._flat.data_ptr() + model._flat.numel() * 4
+    model.load_state_dict({k: torch.from_numpy(np.asarray(np.array(v) * (2 if v.dtype == np.float32 else 1))) for k, v in W.items()})
+    assert model._flat.data_ptr() <= model.mlp[0].weight.data_ptr() < model._flat.data_ptr() + model._flat.numel() * 4
+    batch, _ = synth.make_batch(seed=1, batch=8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model({k: torch.from_numpy(v) for k, v in batch.items()})
+    with pytest.raises(ValueError):
+        build_model(None, {"embedding_dim": 64})
+    with pytest.raises(ValueError):
+        build_model(None, {})                                        # reference default embedding_dim=64
+    from ctr_recommendation_b200 import BilinearInteraction
+    with pytest.raises(ValueError, match="bilinear_type must be 'all' or 'each'"):
+        BilinearInteraction(128, 6, "bogus")
+    assert [tuple(w.shape) for w in BilinearInteraction(128, 6, "each").W_list] == [(128, 128)] * 5
+
+
+def test_same_seed_same_init_as_reference_order():
+    """Parameters are created in the reference's order with torch's initialisers, so a seed gives the same weights
+    as the reference (checked against it when /root/reference is present)."""
+    from ctr_recommendation_b200 import build_model
+    torch.manual_seed(2025)
+    a = build_model(None, {"embedding_dim": 128}).state_dict()
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference not present on this box")
+    sys.path.insert(0, "/root/reference/src")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_model_fibinet", "/root/reference/src/model_fibinet.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    sys.path.pop(0)
+    torch.manual_seed(2025)
+    b = ref.build_model(None, {"embedding_dim": 128}).state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_fused_adam_exposes_param_groups_for_onecycle():
+    from ctr_recommendation_b200 import FusedAdam, build_model
+    model = build_model(None, {"embedding_dim": 128})
+    opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, epochs=2, steps_per_epoch=10, pct_start=0.3, div_factor=25.0,
+                                                final_div_factor=1000.0)
+    g = opt.param_groups[0]
+    assert abs(g["lr"] - 4e-4) < 1e-12 and abs(g["betas"][0] - 0.95) < 1e-12
+    assert all(id(p) != id(model.user_emb.weight) for p in g["params"])            # user_emb never gets a gradient
+    with pytest.raises(TypeError):
+        FusedAdam(torch.nn.Linear(2, 2))
+    assert sched.get_last_lr()[0] == g["lr"]
+
+
+def test_loader_matches_reference_loader(tmp_path):
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference not present on this box")
+    import subprocess
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_dataset.py"), str(tmp_path), "--train", "300", "--valid", "10",
+                    "--test", "50", "--items", "2000"], check=True, capture_output=True)
+    import importlib.util
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    ours = load("our_dl", os.path.join(ROOT, "src", "dataloader.py"))
+    ref = load("ref_dl", "/root/reference/src/dataloader.py")
+    kw = dict(batch_size=64, shuffle=False, num_workers=0, max_len=20)
+    a = ours.MMCTRDataLoader(None, str(tmp_path / "train.parquet"), str(tmp_path / "item_info.parquet"), **kw)
+    b = ref.MMCTRDataLoader(None, str(tmp_path / "train.parquet"), str(tmp_path / "item_info.parquet"), **kw)
+    assert a.dataset.darray.dtype == b.dataset.darray.dtype == np.float64 and a.column_index == b.column_index
+    n = 0
+    for (ba, ya), (bb, yb) in zip(a, b):
+        assert list(ba) == list(bb)
+        for k in bb:
+            assert ba[k].dtype == bb[k].dtype and torch.equal(ba[k], bb[k]), k
+        assert torch.equal(ya, yb)
+        n += 1
+    assert n == 5
+    coll = ours.BatchCollator(None, 20, a.column_index, str(tmp_path / "item_info.parquet"))
+    with pytest.raises(KeyError):
+        coll.lookup(np.array([1, 999999]))
