@@ -342,7 +342,8 @@ def test_train_step_engine_matches_module_path(gpu, precision):
         if k in NOISE_DRIVEN or "num_batches" in k:
             continue
         d = np.abs(w0[k].astype(np.float64) - w1[k])
-        assert d.mean() <= 1e-6 * max(np.abs(w0[k]).max(), 1e-30) + 1e-9, (k, d.mean())
+        slack = 2e-5 if k.endswith("running_mean") else 1e-9      # running_mean absorbs the noise-driven Linear bias
+        assert d.mean() <= 1e-6 * max(np.abs(w0[k]).max(), 1e-30) + slack, (k, d.mean())
     assert int(w2["mlp.1.num_batches_tracked"]) == int(synth.make_weights(7)["mlp.1.num_batches_tracked"]) + steps
 
 
