@@ -5,6 +5,19 @@
 
 namespace fbn {
 
+// An operand already converted to the tcgen05 format (tf32 hi|lo split or bf16) in its natural row-major layout.
+struct Packed {
+  void* data = nullptr;      // hi part (or the bf16 copy); (rows, pitch) elements
+  long long pitch = 0;       // elements per row (multiple of 8)
+  long long lo_off = 0;      // element offset of the lo part (tf32x3)
+  long long rows = 0, cols = 0;
+  Packed view_cols(long long col0, int esz) const {   // column-block view (same pitch / lo_off)
+    Packed p = *this;
+    p.data = static_cast<char*>(data) + col0 * esz;
+    return p;
+  }
+};
+
 // C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N])
 //   a_t == 0: A stored (M,K) row-major, lda ; a_t != 0: A stored (K,M) row-major, lda
 //   b_t == 0: B stored (K,N) row-major, ldb ; b_t != 0: B stored (N,K) row-major, ldb
@@ -23,6 +36,9 @@ struct GemmArgs {
   unsigned long long kmask = ~0ull;  // bit i: 128-wide K block i is non-zero
   unsigned long long nmask = ~0ull;  // bit i: 128-wide N block i is needed
   int accumulate = 0;
+  // optional pre-packed operands (tcgen05 precisions): same storage orientation as A / B; batch index advances them by
+  // strideA / strideB elements like the fp32 pointers
+  Packed pkA, pkB;
 };
 
 int gemm_simt(const GemmArgs& g, cudaStream_t st);
@@ -31,6 +47,9 @@ int gemm_simt(const GemmArgs& g, cudaStream_t st);
 int gemm_tc(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& g, int precision);
 size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precision);
+size_t packed_bytes(long long rows, long long cols, int precision);
+int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
+                 Packed* out, cudaStream_t st);
 int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 }  // namespace fbn

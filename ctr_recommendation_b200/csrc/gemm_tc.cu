@@ -14,9 +14,10 @@
 // long K loop (measured 2.2e-5 relative at K = 2688 with 3xTF32 -- no better than one TF32 pass).  So the MMA warp
 // switches between two TMEM accumulators every TC_CHUNK k-blocks and the epilogue warps fold each finished chunk
 // into fp32 registers with round-to-nearest adds while the next chunk is being computed.
-// Both operands are consumed K-major.  A "pack" pre-pass (pack kernels below) converts the fp32 activations /
-// weights to the operand format (hi|lo split or bf16) and transposes when the contraction runs over the
-// leading dimension (weight gradients), so every GEMM flavour of the step maps onto this one kernel.
+// Operands are "packed" once per step by an elementwise pre-pass into the MMA operand format (tf32 hi | lo split, or
+// bf16) in their NATURAL row-major layout -- no transposes: an operand whose contraction index is the leading (row)
+// index is consumed MN-major, the other way K-major, so every GEMM flavour of the step (forward NT, data-gradient NN,
+// weight-gradient TN) maps onto this one kernel and a packed tensor is shared by all GEMMs that read it.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -35,7 +36,6 @@ struct TcArgs {
   int splits; long long strideSplit;
   unsigned long long kmask, nmask;
   int accumulate;
-  int a_lo_row, b_lo_row;  // row offset of the "lo" half inside the packed operand (tf32x3)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -80,20 +80,29 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // K-major, 128-byte swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start >> 4 ; [16,30) LBO >> 4 (=1, unused for swizzled K-major) ; [32,46) SBO >> 4 = 1024 B between
 //   8-row groups ; [46,48) version = 1 ; [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+//
+// MN-major operands (stored [K][MN], the natural layout of an activation whose batch dimension is contracted, or of
+// an nn.Linear weight used transposed) use the canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)): one TMA box is
+// [BK k-rows][128 bytes of MN]; 8-row K groups are SBO = 1024 B apart and successive 128-byte MN chunks are
+// LBO = (bytes of one box) apart.
+// 32-bit (tf32) MN-major operands only exist in the SWIZZLE_128B_BASE32B flavour (cutlass: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): 32-byte chunks swizzled over 4-row groups (TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), SBO = 512 B between the 4-row groups, layout type 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes = 16, uint32_t sbo_bytes = 1024, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6); a/b format @ [7,10) / [10,13)
-// (BF16 = 1, TF32 = 2); K-major A and B; N >> 3 @ [17,23); M >> 4 @ [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// (BF16 = 1, TF32 = 2); a_major @ 15, b_major @ 16 (0 = K-major, 1 = MN-major); N >> 3 @ [17,23); M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 template <int MODE>
@@ -131,20 +140,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 struct TcCfg {
-  static constexpr int BK = MODE == FBN_PREC_TF32X3 ? 32 : 64;          // elements per 128-byte swizzle row
-  static constexpr int UK = MODE == FBN_PREC_TF32X3 ? 8 : 16;           // K per tcgen05.mma
-  static constexpr int NPART = MODE == FBN_PREC_TF32X3 ? 2 : 1;         // hi + lo
-  static constexpr int TILE_BYTES = TC_BM * 128;                        // one 128-row x 128-byte operand tile
-  static constexpr int STAGE_BYTES = 2 * NPART * TILE_BYTES;            // A parts + B parts
+  static constexpr int ESZ = MODE == FBN_PREC_TF32X3 ? 4 : 2;
+  static constexpr int BK = 128 / ESZ;                                   // k-block: 32 (tf32) / 64 (bf16) elements
+  static constexpr int UK = 32 / ESZ;                                    // K per tcgen05.mma: 8 / 16
+  static constexpr int EPB = 128 / ESZ;                                  // elements per 128-byte swizzle row
+  static constexpr int NPART = MODE == FBN_PREC_TF32X3 ? 2 : 1;          // hi + lo
+  static constexpr int TILE_BYTES = TC_BM * 128;                         // 128 x BK (K-major) == BK x 128 (MN-major)
+  static constexpr int BOX_MN_BYTES = BK * 128;                          // one MN-major box: BK rows x 128 bytes
+  static constexpr int STAGE_BYTES = 2 * NPART * TILE_BYTES;
   static constexpr int STAGES = MODE == FBN_PREC_TF32X3 ? 3 : 6;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int NBAR = 2 * STAGES + 4;
   static constexpr int FMT = MODE == FBN_PREC_TF32X3 ? 2 : 1;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+struct TcMaps { CUtensorMap a[2], b[2]; };   // [0] = hi (or the only part), [1] = lo
+
+template <int MODE, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps tm, const TcArgs g) {
   using Cfg = TcCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -189,8 +202,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0 && nact > 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+#pragma unroll
+      for (int p = 0; p < Cfg::NPART; ++p) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.a[p])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.b[p])) : "memory");
+      }
       int it = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!active(kb)) continue;
@@ -200,18 +216,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(full + s, Cfg::STAGE_BYTES);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const int kc = kb * Cfg::BK;
-        tma_load_2d(st, &tmA, full + s, kc, m0);
-        tma_load_2d(st + Cfg::NPART * Cfg::TILE_BYTES, &tmB, full + s, kc, n0);
-        if (Cfg::NPART == 2) {
-          tma_load_2d(st + Cfg::TILE_BYTES, &tmA, full + s, kc, g.a_lo_row + m0);
-          tma_load_2d(st + 3 * Cfg::TILE_BYTES, &tmB, full + s, kc, g.b_lo_row + n0);
+#pragma unroll
+        for (int p = 0; p < Cfg::NPART; ++p) {
+          uint8_t* sa = st + p * Cfg::TILE_BYTES;                       // stage = [A parts | B parts]
+          uint8_t* sb = st + (Cfg::NPART + p) * Cfg::TILE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tm.a[p], full + s, kc, m0);                // box: BK elements of K x 128 rows of M
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BM / Cfg::EPB; ++j)                   // boxes: 128 B of M x BK rows of K
+              tma_load_2d(sa + j * Cfg::BOX_MN_BYTES, &tm.a[p], full + s, m0 + j * Cfg::EPB, kc);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tm.b[p], full + s, kc, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BN / Cfg::EPB; ++j)
+              tma_load_2d(sb + j * Cfg::BOX_MN_BYTES, &tm.b[p], full + s, n0 + j * Cfg::EPB, kc);
+          }
         }
         ++it;
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nact > 0) {
-      constexpr uint32_t idesc = make_idesc(Cfg::FMT, TC_BM, TC_BN);
+      constexpr uint32_t idesc = make_idesc(Cfg::FMT, TC_BM, TC_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // per-MMA K advance of the descriptor start address (16-byte units): K-major: UK elements inside the 128-byte
+      // swizzle row; MN-major: UK rows of 128 bytes
+      constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
+      constexpr bool base32 = MODE == FBN_PREC_TF32X3;   // 4-byte elements, MN-major: 32B-atom swizzle
+      constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
+      constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
       int it = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!active(kb)) continue;
@@ -226,18 +263,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * TC_BN);
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t a_hi = make_desc(sa), b_hi = make_desc(sa + Cfg::NPART * Cfg::TILE_BYTES);
+        const uint64_t a_hi = make_desc(sa, lbo_a, sbo_a, lay_a);
+        const uint64_t b_hi = make_desc(sa + Cfg::NPART * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
 #pragma unroll
         for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
-          const uint64_t adv = (uint64_t)((k * Cfg::UK * (MODE == FBN_PREC_TF32X3 ? 4 : 2)) >> 4);
           const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
           if (Cfg::NPART == 2) {
-            const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES), b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES);
-            umma<MODE>(tacc, a_lo + adv, b_hi + adv, idesc, acc);      // small terms first
-            umma<MODE>(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma<MODE>(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+            const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
+            const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+            umma<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);      // small terms first
+            umma<MODE>(tacc, a_hi + k * adv_a, b_lo + k * adv_b, idesc, 1u);
+            umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
           } else {
-            umma<MODE>(tacc, a_hi + adv, b_hi + adv, idesc, acc);
+            umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
           }
         }
         tc_commit(empty + s);                                  // frees the smem stage once the MMAs have read it
@@ -287,18 +325,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// pack kernels: fp32 (rows x cols, ld) -> K-major operand, optionally transposed
-//   tf32x3: dst[0..R) = hi, dst[lo_row .. lo_row+R) = lo, row pitch Kp floats
-//   bf16  : dst (R x Kp) bf16
+// pack kernel: fp32 (rows x cols, ld) -> same layout in operand format, pitch Kp elements
+//   tf32x3: hi at dst, lo at dst + lo_off floats ; bf16: dst (rows x pitch) bf16
+//   colmask: 128-column blocks to convert (structurally-zero blocks of the MLP input are never read)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 template <int MODE>
 __global__ void pack_rows_kernel(const float* __restrict__ src, long long ld, long long R, long long K, long long Kp, void* dst,
-                                 long long lo_row) {
+                                 long long lo_off, unsigned long long colmask) {
   const long long q = Kp / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * q; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / q, c = (i % q) * 4;
+    if (colmask != ~0ull && !((colmask >> (c / 128)) & 1ull)) continue;
     float4 v = f4(0.f);
     if (c + 3 < K) v = ld4s(src + r * ld + c);
     else {
@@ -310,7 +349,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long ld, lo
       float* d = static_cast<float*>(dst);
       const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
       st4(d + r * Kp + c, h);
-      st4(d + (lo_row + r) * Kp + c, v - h);
+      st4(d + lo_off + r * Kp + c, v - h);
     } else {
       __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
       __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
@@ -318,36 +357,6 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long ld, lo
       o.x = *reinterpret_cast<uint32_t*>(&p0);
       o.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(d + r * Kp + c) = o;
-    }
-  }
-}
-
-// src stored (K rows, R cols) -> dst[r][k] = src[k][r]
-template <int MODE>
-__global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ src, long long ld, long long R, long long K,
-                                                             long long Kp, void* dst, long long lo_row) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const long long r0 = (long long)blockIdx.x * 32, k0 = (long long)blockIdx.y * 32;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long k = k0 + ty + i * 8, r = r0 + tx;
-    tile[ty + i * 8][tx] = (k < K && r < R) ? src[k * ld + r] : 0.f;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long r = r0 + ty + i * 8, k = k0 + tx;
-    if (r < R && k < Kp) {
-      const float v = tile[tx][ty + i * 8];
-      if (MODE == FBN_PREC_TF32X3) {
-        float* d = static_cast<float*>(dst);
-        const float h = tf32_hi(v);
-        d[r * Kp + k] = h;
-        d[(lo_row + r) * Kp + k] = v - h;
-      } else {
-        static_cast<__nv_bfloat16*>(dst)[r * Kp + k] = __float2bfloat16_rn(v);
-      }
     }
   }
 }
@@ -370,49 +379,72 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D map over a (rows, K) K-contiguous operand; box = (128 bytes of K) x 128 rows, 128B swizzle, OOB -> 0
-static int make_map(CUtensorMap* m, int mode, void* base, long long rows, long long K, long long pitch_elems) {
+// 2-D map over a row-major (rows, cols) operand part with `pitch` elements per row, 128B swizzle, OOB -> 0.
+//   k_major: rows index M/N, cols index K -> box = (128 bytes of K) x 128 rows
+//   mn_major: rows index K, cols index M/N -> box = (128 bytes of M/N) x BK rows
+static int make_map(CUtensorMap* m, int mode, const void* base, long long rows, long long cols, long long pitch, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   FBN_REQUIRE(enc != nullptr, FBN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int esz = mode == FBN_PREC_TF32X3 ? 4 : 2;
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)(pitch_elems * esz)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 128};
+  const cuuint32_t epb = 128 / esz;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(pitch * esz)};
+  cuuint32_t box[2] = {epb, mn_major ? epb : 128u};   // MN-major: BK == epb rows of K
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, mode == FBN_PREC_TF32X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FBN_REQUIRE(r == CUDA_SUCCESS, FBN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows %lld K %lld pitch %lld)", (int)r, rows, K,
-              pitch_elems);
+  FBN_REQUIRE(aligned16(base) && (pitch * esz) % 16 == 0, FBN_ERR_ALIGN, "tcgen05 operand is not 16-byte aligned");
+  CUresult r = enc(m, mode == FBN_PREC_TF32X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FBN_REQUIRE(r == CUDA_SUCCESS, FBN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows %lld cols %lld pitch %lld)", (int)r, rows,
+              cols, pitch);
   return FBN_OK;
 }
 
 static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
-// bytes of scratch one gemm_tc call needs for the packed operands
+size_t packed_bytes(long long rows, long long cols, int precision) {
+  const long long pitch = round_up(cols, 8);
+  return (size_t)(rows * pitch * (precision == FBN_PREC_TF32X3 ? 8 : 2)) + 1024;
+}
+
+// converts src (rows x cols fp32, ld) into operand format at dst (1024-byte aligned inside the caller's region)
+int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
+                 Packed* out, cudaStream_t st) {
+  FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16, FBN_ERR_ARG, "pack_operand: bad precision");
+  FBN_REQUIRE(aligned16(src) && ld % 4 == 0, FBN_ERR_ALIGN, "pack_operand: source must be 16-byte aligned with ld %% 4 == 0");
+  const long long pitch = round_up(cols, 8);
+  void* base = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(dst) + 1023) & ~uintptr_t(1023));
+  const long long lo_off = rows * pitch;
+  const long long n = rows * (pitch / 4);
+  int blocks = (int)std::min<long long>(cdiv(n, 256), 16LL * num_sms());
+  if (precision == FBN_PREC_TF32X3)
+    pack_rows_kernel<FBN_PREC_TF32X3><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, rows, cols, pitch, base, lo_off, colmask);
+  else
+    pack_rows_kernel<FBN_PREC_BF16><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, rows, cols, pitch, base, lo_off, colmask);
+  FBN_CHECK_LAUNCH();
+  out->data = base; out->pitch = pitch; out->lo_off = lo_off; out->rows = rows; out->cols = cols;
+  return FBN_OK;
+}
+
+// bytes of scratch one gemm_tc call needs when it has to pack both operands itself
 size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precision) {
-  const long long Kp = round_up(K, 8);
-  const long long parts = precision == FBN_PREC_TF32X3 ? 2 : 1;
-  const long long esz = precision == FBN_PREC_TF32X3 ? 4 : 2;
-  const long long Mp = round_up(M, 128), Np = round_up(N, 128);
-  return (size_t)((Mp + Np) * parts * Kp * esz + 2048);
+  return packed_bytes(M, K, precision) + packed_bytes(N, K, precision) + packed_bytes(K, std::max(M, N), precision) + 4096;
 }
 
 bool gemm_tc_supported(const GemmArgs& g, int precision) {
   return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16) && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch >= 1;
 }
 
-template <int MODE>
-static int pack_operand(const float* src, long long ld, bool stored_k_major, long long R, long long K, long long Kp, void* dst,
-                        long long lo_row, cudaStream_t st) {
-  if (stored_k_major) {  // (R, K) row-major: straight conversion
-    const long long n = R * (Kp / 4);
-    int blocks = (int)std::min<long long>(cdiv(n, 256), 16LL * num_sms());
-    pack_rows_kernel<MODE><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, R, K, Kp, dst, lo_row);
-  } else {               // stored (K, R): transpose
-    dim3 grid((unsigned)cdiv(R, 32), (unsigned)cdiv(Kp, 32));
-    pack_transpose_kernel<MODE><<<grid, 256, 0, st>>>(src, ld, R, K, Kp, dst, lo_row);
+template <int MODE, bool A_MN, bool B_MN>
+static int launch_tc(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<MODE>;
+  static bool attr = false;
+  if (!attr) {
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
   }
+  gemm_tc_kernel<MODE, A_MN, B_MN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(maps, t);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -420,41 +452,53 @@ static int pack_operand(const float* src, long long ld, bool stored_k_major, lon
 template <int MODE>
 static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   using Cfg = TcCfg<MODE>;
-  static bool attr = false;
-  if (!attr) {
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr = true;
-  }
-  const long long Kp = round_up(g.K, 8);
-  const long long Mp = round_up(g.M, 128), Np = round_up(g.N, 128);
-  const long long esz = MODE == FBN_PREC_TF32X3 ? 4 : 2;
-  const size_t a_bytes = (size_t)(Mp * Cfg::NPART * Kp * esz), b_bytes = (size_t)(Np * Cfg::NPART * Kp * esz);
-  FBN_REQUIRE(scratch != nullptr && scratch_bytes >= a_bytes + b_bytes + 2048, FBN_ERR_ARG,
-              "tcgen05 GEMM needs %zu bytes of operand scratch, got %zu", a_bytes + b_bytes + 2048, scratch_bytes);
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~uintptr_t(1023));
-  void* packA = base;
-  void* packB = base + ((a_bytes + 1023) & ~size_t(1023));
+  const bool a_mn = g.a_t != 0;   // A stored (K,M): contraction index leads -> MN-major
+  const bool b_mn = g.b_t == 0;   // B stored (K,N)
+  uint8_t* sp = static_cast<uint8_t*>(scratch);
+  size_t left = scratch_bytes;
   for (int bi = 0; bi < g.batch; ++bi) {
-    const float* A = g.A + bi * g.strideA;
-    const float* Bm = g.B + bi * g.strideB;
-    // A: a_t == 0 -> stored (M,K) = K-major ; a_t != 0 -> stored (K,M)
-    int rc = pack_operand<MODE>(A, g.lda, g.a_t == 0, g.M, g.K, Kp, packA, Mp, st);
-    if (rc) return rc;
-    // B: b_t != 0 -> stored (N,K) = K-major ; b_t == 0 -> stored (K,N)
-    rc = pack_operand<MODE>(Bm, g.ldb, g.b_t != 0, g.N, g.K, Kp, packB, Np, st);
-    if (rc) return rc;
-    CUtensorMap tmA, tmB;
-    rc = make_map(&tmA, MODE, packA, Mp * Cfg::NPART, g.K, Kp);
-    if (rc) return rc;
-    rc = make_map(&tmB, MODE, packB, Np * Cfg::NPART, g.K, Kp);
-    if (rc) return rc;
+    Packed pa, pb;
+    const long long ra = a_mn ? g.K : g.M, ca = a_mn ? g.M : g.K;
+    const long long rb = b_mn ? g.K : g.N, cb = b_mn ? g.N : g.K;
+    uint8_t* cur = sp;
+    size_t rem = left;
+    if (g.pkA.data) {
+      pa = g.pkA;
+      pa.data = static_cast<uint8_t*>(pa.data) + (size_t)bi * g.strideA * Cfg::ESZ;
+    } else {
+      const size_t need = packed_bytes(ra, ca, MODE);
+      FBN_REQUIRE(cur != nullptr && rem >= need, FBN_ERR_ARG, "tcgen05 GEMM: operand scratch too small (%zu < %zu)", rem, need);
+      int rc = pack_operand(g.A + bi * g.strideA, g.lda, ra, ca, MODE, cur, ~0ull, &pa, st);
+      if (rc) return rc;
+      cur += need; rem -= need;
+    }
+    if (g.pkB.data) {
+      pb = g.pkB;
+      pb.data = static_cast<uint8_t*>(pb.data) + (size_t)bi * g.strideB * Cfg::ESZ;
+    } else {
+      const size_t need = packed_bytes(rb, cb, MODE);
+      FBN_REQUIRE(cur != nullptr && rem >= need, FBN_ERR_ARG, "tcgen05 GEMM: operand scratch too small (%zu < %zu)", rem, need);
+      int rc = pack_operand(g.B + bi * g.strideB, g.ldb, rb, cb, MODE, cur, ~0ull, &pb, st);
+      if (rc) return rc;
+    }
+    TcMaps maps;
+    for (int p = 0; p < Cfg::NPART; ++p) {
+      int rc = make_map(&maps.a[p], MODE, static_cast<uint8_t*>(pa.data) + (size_t)p * pa.lo_off * Cfg::ESZ, ra, ca, pa.pitch, a_mn);
+      if (rc) return rc;
+      rc = make_map(&maps.b[p], MODE, static_cast<uint8_t*>(pb.data) + (size_t)p * pb.lo_off * Cfg::ESZ, rb, cb, pb.pitch, b_mn);
+      if (rc) return rc;
+    }
+    if (Cfg::NPART == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
     TcArgs t;
     t.C = g.C + bi * g.strideC; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
     t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
-    t.a_lo_row = (int)Mp; t.b_lo_row = (int)Np;
     dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)g.splits);
-    gemm_tc_kernel<MODE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, t);
-    FBN_CHECK_LAUNCH();
+    int rc;
+    if (a_mn && b_mn) rc = launch_tc<MODE, true, true>(maps, t, grid, st);
+    else if (a_mn) rc = launch_tc<MODE, true, false>(maps, t, grid, st);
+    else if (b_mn) rc = launch_tc<MODE, false, true>(maps, t, grid, st);
+    else rc = launch_tc<MODE, false, false>(maps, t, grid, st);
+    if (rc) return rc;
   }
   return FBN_OK;
 }

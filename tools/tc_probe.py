@@ -6,7 +6,7 @@ torch.manual_seed(0)
 for prec in ("tf32x3", "bf16"):
     for (M, N, K, a_t, b_t) in [(128, 128, 32, False, True), (128, 128, 64, False, True), (128, 128, 256, False, True),
                                 (256, 256, 512, False, True), (300, 512, 2688, False, True), (4096, 512, 2688, False, True),
-                                (300, 512, 2688, False, False), (512, 2688, 300, True, False)]:
+                                (300, 512, 2688, False, False), (512, 2688, 300, True, False), (256, 128, 64, True, True), (4096, 2688, 512, False, False), (128, 128, 16384, True, False)]:
         A = torch.randn(M, K, device="cuda"); B = torch.randn(K, N, device="cuda")
         ref = (A.double() @ B.double()).float()
         a_in = A.t().contiguous() if a_t else A
