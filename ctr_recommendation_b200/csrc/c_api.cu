@@ -113,12 +113,20 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   w.cub_bytes = emb_sort_temp_bytes(nocc, rows);
   w.cub_tmp = take(w.cub_bytes);
   // operand scratch of the tcgen05 path: the largest call is the MLP-1 weight gradient (512 + 2688) x B
-  size_t gs = 0;
-  gs = std::max(gs, gemm_tc_scratch_bytes(H1, K1, Bp, FBN_PREC_TF32X3));
-  gs = std::max(gs, gemm_tc_scratch_bytes(Bp, H1, K1, FBN_PREC_TF32X3));
-  gs = std::max(gs, gemm_tc_scratch_bytes(Bp, K1, H1, FBN_PREC_TF32X3));
+  size_t gs = 4096;   // every operand of the model path is pre-packed into the pk_* regions below
   w.gemm_scratch_bytes = gs;
   w.gemm_scratch = take(gs);
+  const int PX = FBN_PREC_TF32X3;   // sized for the larger (hi|lo) format
+  w.pk_C = take(packed_bytes(Bp, K1, PX));
+  w.pk_A1 = take(packed_bytes(Bp, H1, PX));
+  w.pk_dH2 = take(packed_bytes(Bp, H2, PX));
+  w.pk_dH1 = take(packed_bytes(Bp, H1, PX));
+  w.pk_dT = take(packed_bytes(Bp, 10 * D, PX));
+  w.pk_dy = take(packed_bytes(Bp, D, PX));
+  w.pk_xmm = take(packed_bytes(Bp, D, PX));
+  w.pk_w1 = take(packed_bytes(H1, K1, PX));
+  w.pk_w2 = take(packed_bytes(H2, H1, PX));
+  w.pk_bil = take(packed_bytes(FBN_PAIRS * D, D, PX));
   w.total_bytes = off;
 }
 
@@ -126,6 +134,40 @@ int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, 
   if (precision == FBN_PREC_FP32) return gemm_simt(g, st);
   return gemm_tc(g, precision, scratch, scratch_bytes, st);
 }
+
+// Registry of the tensors packed so far in this step: a GEMM operand given as an fp32 pointer anywhere inside a
+// registered (contiguous) tensor is served from its packed copy at the same element offset (pitch == ld for all of
+// them), so each activation / weight is converted exactly once per step.
+struct PkReg {
+  int prec = FBN_PREC_FP32;
+  cudaStream_t st = nullptr;
+  struct E { const float* src; size_t n; Packed pk; } e[16];
+  int ne = 0;
+  bool on() const { return prec != FBN_PREC_FP32; }
+  int esz() const { return prec == FBN_PREC_TF32X3 ? 4 : 2; }
+  void describe(const float* src, long long rows, long long cols, void* region) {
+    if (!on()) return;
+    for (int i = 0; i < ne; ++i) if (e[i].src == src) return;
+    e[ne].src = src; e[ne].n = (size_t)rows * cols; e[ne].pk = packed_describe(region, rows, cols);
+    ++ne;
+  }
+  int pack(const float* src, long long rows, long long cols, void* region, unsigned long long colmask = ~0ull) {
+    if (!on()) return FBN_OK;
+    describe(src, rows, cols, region);
+    Packed tmp;
+    return pack_operand(src, cols, rows, cols, prec, region, colmask, &tmp, st);
+  }
+  Packed find(const float* p) const {
+    for (int i = 0; i < ne; ++i)
+      if (p >= e[i].src && p < e[i].src + e[i].n) return e[i].pk.view_cols((long long)(p - e[i].src), esz());
+    return Packed();
+  }
+  int run(GemmArgs g, Workspace& w) const {
+    if (on()) { g.pkA = find(g.A); g.pkB = find(g.B); }
+    return gemm(g, prec, w.gemm_scratch, w.gemm_scratch_bytes, st);
+  }
+};
+static thread_local PkReg tl_reg;   // rebuilt at the start of every fbn_forward / fbn_backward call
 
 // launchers defined in embed.cu
 struct EmbedFwdArgs;
@@ -195,11 +237,11 @@ static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStrea
   g.M = w.B; g.N = D; g.K = D; g.lda = K1; g.ldb = D; g.ldc = nT * D; g.a_t = 0; g.b_t = 0;
   if (type == FBN_BILINEAR_ALL) {           // T_t = V_{t+2} W
     g.A = w.C + 2 * D; g.strideA = D; g.B = p->bil_w; g.strideB = 0; g.C = w.T; g.strideC = D; g.batch = 4;
-    return gemm(g, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st);
+    return tl_reg.run(g, w);
   }
   if (type == FBN_BILINEAR_EACH) {          // T_t = V_{t+1} W_{t+1}
     g.A = w.C + 1 * D; g.strideA = D; g.B = p->bil_w + 1 * D * D; g.strideB = D * D; g.C = w.T; g.strideC = D; g.batch = 4;
-    return gemm(g, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st);
+    return tl_reg.run(g, w);
   }
   int q0 = 0;                               // T_q = V_i W_(i,j), grouped by i
   for (int i = 1; i < NF - 1; ++i) {
@@ -207,7 +249,7 @@ static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStrea
     const int pidx = i * (2 * NF - i - 1) / 2;  // pair index of (i, i+1) in the full enumeration
     g.A = w.C + i * D; g.strideA = 0; g.B = p->bil_w + (long long)pidx * D * D; g.strideB = D * D;
     g.C = w.T + q0 * D; g.strideC = D; g.batch = nj;
-    RC(gemm(g, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
+    RC(tl_reg.run(g, w));
     q0 += nj;
   }
   return FBN_OK;
@@ -246,25 +288,36 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
   const long long B = b->batch;
 
+  tl_reg = PkReg();
+  tl_reg.prec = p->precision; tl_reg.st = st;
+  const unsigned long long fmask = 0x3Eull;                       // MLP-input blocks 1..5: the SENET-weighted fields
+  const int nW = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
+  RC(tl_reg.pack(p->w1, H1, K1, w.pk_w1, active_mask()));
+  RC(tl_reg.pack(p->w2, H2, H1, w.pk_w2));
+  RC(tl_reg.pack(p->bil_w, (long long)nW * D, D, w.pk_bil));
+
   RC(run_embed_fwd(p, b, w, 1, st));
+  RC(tl_reg.pack(w.C, B, K1, w.pk_C, fmask));                     // fields first: the bilinear transform reads them
 
   RC(bilinear_transform_fwd(p, w, st));
   RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, st));
+  RC(tl_reg.pack(w.C, B, K1, w.pk_C, active_mask() & ~fmask));    // then the pair blocks
 
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   GemmArgs g1;
   g1.A = w.C; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = K1; g1.lda = K1; g1.ldb = K1; g1.ldc = H1;
   g1.b_t = 1; g1.kmask = active_mask();
-  RC(gemm(g1, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
+  RC(tl_reg.run(g1, w));
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
   DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
   RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, st));
+  RC(tl_reg.pack(w.A1, B, H1, w.pk_A1));
 
   GemmArgs g2;
   g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2;
   g2.b_t = 1;
-  RC(gemm(g2, p->precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
+  RC(tl_reg.run(g2, w));
   if (train) RC(bn_train_stats(w.Hd2, B, H2, w.partial, mean2, rstd2, p->bn2_mean, p->bn2_var, st));
   else RC(bn_eval_stats(p->bn2_mean, p->bn2_var, H2, mean2, rstd2, st));
   DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2; d2.step_dev = step_counter_dev;
@@ -282,7 +335,7 @@ static int wgrad(const float* dOut, long long ldo, const float* In, long long ld
   g.nmask = nmask;
   FBN_REQUIRE((size_t)g.splits * M * N <= w.partial_floats, FBN_ERR_ARG, "internal: split-K scratch too small");
   g.C = w.partial; g.strideSplit = M * N;
-  RC(gemm(g, precision, w.gemm_scratch, w.gemm_scratch_bytes, st));
+  RC(tl_reg.run(g, w));
   return reduce_splits(w.partial, g.splits, M, N, M * N, nmask, out, st);
 }
 
@@ -298,6 +351,17 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   const long long B = b->batch;
   const int prec = p->precision;
   const float scale = (train && dropout_p > 0.f) ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  // operands packed by fbn_forward are still valid: re-register them (no launch), pack the new ones as they appear
+  tl_reg = PkReg();
+  tl_reg.prec = p->precision; tl_reg.st = st;
+  {
+    const int nWr = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
+    tl_reg.describe(p->w1, H1, K1, w.pk_w1);
+    tl_reg.describe(p->w2, H2, H1, w.pk_w2);
+    tl_reg.describe(p->bil_w, (long long)nWr * D, D, w.pk_bil);
+    tl_reg.describe(w.C, B, K1, w.pk_C);
+    tl_reg.describe(w.A1, B, H1, w.pk_A1);
+  }
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   const unsigned long long amask = active_mask();
 
@@ -305,43 +369,46 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
                     st));
   RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2, st));
+  RC(tl_reg.pack(w.dH2, B, H2, w.pk_dH2));
   RC(colsum(w.dH2, B, H2, w.partial, g->b2, st));
   RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, st));
   {
     GemmArgs d;  // dA1 = dH2 * w2
     d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
-    RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+    RC(tl_reg.run(d, w));
   }
   // ---- layer 1 ----
   RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
   RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1, st));
+  RC(tl_reg.pack(w.dH1, B, H1, w.pk_dH1));
   RC(colsum(w.dH1, B, H1, w.partial, g->b1, st));
   RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, st));
   {
     GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
     d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
-    RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+    RC(tl_reg.run(d, w));
   }
   // ---- bilinear ----
   const int type = p->bilinear_type;
   const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
   RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, st));
+  RC(tl_reg.pack(w.dT, B, (long long)nT * D, w.pk_dT));
   {
     GemmArgs d;  // dV[src] += dT_t * W^T
     d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
     if (type == FBN_BILINEAR_ALL) {
       d.A = w.dT; d.strideA = D; d.B = p->bil_w; d.strideB = 0; d.C = w.dV + 1 * D; d.strideC = D; d.batch = 4;
-      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+      RC(tl_reg.run(d, w));
     } else if (type == FBN_BILINEAR_EACH) {
       d.A = w.dT; d.strideA = D; d.B = p->bil_w + D * D; d.strideB = D * D; d.C = w.dV; d.strideC = D; d.batch = 4;
-      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+      RC(tl_reg.run(d, w));
     } else {
       int q = 0;
       for (int i = 1; i < NF - 1; ++i)
         for (int j = i + 1; j < NF; ++j, ++q) {
           const int pidx = i * (2 * NF - i - 1) / 2 + (j - i - 1);
           d.A = w.dT + q * D; d.B = p->bil_w + (long long)pidx * D * D; d.C = w.dV + (i - 1) * D; d.batch = 1;
-          RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+          RC(tl_reg.run(d, w));
         }
     }
   }
@@ -354,11 +421,11 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     FBN_REQUIRE((size_t)nT * S * D * D <= w.partial_floats, FBN_ERR_ARG, "internal: bilinear scratch too small");
     if (type == FBN_BILINEAR_ALL) {
       d.A = w.C + 2 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
-      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+      RC(tl_reg.run(d, w));
       RC(reduce_splits(w.partial, 4 * S, D, D, (long long)D * D, ~0ull, g->bil_w, st));
     } else if (type == FBN_BILINEAR_EACH) {
       d.A = w.C + 1 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
-      RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+      RC(tl_reg.run(d, w));
       FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * D * D, st));  // W_0 multiplies the zero field
       for (int t = 0; t < 4; ++t)
         RC(reduce_splits(w.partial + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull, g->bil_w + (long long)(t + 1) * D * D, st));
@@ -368,7 +435,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
       for (int i = 1; i < NF - 1; ++i) {
         const int nj = NF - 1 - i;
         d.A = w.C + i * D; d.strideA = 0; d.B = w.dT + q * D; d.strideB = D; d.batch = nj; d.C = w.partial + (long long)q * S * D * D;
-        RC(gemm(d, prec, w.gemm_scratch, w.gemm_scratch_bytes, st));
+        RC(tl_reg.run(d, w));
         q += nj;
       }
       for (int t = 0; t < 10; ++t)
@@ -388,6 +455,8 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   RC(launch_senet_param_grads(w.sestat, B, w.partial, g->se_w1, g->se_b1, g->se_w2, g->se_b2, st));
   RC(colprod2(w.dln, w.xhat, B, D, w.partial, g->ln_g, g->ln_b, st));
   RC(colsum(w.dy, B, D, w.partial, g->mm_b, st));
+  RC(tl_reg.pack(w.dy, B, D, w.pk_dy));
+  RC(tl_reg.pack(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm));
   RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, st));
   // ---- embedding table rows ----
   EmbGradArgs eg{};

@@ -164,8 +164,11 @@ struct Workspace {
   int32_t* row_cnt;  // (item_rows + 1)
   void* cub_tmp;
   size_t cub_bytes;
-  void* gemm_scratch;   // packed tcgen05 operands (hi|lo or bf16)
+  void* gemm_scratch;   // operand scratch for GEMMs whose inputs are not pre-packed
   size_t gemm_scratch_bytes;
+  // tcgen05 operands packed once per step (tf32 hi|lo or bf16), natural layout
+  void* pk_C; void* pk_A1; void* pk_dH2; void* pk_dH1; void* pk_dT; void* pk_dy; void* pk_xmm;
+  void* pk_w1; void* pk_w2; void* pk_bil;
   size_t total_bytes;
 };
 

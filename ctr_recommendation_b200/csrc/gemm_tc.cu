@@ -408,14 +408,23 @@ size_t packed_bytes(long long rows, long long cols, int precision) {
   return (size_t)(rows * pitch * (precision == FBN_PREC_TF32X3 ? 8 : 2)) + 1024;
 }
 
+Packed packed_describe(void* region, long long rows, long long cols) {
+  Packed p;
+  p.data = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(region) + 1023) & ~uintptr_t(1023));
+  p.pitch = round_up(cols, 8);
+  p.lo_off = rows * p.pitch;
+  p.rows = rows; p.cols = cols;
+  return p;
+}
+
 // converts src (rows x cols fp32, ld) into operand format at dst (1024-byte aligned inside the caller's region)
 int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
                  Packed* out, cudaStream_t st) {
   FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16, FBN_ERR_ARG, "pack_operand: bad precision");
   FBN_REQUIRE(aligned16(src) && ld % 4 == 0, FBN_ERR_ALIGN, "pack_operand: source must be 16-byte aligned with ld %% 4 == 0");
-  const long long pitch = round_up(cols, 8);
-  void* base = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(dst) + 1023) & ~uintptr_t(1023));
-  const long long lo_off = rows * pitch;
+  *out = packed_describe(dst, rows, cols);
+  const long long pitch = out->pitch, lo_off = out->lo_off;
+  void* base = out->data;
   const long long n = rows * (pitch / 4);
   int blocks = (int)std::min<long long>(cdiv(n, 256), 16LL * num_sms());
   if (precision == FBN_PREC_TF32X3)
@@ -423,7 +432,6 @@ int pack_operand(const float* src, long long ld, long long rows, long long cols,
   else
     pack_rows_kernel<FBN_PREC_BF16><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, rows, cols, pitch, base, lo_off, colmask);
   FBN_CHECK_LAUNCH();
-  out->data = base; out->pitch = pitch; out->lo_off = lo_off; out->rows = rows; out->cols = cols;
   return FBN_OK;
 }
 
