@@ -518,6 +518,16 @@ extern "C" size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int pr
   return precision == FBN_PREC_FP32 ? 0 : gemm_tc_scratch_bytes(M, N, K, precision);
 }
 
+namespace fbn { void set_tc_pair(int on); }
+
+// runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles
+extern "C" int fbn_set_option(const char* name, int value) {
+  FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
+  if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
+  set_error("fbn_set_option: unknown option '%s'", name);
+  return FBN_ERR_ARG;
+}
+
 extern "C" const char* fbn_last_error(void) { return g_err; }
 extern "C" uint64_t fbn_launch_count(void) { return g_launches; }
 extern "C" const char* fbn_version(void) { return "fibinet_b200 0.1 (sm_100a)"; }

@@ -325,6 +325,228 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): one 256 x 256 output tile per 2-CTA cluster.
+//   Each CTA stages ITS 128 rows of A and ITS 128-row half of the B tile (64 KB per stage for tf32x3, as above) but the
+//   pair's tensor cores multiply 256 x 256 per instruction, so the L2 -> smem traffic per MMA is halved -- the 1-CTA
+//   kernel is bound by exactly that traffic (profiles/: ~50 % tensor-pipe activity).
+//   Roles per CTA (320 threads): warp 0 TMA producer (TMA completes on the LEADER's full barrier), warp 1 of the leader
+//   CTA issues tcgen05.mma.cta_group::2 and multicasts tcgen05.commit to both CTAs' barriers, warps 2..9 epilogue
+//   (lane quarter = warp % 4, 128-column half = (warp - 2) / 4) with the same chunked round-to-nearest folding.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC2_THREADS = 320;
+constexpr int TC2_BN = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on the same barrier in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <int MODE>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (MODE == FBN_PREC_TF32X3) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+
+template <int MODE, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ TcMaps tm, const TcArgs g) {
+  using Cfg = TcCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                            // used on the leader: TMA bytes of BOTH CTAs
+  uint64_t* empty = bars + Cfg::STAGES;             // per CTA: stage free (multicast commit)
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;         // per CTA [2]: accumulator chunk complete (multicast commit)
+  uint64_t* tempty = bars + 2 * Cfg::STAGES + 2;    // leader [2]: both CTAs' epilogues drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n0 = blockIdx.y * TC2_BN, sp = blockIdx.z;
+  const int m0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;      // this CTA's 128 rows of the 256-row cluster tile
+  // both 128-column halves of this N tile inactive -> nothing to do (uniform across the pair)
+  if (g.nmask != ~0ull && !((g.nmask >> (n0 / 128)) & 3ull)) return;
+
+  const int kblocks = (int)((g.K + Cfg::BK - 1) / Cfg::BK);
+  const int per = (kblocks + g.splits - 1) / g.splits;
+  const int kb0 = sp * per, kb1 = min(kblocks, kb0 + per);
+  auto active = [&](int kb) { return g.kmask == ~0ull || ((g.kmask >> ((kb * Cfg::BK) / 128)) & 1ull); };
+  int nact = 0;
+  for (int kb = kb0; kb < kb1; ++kb) nact += active(kb) ? 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 2 * 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // both CTAs, same warp id: two accumulators of 256 fp32 columns = the whole TMEM
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nact > 0) {
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!active(kb)) continue;
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);                                   // my smem stage is free
+        const uint32_t lbar = mapa_u32(smem_u32(full + s), 0);          // leader's full barrier
+        if (rank == 0) mbar_expect_tx(full + s, 2 * Cfg::STAGE_BYTES);  // bytes of both CTAs land here
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const int kc = kb * Cfg::BK;
+        const int nb = n0 + (int)rank * 128;                            // my half of the B tile
+#pragma unroll
+        for (int p = 0; p < Cfg::NPART; ++p) {
+          uint8_t* sa = st + p * Cfg::TILE_BYTES;
+          uint8_t* sb = st + (Cfg::NPART + p) * Cfg::TILE_BYTES;
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tm.a[p], lbar, kc, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BM / Cfg::EPB; ++j) tma_load_2d_pair(sa + j * Cfg::BOX_MN_BYTES, &tm.a[p], lbar, m0 + j * Cfg::EPB, kc);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tm.b[p], lbar, kc, nb);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 128 / Cfg::EPB; ++j) tma_load_2d_pair(sb + j * Cfg::BOX_MN_BYTES, &tm.b[p], lbar, nb + j * Cfg::EPB, kc);
+          }
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0 && nact > 0) {
+      constexpr uint32_t idesc = make_idesc(Cfg::FMT, 256, TC2_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
+      constexpr bool base32 = MODE == FBN_PREC_TF32X3;
+      constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
+      constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!active(kb)) continue;
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        const int chunk = it / TC_CHUNK, buf = chunk & 1, pos = it % TC_CHUNK;
+        if (pos == 0) {
+          mbar_wait(tempty + buf, ((chunk >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * TC2_BN);
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t a_hi = make_desc(sa, lbo_a, sbo_a, lay_a);
+        const uint64_t b_hi = make_desc(sa + Cfg::NPART * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+#pragma unroll
+        for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+          const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+          if (Cfg::NPART == 2) {
+            const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
+            const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+            umma_pair<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);
+            umma_pair<MODE>(tacc, a_hi + k * adv_a, b_lo + k * adv_b, idesc, 1u);
+            umma_pair<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
+          } else {
+            umma_pair<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
+          }
+        }
+        tc_commit_pair(empty + s);
+        if (pos == TC_CHUNK - 1 || it == nact - 1) tc_commit_pair(tfull + buf);
+        ++it;
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const long long row = (long long)m0 + q * 32 + lane;
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+    const int nchunks = (nact + TC_CHUNK - 1) / TC_CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(tfull + buf, (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC2_BN + half * 128 + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_u32(smem_u32(tempty + buf), 0));       // tell the leader's MMA warp
+    }
+    const int ncol0 = n0 + half * 128;
+    const bool col_on = ncol0 < g.N && (g.nmask == ~0ull || ((g.nmask >> (ncol0 / 128)) & 1ull));
+    if (row < g.M && col_on) {
+      float* crow = g.C + (long long)sp * g.strideSplit + row * g.ldc + ncol0;
+#pragma unroll
+      for (int j = 0; j < 128; j += 4) {
+        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (g.bias) o += ld4(g.bias + ncol0 + j);
+        if (g.accumulate) o += *reinterpret_cast<const float4*>(crow + j);
+        st4(crow + j, o);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the peer's smem / TMEM must stay alive until every MMA and remote arrive has landed
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pack kernel: fp32 (rows x cols, ld) -> same layout in operand format, pitch Kp elements
 //   tf32x3: hi at dst, lo at dst + lo_off floats ; bf16: dst (rows x pitch) bf16
 //   colmask: 128-column blocks to convert (structurally-zero blocks of the MLP input are never read)
@@ -457,6 +679,22 @@ static int launch_tc(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_
   return FBN_OK;
 }
 
+template <int MODE, bool A_MN, bool B_MN>
+static int launch_tc2(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<MODE>;
+  static bool attr = false;
+  if (!attr) {
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  gemm_tc2_kernel<MODE, A_MN, B_MN><<<grid, TC2_THREADS, Cfg::SMEM, st>>>(maps, t);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+static int g_tc_pair = 1;   // 0: always use the 1-CTA kernel (fbn_set_option("tc_pair", 0))
+void set_tc_pair(int on) { g_tc_pair = on; }
+
 template <int MODE>
 static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   using Cfg = TcCfg<MODE>;
@@ -500,8 +738,17 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     TcArgs t;
     t.C = g.C + bi * g.strideC; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
     t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
-    dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)g.splits);
     int rc;
+    if (g_tc_pair && g.M > 128 && g.N >= 256) {      // CTA pairs: 256 x 256 tiles, half the L2 traffic per MMA
+      dim3 grid2((unsigned)(2 * cdiv(g.M, 256)), (unsigned)cdiv(g.N, TC2_BN), (unsigned)g.splits);
+      if (a_mn && b_mn) rc = launch_tc2<MODE, true, true>(maps, t, grid2, st);
+      else if (a_mn) rc = launch_tc2<MODE, true, false>(maps, t, grid2, st);
+      else if (b_mn) rc = launch_tc2<MODE, false, true>(maps, t, grid2, st);
+      else rc = launch_tc2<MODE, false, false>(maps, t, grid2, st);
+      if (rc) return rc;
+      continue;
+    }
+    dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)g.splits);
     if (a_mn && b_mn) rc = launch_tc<MODE, true, true>(maps, t, grid, st);
     else if (a_mn) rc = launch_tc<MODE, true, false>(maps, t, grid, st);
     else if (b_mn) rc = launch_tc<MODE, false, true>(maps, t, grid, st);

@@ -217,6 +217,8 @@ int fbn_gemm(const float* A, const float* B, const float* bias, float* C, int64_
 /* scratch the tcgen05 precisions need for their packed operands (0 for FBN_PREC_FP32) */
 size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int precision);
 
+/* runtime knobs: "tc_pair" (1 = CTA-pair 256x256 tcgen05 tiles for large GEMMs [default], 0 = single-CTA 128x128) */
+int fbn_set_option(const char* name, int value);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 uint64_t fbn_launch_count(void);
 const char* fbn_last_error(void);
