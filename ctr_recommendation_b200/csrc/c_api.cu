@@ -94,7 +94,7 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   w.dy = (float*)take(Bp * D * f);
   w.sestat = (float*)take(Bp * 24 * f);
   size_t pf = 0;
-  pf = std::max<size_t>(pf, (size_t)pick_splits(4 * 21, Bp) * H1 * K1);
+  pf = std::max<size_t>(pf, (size_t)8 * H1 * K1);   // up to 8-way split-K of the MLP-1 weight gradient
   pf = std::max<size_t>(pf, (size_t)pick_splits(2 * 4, Bp) * H2 * H1);
   pf = std::max<size_t>(pf, (size_t)10 * 32 * D * D);
   pf = std::max<size_t>(pf, (size_t)2 * 148 * 4 * MAX_CATE * D);
@@ -326,12 +326,31 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   return FBN_OK;
 }
 
+// split-K factor for a weight gradient on the tcgen05 path: with CTA-pair tiles the CTA count is 2 * clusters * splits;
+// choose the split that wastes the least of the last wave of 148 SMs
+static int pick_splits_pair(long long M, long long N, long long K, unsigned long long nmask, size_t max_floats) {
+  long long clusters = 0;
+  for (long long n0 = 0; n0 < N; n0 += 256)
+    if (nmask == ~0ull || ((nmask >> (n0 / 128)) & 3ull)) clusters += cdiv(M, 256);
+  const long long kblocks = std::max<long long>(1, cdiv(K, 32));
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 32; ++s) {
+    if ((size_t)s * M * N > max_floats || cdiv(kblocks, s) < 4) break;
+    const long long ctas = 2 * clusters * s;
+    const double cost = (double)cdiv(ctas, 148) / s + 0.002 * s;   // waves per unit of K work (+ a little for the reduce)
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 static int wgrad(const float* dOut, long long ldo, const float* In, long long ldi, long long B, long long M, long long N,
                  unsigned long long nmask, int precision, Workspace& w, float* out, cudaStream_t st) {
   // out[M,N] = dOut[B,M]^T * In[B,N]
   GemmArgs g;
   g.A = dOut; g.lda = ldo; g.a_t = 1; g.B = In; g.ldb = ldi; g.b_t = 0; g.M = M; g.N = N; g.K = B; g.ldc = N;
   g.splits = pick_splits(cdiv(M, 128) * cdiv(N, 128), B);
+  if (precision != FBN_PREC_FP32 && M > 128 && N >= 256) g.splits = pick_splits_pair(M, N, B, nmask, w.partial_floats);
   g.nmask = nmask;
   FBN_REQUIRE((size_t)g.splits * M * N <= w.partial_floats, FBN_ERR_ARG, "internal: split-K scratch too small");
   g.C = w.partial; g.strideSplit = M * N;

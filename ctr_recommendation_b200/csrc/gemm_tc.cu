@@ -739,7 +739,10 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     t.C = g.C + bi * g.strideC; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
     t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
     int rc;
-    if (g_tc_pair && g.M > 128 && g.N >= 256) {      // CTA pairs: 256 x 256 tiles, half the L2 traffic per MMA
+    // CTA pairs (256 x 256 tiles, half the L2 traffic per MMA) once they can fill most of the 148 SMs; small problems
+    // keep the 128 x 128 single-CTA tiles (4x as many CTAs)
+    const long long pair_ctas = 2 * cdiv(g.M, 256) * cdiv(g.N, TC2_BN) * g.splits;
+    if (g_tc_pair && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {
       dim3 grid2((unsigned)(2 * cdiv(g.M, 256)), (unsigned)cdiv(g.N, TC2_BN), (unsigned)g.splits);
       if (a_mn && b_mn) rc = launch_tc2<MODE, true, true>(maps, t, grid2, st);
       else if (a_mn) rc = launch_tc2<MODE, true, false>(maps, t, grid2, st);
