@@ -68,6 +68,8 @@ _SIGNATURES = {
     "fbn_bilinear_scratch_bytes": (_sz, [_i64, C.c_int, C.c_int, C.c_int]),
     "fbn_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp, _sz, _vp]),
     "fbn_gemm_scratch_bytes": (_sz, [_i64, _i64, _i64, C.c_int]),
+    "fbn_time_gemm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, _u64, C.c_int, _vp, _sz, _vp, _sz, C.c_int,
+                                C.POINTER(C.c_float), _vp]),
     "fbn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "fbn_launch_count": (_u64, []),
     "fbn_last_error": (C.c_char_p, []),

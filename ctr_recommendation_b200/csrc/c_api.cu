@@ -537,6 +537,46 @@ extern "C" size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int pr
   return precision == FBN_PREC_FP32 ? 0 : gemm_tc_scratch_bytes(M, N, K, precision);
 }
 
+// Times ONE GEMM configuration with CUDA events on `stream`: operands are packed once (tcgen05 precisions), then the GEMM
+// kernel alone is launched `iters` times, each preceded by an (untimed) overwrite of `flush` so that operands come from HBM,
+// not L2.  ms_out[0] = mean duration of the GEMM launch in milliseconds.  Synchronises the stream (benchmark helper).
+extern "C" int fbn_time_gemm(const float* A, const float* Bm, float* C, int64_t M, int64_t N, int64_t K, int a_t, int b_t,
+                             uint64_t kmask, int precision, void* scratch, size_t scratch_bytes, void* flush, size_t flush_bytes,
+                             int iters, float* ms_out, fbn_stream_t stream) {
+  FBN_REQUIRE(A && Bm && C && ms_out && iters > 0, FBN_ERR_ARG, "fbn_time_gemm: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmArgs g;
+  g.A = A; g.B = Bm; g.C = C; g.M = M; g.N = N; g.K = K; g.a_t = a_t; g.b_t = b_t; g.kmask = kmask;
+  g.lda = a_t ? M : K; g.ldb = b_t ? K : N; g.ldc = N;
+  uint8_t* sp = static_cast<uint8_t*>(scratch);
+  if (precision != FBN_PREC_FP32) {
+    const long long ra = a_t ? K : M, ca = a_t ? M : K, rb = b_t ? N : K, cb = b_t ? K : N;
+    const size_t na = packed_bytes(ra, ca, precision), nb = packed_bytes(rb, cb, precision);
+    FBN_REQUIRE(scratch && scratch_bytes >= na + nb, FBN_ERR_ARG, "fbn_time_gemm: scratch too small");
+    RC(pack_operand(A, g.lda, ra, ca, precision, sp, ~0ull, &g.pkA, st));
+    RC(pack_operand(Bm, g.ldb, rb, cb, precision, sp + na, ~0ull, &g.pkB, st));
+  }
+  cudaEvent_t e0, e1;
+  FBN_CHECK_CUDA(cudaEventCreate(&e0));
+  FBN_CHECK_CUDA(cudaEventCreate(&e1));
+  RC(gemm(g, precision, nullptr, 0, st));   // warm-up (function attributes, descriptors)
+  double tot = 0.0;
+  for (int i = 0; i < iters; ++i) {
+    if (flush) FBN_CHECK_CUDA(cudaMemsetAsync(flush, i & 0xff, flush_bytes, st));
+    FBN_CHECK_CUDA(cudaEventRecord(e0, st));
+    RC(gemm(g, precision, nullptr, 0, st));
+    FBN_CHECK_CUDA(cudaEventRecord(e1, st));
+    FBN_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    FBN_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    tot += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ms_out[0] = (float)(tot / iters);
+  return FBN_OK;
+}
+
 namespace fbn { void set_tc_pair(int on); }
 
 // runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles

@@ -217,6 +217,12 @@ int fbn_gemm(const float* A, const float* B, const float* bias, float* C, int64_
 /* scratch the tcgen05 precisions need for their packed operands (0 for FBN_PREC_FP32) */
 size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int precision);
 
+/* Benchmark helper: mean CUDA-event duration (ms, host pointer ms_out) of the GEMM kernel alone for one configuration --
+ * operands packed once, `iters` timed launches each preceded by an untimed overwrite of `flush` (L2 eviction).
+ * A is (M,K) [a_t=0] or (K,M) [a_t=1] contiguous; B is (K,N) [b_t=0] or (N,K) [b_t=1] contiguous; kmask as in the MLP path. */
+int fbn_time_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int a_t, int b_t, uint64_t kmask,
+                  int precision, void* scratch, size_t scratch_bytes, void* flush, size_t flush_bytes, int iters, float* ms_out,
+                  fbn_stream_t stream);
 /* runtime knobs: "tc_pair" (1 = CTA-pair 256x256 tcgen05 tiles for large GEMMs [default], 0 = single-CTA 128x128) */
 int fbn_set_option(const char* name, int value);
 /* number of kernels this library has launched so far in this process (host-side counter) */
