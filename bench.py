@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train = the headline train step; infer = eval forward over the batch (Prediction.py loop body, BASELINE config 3)")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
 
@@ -138,10 +140,19 @@ def run_ours(args):
     stage = ({k: torch.empty_like(v, device=dev) for k, v in pool[0][0].items()}, torch.empty_like(pool[0][1], device=dev))
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool[0][0].values()) + pool[0][1].numel() * 4
 
-    from ctr_recommendation_b200.engine import TrainStep
-    engine = None if args.eager else TrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0)
+    from ctr_recommendation_b200.engine import Scorer, TrainStep
+    infer = args.mode == "infer"
+    if infer:
+        model.eval()
+    engine = None if args.eager else (Scorer(model, args.batch, L_HIST, idx_dtype=torch.float64) if infer else
+                                      TrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0))
 
     def step(batch, labels):
+        if infer:                    # scoring: forward only, predictions read back by the caller
+            if engine is not None:
+                return engine(batch)
+            with torch.no_grad():
+                return model(batch)
         if engine is not None:       # CUDA-graph replay of the same loop body
             loss = engine(batch, labels)
             sched.step()
@@ -191,6 +202,8 @@ def run_ours(args):
                 stage[0][name].copy_(t, non_blocking=True)
             stage[1].copy_(hy, non_blocking=True)
             loss = step(stage[0], stage[1])
+        if infer:
+            return loss.cpu()   # predictions to the host every batch, like Prediction.py:113
         return loss.item()      # D2H read of the step's result, like the reference loop (:124)
 
     for k in range(args.warmup):
@@ -208,9 +221,9 @@ def run_ours(args):
     value = global_batch * args.steps / (ms / 1e3)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
     peaks = load_peaks()
-    kernels = kernel_rooflines(args, model, dev_pool[0], peaks, lib) if rank == 0 else {}
+    kernels = kernel_rooflines(args, model, dev_pool[0], peaks, lib) if (rank == 0 and not infer) else {}
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if not infer else "inference samples/sec FiBiNET MicroLens-shape (Prediction.py path)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": f"FiBiNET train step (config/fibinet_config.yaml model: D=128, 6 fields, bilinear all, MLP 2688-512-256-1), "
@@ -220,8 +233,8 @@ def run_ours(args):
                    "l2": "working set per step (table p/m/v/grad 188 MB + activations) exceeds the 126 MB L2; inputs cycle over "
                          f"{args.pool} distinct batches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4},
-        "gpu_launches": int(engine.kernels_per_step * args.steps) if engine is not None else int(launches),
+                "d2h_bytes_per_step": 4 if not infer else 4 * args.batch},
+        "gpu_launches": int(getattr(engine, "kernels_per_step", 0) * args.steps) if engine is not None else int(launches),
         "clocks": clk.summary(),
         "clocks_e2e": clk2.summary(),
     }

@@ -229,6 +229,7 @@ class Scorer:
         self.prob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self._bs = TrainStep._batch_struct(self)
         self._graph, self._use_graph = None, graph
+        self.kernels_per_step = 0
 
     def _fwd(self):
         m = self.model
@@ -247,7 +248,9 @@ class Scorer:
             self._fwd()
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
+            n0 = self.lib.fbn_launch_count()
             with torch.cuda.graph(self._graph):
                 self._fwd()
+            self.kernels_per_step = int(self.lib.fbn_launch_count() - n0)
         self._graph.replay()
         return self.prob
