@@ -51,7 +51,8 @@ _SIGNATURES = {
     "fbn_forward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "fbn_embed_forward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _vp]),
     "fbn_backward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, C.POINTER(Grads), _vp, _i64,
-                               _vp, _vp, C.c_int, _vp, _vp]),
+                               _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "fbn_embed_index": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, _vp, _vp]),
     "fbn_bce_loss": (C.c_int, [_vp, _vp, _i64, _f, _vp, _vp, _vp]),
     "fbn_clip_coef": (C.c_int, [_vp, C.c_int, _f, _vp, _vp]),
     "fbn_adam_table": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(AdamHyper), _vp, _vp]),

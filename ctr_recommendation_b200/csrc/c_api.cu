@@ -157,6 +157,15 @@ struct PkReg {
     Packed tmp;
     return pack_operand(src, cols, rows, cols, prec, region, colmask, &tmp, st);
   }
+  // register `src` as packed-by-its-producer and return the destination descriptor for that kernel
+  PackDst dst(const float* src, long long rows, long long cols, void* region) {
+    PackDst d;
+    if (!on()) return d;
+    describe(src, rows, cols, region);
+    const Packed pk = packed_describe(region, rows, cols);
+    d.base = pk.data; d.pitch = pk.pitch; d.lo_off = pk.lo_off; d.mode = prec;
+    return d;
+  }
   Packed find(const float* p) const {
     for (int i = 0; i < ne; ++i)
       if (p >= e[i].src && p < e[i].src + e[i].n) return e[i].pk.view_cols((long long)(p - e[i].src), esz());
@@ -255,7 +264,8 @@ static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStrea
   return FBN_OK;
 }
 
-static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace& w, int save, cudaStream_t st) {
+static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace& w, int save, cudaStream_t st,
+                         PackDst pkC = PackDst(), PackDst pkX = PackDst()) {
   const long long B = b->batch;
   EmbedFwdArgs e{};
   e.item_emb = p->item_emb; e.cate_emb = p->cate_emb; e.mm_w = p->mm_w; e.mm_b = p->mm_b; e.ln_g = p->ln_g; e.ln_b = p->ln_b;
@@ -266,6 +276,7 @@ static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace&
   e.B = B; e.L = (int)b->seq_len; e.item_rows = p->item_rows; e.cate_rows = (int)p->cate_rows; e.save = save;
   e.ids = w.ids; e.seq32 = w.seq; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.xmm = w.xmm; e.rstd = w.rstd; e.cnt = w.cnt;
   e.C = w.C;
+  e.pkC = pkC; e.pkX = pkX;
   return launch_embed_senet_fwd(e, st);
 }
 
@@ -296,12 +307,12 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   RC(tl_reg.pack(p->w2, H2, H1, w.pk_w2));
   RC(tl_reg.pack(p->bil_w, (long long)nW * D, D, w.pk_bil));
 
-  RC(run_embed_fwd(p, b, w, 1, st));
-  RC(tl_reg.pack(w.C, B, K1, w.pk_C, fmask));                     // fields first: the bilinear transform reads them
-
+  // activations are converted to the operand format by the kernels that produce them (no separate pack pass)
+  const PackDst pkC = tl_reg.dst(w.C, B, K1, w.pk_C);
+  RC(run_embed_fwd(p, b, w, 1, st, pkC, tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm)));
+  (void)fmask;
   RC(bilinear_transform_fwd(p, w, st));
-  RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, st));
-  RC(tl_reg.pack(w.C, B, K1, w.pk_C, active_mask() & ~fmask));    // then the pair blocks
+  RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, pkC, st));
 
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   GemmArgs g1;
@@ -311,8 +322,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
   DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
-  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, st));
-  RC(tl_reg.pack(w.A1, B, H1, w.pk_A1));
+  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst(w.A1, B, H1, w.pk_A1), st));
 
   GemmArgs g2;
   g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2;
@@ -344,6 +354,29 @@ static int pick_splits_pair(long long M, long long N, long long K, unsigned long
   return best;
 }
 
+static EmbGradArgs make_emb_args(const fbn_params_t* p, const fbn_batch_t* b, Workspace& w, int32_t* row_touched) {
+  EmbGradArgs eg{};
+  eg.item_id = b->item_id; eg.idx_dtype = b->idx_dtype;
+  eg.seq = (b->seq_len > 0 && b->item_seq) ? b->item_seq : nullptr; eg.seq_dtype = b->seq_dtype;
+  eg.B = b->batch; eg.L = (int)b->seq_len; eg.rows = p->item_rows;
+  eg.dXitem = w.dXitem; eg.dXhist = w.dXhist; eg.keys_in = w.keys_in; eg.keys_out = w.keys_out; eg.vals_in = w.vals_in;
+  eg.vals_out = w.vals_out; eg.row_count = row_touched ? row_touched : w.row_cnt; eg.row_off = w.row_off; eg.cub_tmp = w.cub_tmp;
+  eg.cub_bytes = w.cub_bytes; eg.sumsq_partial = w.partial;
+  return eg;
+}
+
+// Occurrence index of the embedding backward (sort of the B + B*L row ids, per-row counts / offsets).  It depends on the
+// batch ids only, so a host may run it on a second stream concurrently with fbn_forward and pass index_ready = 1 to
+// fbn_backward (engine.TrainStep does).
+extern "C" int fbn_embed_index(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int32_t* row_touched,
+                               fbn_stream_t stream) {
+  RC(check_common(p, b, ws, ws_bytes));
+  Workspace w;
+  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
+  return emb_index(eg, (cudaStream_t)stream);
+}
+
 static int wgrad(const float* dOut, long long ldo, const float* In, long long ldi, long long B, long long M, long long N,
                  unsigned long long nmask, int precision, Workspace& w, float* out, cudaStream_t st) {
   // out[M,N] = dOut[B,M]^T * In[B,N]
@@ -360,7 +393,8 @@ static int wgrad(const float* dOut, long long ldo, const float* In, long long ld
 
 extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
                             const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat, int64_t dense_grad_n,
-                            float* item_grad, int32_t* row_touched, int zero_fill, float* grad_sumsq, fbn_stream_t stream) {
+                            float* item_grad, int32_t* row_touched, int zero_fill, int index_ready, float* grad_sumsq,
+                            fbn_stream_t stream) {
   RC(check_common(p, b, ws, ws_bytes));
   FBN_REQUIRE(dprob && g && item_grad && grad_sumsq, FBN_ERR_ARG, "fbn_backward: null pointer");
   FBN_REQUIRE(aligned16(item_grad), FBN_ERR_ALIGN, "item_grad is not 16-byte aligned");
@@ -380,6 +414,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     tl_reg.describe(p->bil_w, (long long)nWr * D, D, w.pk_bil);
     tl_reg.describe(w.C, B, K1, w.pk_C);
     tl_reg.describe(w.A1, B, H1, w.pk_A1);
+    tl_reg.describe(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm);
   }
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   const unsigned long long amask = active_mask();
@@ -387,8 +422,8 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   // ---- head + layer 2 ----
   RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
                     st));
-  RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2, st));
-  RC(tl_reg.pack(w.dH2, B, H2, w.pk_dH2));
+  RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
+                   tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
   RC(colsum(w.dH2, B, H2, w.partial, g->b2, st));
   RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, st));
   {
@@ -398,8 +433,8 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   }
   // ---- layer 1 ----
   RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
-  RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1, st));
-  RC(tl_reg.pack(w.dH1, B, H1, w.pk_dH1));
+  RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
+                   tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
   RC(colsum(w.dH1, B, H1, w.partial, g->b1, st));
   RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, st));
   {
@@ -410,8 +445,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   // ---- bilinear ----
   const int type = p->bilinear_type;
   const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
-  RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, st));
-  RC(tl_reg.pack(w.dT, B, (long long)nT * D, w.pk_dT));
+  RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, tl_reg.dst(w.dT, B, (long long)nT * D, w.pk_dT), st));
   {
     GemmArgs d;  // dV[src] += dT_t * W^T
     d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
@@ -467,6 +501,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
   e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.ln_g = p->ln_g; e.B = B; e.cate_rows = (int)p->cate_rows;
   e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial;
+  e.pkdy = tl_reg.dst(w.dy, B, D, w.pk_dy);
   const int eb = embed_bwd_blocks(B);
   FBN_REQUIRE((size_t)eb * p->cate_rows * D <= w.partial_floats, FBN_ERR_ARG, "internal: cate scratch too small");
   RC(launch_embed_senet_bwd(e, eb, st));
@@ -474,16 +509,12 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   RC(launch_senet_param_grads(w.sestat, B, w.partial, g->se_w1, g->se_b1, g->se_w2, g->se_b2, st));
   RC(colprod2(w.dln, w.xhat, B, D, w.partial, g->ln_g, g->ln_b, st));
   RC(colsum(w.dy, B, D, w.partial, g->mm_b, st));
-  RC(tl_reg.pack(w.dy, B, D, w.pk_dy));
-  RC(tl_reg.pack(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm));
   RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, st));
   // ---- embedding table rows ----
-  EmbGradArgs eg{};
-  eg.ids = w.ids; eg.seq = (b->seq_len > 0 && b->item_seq) ? w.seq : nullptr; eg.B = B; eg.L = (int)b->seq_len; eg.rows = p->item_rows;
-  eg.dXitem = w.dXitem; eg.dXhist = w.dXhist; eg.keys_in = w.keys_in; eg.keys_out = w.keys_out; eg.vals_in = w.vals_in;
-  eg.vals_out = w.vals_out; eg.row_count = row_touched ? row_touched : w.row_cnt; eg.row_off = w.row_off; eg.cub_tmp = w.cub_tmp;
-  eg.cub_bytes = w.cub_bytes; eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_partial = w.partial; eg.sumsq_out = grad_sumsq + 1;
-  RC(emb_grad_rows(eg, st));
+  EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
+  eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_out = grad_sumsq + 1;
+  if (!index_ready) RC(emb_index(eg, st));
+  RC(emb_rows(eg, st));
   if (dense_grad_flat) {
     FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");
     RC(sumsq(dense_grad_flat, dense_grad_n, w.partial, grad_sumsq, st));

@@ -86,6 +86,30 @@ __device__ __forceinline__ void operator+=(float4& a, const float4& b) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// store 4 consecutive values in tcgen05 operand format at element index `e` of a packed tensor (see PackDst in tower.h):
+// mode FBN_PREC_TF32X3: hi = x & 0xffffe000 at e, lo = x - hi at e + lo_off ; FBN_PREC_BF16: bf16 round-to-nearest
+__device__ __forceinline__ void store_packed4(void* base, long long lo_off, int mode, long long e, const float4& v) {
+  if (mode == FBN_PREC_TF32X3) {
+    float* d = static_cast<float*>(base);
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    st4(d + e, h);
+    st4(d + lo_off + e, v - h);
+  } else if (mode == FBN_PREC_BF16) {
+    unsigned short* d = static_cast<unsigned short*>(base);
+    auto rn = [](float x) {  // fp32 -> bf16 round-to-nearest-even (finite inputs)
+      unsigned u = __float_as_uint(x);
+      u += 0x7fffu + ((u >> 16) & 1u);
+      return (unsigned)(u >> 16);
+    };
+    uint2 o;
+    o.x = rn(v.x) | (rn(v.y) << 16);
+    o.y = rn(v.z) | (rn(v.w) << 16);
+    *reinterpret_cast<uint2*>(d + e) = o;
+  }
+}
+
 // tensor.long() on the reference's index columns (src/model_fibinet.py:140-143): truncation toward
 // zero for floating inputs; exact for |id| < 2^53 (float64) as the loader delivers them.
 __device__ __forceinline__ long long load_index(const void* p, int dtype, long long i) {

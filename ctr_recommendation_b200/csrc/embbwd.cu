@@ -13,13 +13,14 @@
 
 namespace fbn {
 
-__global__ void emb_build_keys_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seq, long long B, int L,
-                                      long long rows, int32_t* __restrict__ keys, int32_t* __restrict__ vals,
+__global__ void emb_build_keys_kernel(const void* __restrict__ item_id, int idx_dtype, const void* __restrict__ seq, int seq_dtype,
+                                      long long B, int L, long long rows, int32_t* __restrict__ keys, int32_t* __restrict__ vals,
                                       int32_t* __restrict__ row_count) {
   const long long n = B * (1 + (seq ? L : 0));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int key = i < B ? ids[i * 4] : seq[i - B];
-    if (key <= 0 || key >= rows) key = (int)rows;  // padding -> sentinel
+    const long long raw = i < B ? load_index(item_id, idx_dtype, i) : load_index(seq, seq_dtype, i - B);
+    int key = (int)min(max(raw, 0LL), rows - 1);   // same clamp as the forward gather
+    if (key <= 0) key = (int)rows;                 // padding -> sentinel beyond the last row
     else atomicAdd(row_count + key, 1);            // integer atomics: order-independent result
     keys[i] = key;
     vals[i] = (int)i;
@@ -39,17 +40,23 @@ __global__ void __launch_bounds__(ER_WARPS * 32) emb_rows_kernel(const int32_t* 
   const long long r = (long long)blockIdx.x * ER_WARPS + warp;
   float sq = 0.f;
   if (r < rows) {
-    const int cnt = row_count[r];
+    const int cnt = __ldg(row_count + r), off = __ldg(row_off + r);   // independent loads, one latency
     if (cnt > 0) {
-      const int off = row_off[r];
       float4 acc = f4(0.f);
       for (int o0 = 0; o0 < cnt; o0 += 32) {
-        const int mine = (o0 + lane < cnt) ? src[off + o0 + lane] : 0;
+        const int mine = (o0 + lane < cnt) ? __ldg(src + off + o0 + lane) : 0;
         const int n = min(32, cnt - o0);
-        for (int k = 0; k < n; ++k) {
-          const int s = __shfl_sync(0xffffffffu, mine, k);
-          const float* p = s < B ? dXitem + (long long)s * D : dXhist + ((long long)(s - B) / L) * D;
-          acc += ld4(p + 4 * lane);
+        for (int k = 0; k < n; k += 8) {            // 8 independent 512-byte row loads in flight, summed in source order
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int s = __shfl_sync(0xffffffffu, mine, min(k + u, 31));
+            const float* p = s < B ? dXitem + (long long)s * D : dXhist + ((long long)(s - B) / L) * D;
+            v[u] = (k + u < n) ? ld4(p + 4 * lane) : f4(0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (k + u < n) acc += v[u];
         }
       }
       st4(grad + r * D + 4 * lane, acc);
@@ -97,12 +104,15 @@ size_t emb_sort_temp_bytes(long long n, long long rows) {
 
 int emb_grad_partial_count(long long rows) { return (int)cdiv(rows, ER_WARPS); }
 
-int emb_grad_rows(const EmbGradArgs& a, cudaStream_t st) {
+// stage 1 (depends on the batch ids only -- can run concurrently with the forward pass): occurrences keyed by table row,
+// stably sorted, per-row counts and offsets
+int emb_index(const EmbGradArgs& a, cudaStream_t st) {
   const long long n = a.B * (1 + (a.seq ? a.L : 0));
   FBN_REQUIRE(n < (1LL << 31) && a.rows < (1LL << 30), FBN_ERR_SHAPE, "embedding backward: too many occurrences");
   FBN_CHECK_CUDA(cudaMemsetAsync(a.row_count, 0, sizeof(int32_t) * a.rows, st));
   int blocks = (int)std::min<long long>(cdiv(n, 256), 8LL * num_sms());
-  emb_build_keys_kernel<<<std::max(blocks, 1), 256, 0, st>>>(a.ids, a.seq, a.B, a.L, a.rows, a.keys_in, a.vals_in, a.row_count);
+  emb_build_keys_kernel<<<std::max(blocks, 1), 256, 0, st>>>(a.item_id, a.idx_dtype, a.seq, a.seq_dtype, a.B, a.L, a.rows, a.keys_in,
+                                                             a.vals_in, a.row_count);
   FBN_CHECK_LAUNCH();
   size_t bytes = a.cub_bytes;
   FBN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(a.cub_tmp, bytes, (const int32_t*)a.keys_in, a.keys_out, (const int32_t*)a.vals_in,
@@ -111,6 +121,11 @@ int emb_grad_rows(const EmbGradArgs& a, cudaStream_t st) {
   bytes = a.cub_bytes;
   FBN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(a.cub_tmp, bytes, (const int32_t*)a.row_count, a.row_off, (int)a.rows, st));
   g_launches += 2;  // cub: scan init + scan
+  return FBN_OK;
+}
+
+// stage 2: one warp per table row sums its occurrences in source order
+int emb_rows(const EmbGradArgs& a, cudaStream_t st) {
   const int nb = emb_grad_partial_count(a.rows);
   emb_rows_kernel<<<nb, ER_WARPS * 32, 0, st>>>(a.row_count, a.row_off, a.vals_out, a.dXitem, a.dXhist, a.B, a.L > 0 ? a.L : 1, a.rows,
                                                 a.zero_fill, a.grad, a.sumsq_partial);

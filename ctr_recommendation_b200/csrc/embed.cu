@@ -15,7 +15,7 @@
 namespace fbn {
 
 constexpr int EMB_WARPS = 8;
-constexpr int EMB_SPW = 4;  // samples per warp per iteration (register-blocks the projection)
+constexpr int EMB_SPW = 2;  // samples per warp per iteration (register-blocks the projection)
 
 
 // smem: Wt[128][128] (k-major copy of mm_w so lane j reads W[4j..4j+3][k] as one float4)
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
           xm = ld4(a.mm_table + iid * D + 4 * lane);
           if (a.save) st4(a.xmm + b * D + 4 * lane, xm);   // wgrad of mm_proj.0.weight needs the gathered rows
         }
+        if (a.save && a.pkX.mode) store_packed4(a.pkX.base, a.pkX.lo_off, a.pkX.mode, b * D + 4 * lane, xm);
         int nvalid = 0;
         float4 acc = f4(0.f);
         if (a.seq != nullptr) {
@@ -82,24 +83,20 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
               if (a.save) a.seq32[b * a.L + l0 + lane] = myid;
             }
             const int n = min(32, a.L - l0);
-            // batches of 4 independent row loads in flight, accumulated in sequence order (ref :172)
-            for (int l = 0; l < n; l += 4) {
-              int id0 = __shfl_sync(0xffffffffu, myid, l);
-              int id1 = __shfl_sync(0xffffffffu, myid, min(l + 1, 31));
-              int id2 = __shfl_sync(0xffffffffu, myid, min(l + 2, 31));
-              int id3 = __shfl_sync(0xffffffffu, myid, min(l + 3, 31));
-              if (l + 1 >= n) id1 = 0;
-              if (l + 2 >= n) id2 = 0;
-              if (l + 3 >= n) id3 = 0;
-              float4 r0 = f4(0.f), r1 = f4(0.f), r2 = f4(0.f), r3 = f4(0.f);
-              if (id0) r0 = ld4(a.item_emb + (long long)id0 * D + 4 * lane);
-              if (id1) r1 = ld4(a.item_emb + (long long)id1 * D + 4 * lane);
-              if (id2) r2 = ld4(a.item_emb + (long long)id2 * D + 4 * lane);
-              if (id3) r3 = ld4(a.item_emb + (long long)id3 * D + 4 * lane);
-              if (id0) { acc += r0; ++nvalid; }
-              if (id1) { acc += r1; ++nvalid; }
-              if (id2) { acc += r2; ++nvalid; }
-              if (id3) { acc += r3; ++nvalid; }
+            // batches of 8 independent row loads in flight, accumulated in sequence order (ref :172)
+            for (int l = 0; l < n; l += 8) {
+              int id[8];
+              float4 r[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                id[u] = __shfl_sync(0xffffffffu, myid, min(l + u, 31));
+                if (l + u >= n) id[u] = 0;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) r[u] = id[u] ? ld4(a.item_emb + (long long)id[u] * D + 4 * lane) : f4(0.f);
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (id[u]) { acc += r[u]; ++nvalid; }
             }
           }
           cntv[s] = (float)max(nvalid, 1);           // clamp(min=1), ref :173
@@ -124,16 +121,20 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
     for (int s = 0; s < EMB_SPW; ++s) y[s] = f4(0.f);
 #pragma unroll 8
     for (int k = 0; k < D; ++k) {
-      const float4 xv = *reinterpret_cast<const float4*>(xs + k * EMB_SPW);
+      float xv[EMB_SPW];
+      if (EMB_SPW == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(xs + k * EMB_SPW);
+        xv[0] = t.x; xv[EMB_SPW - 1] = t.y;
+      } else {
+#pragma unroll
+        for (int s = 0; s < EMB_SPW; ++s) xv[s] = xs[k * EMB_SPW + s];
+      }
       const float4 wv = *reinterpret_cast<const float4*>(Wt + k * D + 4 * lane);
-      y[0].x = fmaf(xv.x, wv.x, y[0].x); y[0].y = fmaf(xv.x, wv.y, y[0].y);
-      y[0].z = fmaf(xv.x, wv.z, y[0].z); y[0].w = fmaf(xv.x, wv.w, y[0].w);
-      y[1].x = fmaf(xv.y, wv.x, y[1].x); y[1].y = fmaf(xv.y, wv.y, y[1].y);
-      y[1].z = fmaf(xv.y, wv.z, y[1].z); y[1].w = fmaf(xv.y, wv.w, y[1].w);
-      y[2].x = fmaf(xv.z, wv.x, y[2].x); y[2].y = fmaf(xv.z, wv.y, y[2].y);
-      y[2].z = fmaf(xv.z, wv.z, y[2].z); y[2].w = fmaf(xv.z, wv.w, y[2].w);
-      y[3].x = fmaf(xv.w, wv.x, y[3].x); y[3].y = fmaf(xv.w, wv.y, y[3].y);
-      y[3].z = fmaf(xv.w, wv.z, y[3].z); y[3].w = fmaf(xv.w, wv.w, y[3].w);
+#pragma unroll
+      for (int s = 0; s < EMB_SPW; ++s) {
+        y[s].x = fmaf(xv[s], wv.x, y[s].x); y[s].y = fmaf(xv[s], wv.y, y[s].y);
+        y[s].z = fmaf(xv[s], wv.z, y[s].z); y[s].w = fmaf(xv[s], wv.w, y[s].w);
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -174,11 +175,20 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
         sg[f] = sigmoidf_(acc);
       }
       float* crow = a.C + b * K1 + 4 * lane;
-      st4(crow + 1 * D, f_like[s] * sg[1]);
-      st4(crow + 2 * D, f_view[s] * sg[2]);
-      st4(crow + 3 * D, f_item[s] * sg[3]);
-      st4(crow + 4 * D, img * sg[4]);
-      st4(crow + 5 * D, f_hist[s] * sg[5]);
+      const float4 v1 = f_like[s] * sg[1], v2 = f_view[s] * sg[2], v3 = f_item[s] * sg[3], v4 = img * sg[4], v5 = f_hist[s] * sg[5];
+      st4(crow + 1 * D, v1);
+      st4(crow + 2 * D, v2);
+      st4(crow + 3 * D, v3);
+      st4(crow + 4 * D, v4);
+      st4(crow + 5 * D, v5);
+      if (a.pkC.mode) {     // the GEMMs read this copy (tf32 hi|lo or bf16): no separate pack pass over C
+        const long long e = b * K1 + 4 * lane;
+        store_packed4(a.pkC.base, a.pkC.lo_off, a.pkC.mode, e + 1 * D, v1);
+        store_packed4(a.pkC.base, a.pkC.lo_off, a.pkC.mode, e + 2 * D, v2);
+        store_packed4(a.pkC.base, a.pkC.lo_off, a.pkC.mode, e + 3 * D, v3);
+        store_packed4(a.pkC.base, a.pkC.lo_off, a.pkC.mode, e + 4 * D, v4);
+        store_packed4(a.pkC.base, a.pkC.lo_off, a.pkC.mode, e + 5 * D, v5);
+      }
       if (a.save) {
         float* xrow = a.X5 + b * (NA * D) + 4 * lane;
         st4(xrow + 0 * D, f_like[s]);
@@ -210,7 +220,7 @@ int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
   }
   const long long ngroups = (a.B + EMB_SPW - 1) / EMB_SPW;
   long long blocks = (ngroups + EMB_WARPS - 1) / EMB_WARPS;
-  const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (80 KB smem each)
+  const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (72 KB smem each)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   embed_senet_fwd_kernel<<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);
@@ -325,7 +335,9 @@ __global__ void __launch_bounds__(EBW_WARPS * 32) embed_senet_bwd_kernel(EmbedBw
     const float m1 = warp_sum(hsum4(dxh)) * (1.0f / D);
     const float m2 = warp_sum(hsum4(dxh * xh)) * (1.0f / D);
     const float rs = a.rstd[b];
-    st4(a.dy + b * D + 4 * lane, (dxh - f4(m1) - xh * m2) * rs);
+    const float4 dyv = (dxh - f4(m1) - xh * m2) * rs;
+    st4(a.dy + b * D + 4 * lane, dyv);
+    if (a.pkdy.mode) store_packed4(a.pkdy.base, a.pkdy.lo_off, a.pkdy.mode, b * D + 4 * lane, dyv);
   }
   __syncthreads();
   // fixed-order reduction of the warps' private accumulators -> one partial per CTA

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "tower.h"
+
 namespace fbn {
 
 struct EmbedFwdArgs {
@@ -16,6 +18,8 @@ struct EmbedFwdArgs {
   int save;            // write the tensors backward needs
   int32_t* ids; int32_t* seq32;
   float* X5; float* sgate; float* xhat; float* xmm; float* rstd; float* cnt; float* C;
+  PackDst pkC;         // packed copy of the field blocks of C
+  PackDst pkX;         // packed copy of the item_emb_d128 rows (B,128)
 };
 
 struct EmbedBwdArgs {
@@ -25,6 +29,7 @@ struct EmbedBwdArgs {
   const float* se_w1; const float* se_b1; const float* se_w2; const float* ln_g;
   long long B; int cate_rows;
   float* dXitem; float* dXhist; float* dln; float* dy; float* sestat;
+  PackDst pkdy;
   float* cate_partial;  // (gridDim.x, cate_rows, 128)
 };
 

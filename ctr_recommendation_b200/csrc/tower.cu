@@ -9,7 +9,7 @@ namespace fbn {
 // ------------------------------------------------------------------------------------------
 // deterministic column reductions over the batch: partial[chunk][q][N]
 // ------------------------------------------------------------------------------------------
-enum { OP_SUM = 0, OP_SQDEV = 1, OP_BNBWD = 2, OP_HEADBWD = 3, OP_PROD2 = 4 };
+enum { OP_SUM = 0, OP_SQDEV = 1, OP_BNBWD = 2, OP_HEADBWD = 3, OP_PROD2 = 4, OP_SHIFT2 = 5 };
 
 struct ColArgs {
   const float* X; const float* Y; const float* Z;  // (B,N) operands (meaning depends on OP)
@@ -28,6 +28,10 @@ __device__ __forceinline__ void col_terms(const ColArgs& a, long long r, int c, 
   } else if (OP == OP_SQDEV) {
     const float4 d = ld4s(a.X + o) - ld4(a.v0 + c);
     q0 += d * d;
+  } else if (OP == OP_SHIFT2) {   // sums of (x - pivot) and (x - pivot)^2, pivot = row 0 of the same column
+    const float4 d = ld4s(a.X + o) - ld4(a.v0 + c);
+    q0 += d;
+    q1 += d * d;
   } else if (OP == OP_PROD2) {
     const float4 x = ld4s(a.X + o);
     q0 += x * ld4s(a.Y + o);
@@ -153,18 +157,41 @@ __global__ void __launch_bounds__(256) bn_var_final_kernel(const float* __restri
   }
 }
 
+// single-pass batch statistics: with the pivot p_c = H[0][c] (a sample of the column, so |mean - p| ~ sigma and the
+// subtraction below loses about one bit), mean = p + S1/B and var = S2/B - (S1/B)^2, finalised in fp64
+__global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __restrict__ partial, int chunks, int N, long long B,
+                                                             const float* __restrict__ pivot, float* mean, float* rstd,
+                                                             float* run_mean, float* run_var) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= N) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = lane; k < chunks; k += 32) {
+    s1 += (double)partial[((long long)k * 2 + 0) * N + c];
+    s2 += (double)partial[((long long)k * 2 + 1) * N + c];
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane != 0) return;
+  const double m1 = s1 / (double)B;
+  const double varb = fmax(s2 / (double)B - m1 * m1, 0.0);
+  const float mu = (float)((double)pivot[c] + m1);
+  mean[c] = mu;
+  rstd[c] = 1.0f / sqrtf((float)varb + 1e-5f);
+  if (run_mean) {
+    const float unb = B > 1 ? (float)(varb * (double)B / (double)(B - 1)) : (float)varb;
+    run_mean[c] = (1.0f - 0.1f) * run_mean[c] + 0.1f * mu;
+    run_var[c] = (1.0f - 0.1f) * run_var[c] + 0.1f * unb;
+  }
+}
+
 int bn_train_stats(const float* H, long long B, int N, float* partial, float* mean, float* rstd, float* run_mean, float* run_var,
                    cudaStream_t st) {
-  ColArgs a{}; a.X = H; a.B = B; a.N = N; a.partial = partial;
+  ColArgs a{}; a.X = H; a.v0 = H; a.B = B; a.N = N; a.partial = partial;
   const int ch = col_chunks(B, N);
-  int rc = launch_colreduce<OP_SUM, 1>(a, ch, st);
+  int rc = launch_colreduce<OP_SHIFT2, 2>(a, ch, st);
   if (rc) return rc;
-  rc = launch_colfinal(partial, ch, N, 1, (float)(1.0 / (double)B), mean, nullptr, nullptr, st);
-  if (rc) return rc;
-  a.v0 = mean;
-  rc = launch_colreduce<OP_SQDEV, 1>(a, ch, st);
-  if (rc) return rc;
-  bn_var_final_kernel<<<(N + 7) / 8, 256, 0, st>>>(partial, ch, N, B, mean, rstd, run_mean, run_var);
+  bn_stats_final_kernel<<<(N + 7) / 8, 256, 0, st>>>(partial, ch, N, B, H, mean, rstd, run_mean, run_var);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -209,21 +236,22 @@ __device__ __forceinline__ float4 bn_relu_drop4(float4 h, float4 mean, float4 rs
 
 __global__ void bn_act_kernel(const float* __restrict__ H, const float* __restrict__ mean, const float* __restrict__ rstd,
                               const float* __restrict__ g, const float* __restrict__ b, long long B, int N, DropArgs d,
-                              float* __restrict__ A) {
+                              float* __restrict__ A, PackDst pk) {
   const long long total4 = B * N / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4;
     const int c = (int)(e % N);
     const float4 y = bn_relu_drop4(ld4s(H + e), ld4(mean + c), ld4(rstd + c), ld4(g + c), ld4(b + c), d, e, d.mask);
     st4(A + e, y);
+    if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, e, y);     // pitch == N
   }
 }
 
 int bn_act(const float* H, const float* mean, const float* rstd, const float* g, const float* b, long long B, int N,
-           const DropArgs& d, float* A, cudaStream_t st) {
+           const DropArgs& d, float* A, PackDst pk, cudaStream_t st) {
   const long long total4 = B * N / 4;
   int blocks = (int)std::min<long long>((total4 + 255) / 256, 8LL * num_sms());
-  bn_act_kernel<<<std::max(blocks, 1), 256, 0, st>>>(H, mean, rstd, g, b, B, N, d, A);
+  bn_act_kernel<<<std::max(blocks, 1), 256, 0, st>>>(H, mean, rstd, g, b, B, N, d, A, pk);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -318,7 +346,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dA, const float* _
                                     const float* __restrict__ A, const float* __restrict__ Hd, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ g, const float* __restrict__ dgamma,
                                     const float* __restrict__ dbeta, long long B, int N, float scale, int train,
-                                    float* __restrict__ dH) {
+                                    float* __restrict__ dH, PackDst pk) {
   const long long total4 = B * N / 4;
   const float invB = 1.0f / (float)B;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
@@ -340,16 +368,17 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dA, const float* _
       out = gr * dY;
     }
     st4(dH + e, out);
+    if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, e, out);
   }
 }
 
 int bn_bwd_apply(const float* dA, const float* dlogit, const float* w3, const float* A, const float* Hd, const float* mean,
                  const float* rstd, const float* g, const float* dgamma, const float* dbeta, long long B, int N, float scale,
-                 int train, float* dH, cudaStream_t st) {
+                 int train, float* dH, PackDst pk, cudaStream_t st) {
   const long long total4 = B * N / 4;
   int blocks = (int)std::min<long long>((total4 + 255) / 256, 8LL * num_sms());
   bn_bwd_apply_kernel<<<std::max(blocks, 1), 256, 0, st>>>(dA, dlogit, w3, A, Hd, mean, rstd, g, dgamma, dbeta, B, N, scale, train,
-                                                           dH);
+                                                           dH, pk);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -367,7 +396,7 @@ __host__ __device__ constexpr int active_q(int i, int j) {  // index among pairs
 }
 
 template <int TYPE>
-__global__ void __launch_bounds__(256) bilinear_pairs_fwd_kernel(float* __restrict__ C, const float* __restrict__ T, long long B) {
+__global__ void __launch_bounds__(256) bilinear_pairs_fwd_kernel(float* __restrict__ C, const float* __restrict__ T, long long B, PackDst pk) {
   constexpr int nT = TYPE == FBN_BILINEAR_INTERACTION ? 10 : 4;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -388,16 +417,17 @@ __global__ void __launch_bounds__(256) bilinear_pairs_fwd_kernel(float* __restri
         else if (TYPE == FBN_BILINEAR_EACH) p = t[i - 1] * v[j];
         else p = t[active_q(i, j)] * v[j];
         st4(crow + pair_block(i, j) * D, p);
+        if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, b * K1 + pair_block(i, j) * D + 4 * lane, p);
       }
   }
 }
 
-int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, cudaStream_t st) {
+int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, PackDst pk, cudaStream_t st) {
   int blocks = (int)std::min<long long>((B + 7) / 8, 8LL * num_sms());
   blocks = std::max(blocks, 1);
-  if (type == FBN_BILINEAR_ALL) bilinear_pairs_fwd_kernel<FBN_BILINEAR_ALL><<<blocks, 256, 0, st>>>(C, T, B);
-  else if (type == FBN_BILINEAR_EACH) bilinear_pairs_fwd_kernel<FBN_BILINEAR_EACH><<<blocks, 256, 0, st>>>(C, T, B);
-  else bilinear_pairs_fwd_kernel<FBN_BILINEAR_INTERACTION><<<blocks, 256, 0, st>>>(C, T, B);
+  if (type == FBN_BILINEAR_ALL) bilinear_pairs_fwd_kernel<FBN_BILINEAR_ALL><<<blocks, 256, 0, st>>>(C, T, B, pk);
+  else if (type == FBN_BILINEAR_EACH) bilinear_pairs_fwd_kernel<FBN_BILINEAR_EACH><<<blocks, 256, 0, st>>>(C, T, B, pk);
+  else bilinear_pairs_fwd_kernel<FBN_BILINEAR_INTERACTION><<<blocks, 256, 0, st>>>(C, T, B, pk);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -406,7 +436,7 @@ int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, cudaStre
 template <int TYPE>
 __global__ void __launch_bounds__(256) bilinear_pairs_bwd_kernel(const float* __restrict__ C, const float* __restrict__ T,
                                                                  const float* __restrict__ dC, long long B, float* __restrict__ dT,
-                                                                 float* __restrict__ dV) {
+                                                                 float* __restrict__ dV, PackDst pk) {
   constexpr int nT = TYPE == FBN_BILINEAR_INTERACTION ? 10 : 4;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -444,16 +474,20 @@ __global__ void __launch_bounds__(256) bilinear_pairs_bwd_kernel(const float* __
 #pragma unroll
     for (int f = 1; f < NF; ++f) st4(dV + b * (NA * D) + (f - 1) * D + 4 * lane, dv[f]);
 #pragma unroll
-    for (int k = 0; k < nT; ++k) st4(dT + b * (nT * D) + k * D + 4 * lane, dt[k]);
+    for (int k = 0; k < nT; ++k) {
+      st4(dT + b * (nT * D) + k * D + 4 * lane, dt[k]);
+      if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, b * (nT * D) + k * D + 4 * lane, dt[k]);
+    }
   }
 }
 
-int bilinear_pairs_bwd(int type, const float* C, const float* T, const float* dC, long long B, float* dT, float* dV, cudaStream_t st) {
+int bilinear_pairs_bwd(int type, const float* C, const float* T, const float* dC, long long B, float* dT, float* dV, PackDst pk,
+                       cudaStream_t st) {
   int blocks = (int)std::min<long long>((B + 7) / 8, 8LL * num_sms());
   blocks = std::max(blocks, 1);
-  if (type == FBN_BILINEAR_ALL) bilinear_pairs_bwd_kernel<FBN_BILINEAR_ALL><<<blocks, 256, 0, st>>>(C, T, dC, B, dT, dV);
-  else if (type == FBN_BILINEAR_EACH) bilinear_pairs_bwd_kernel<FBN_BILINEAR_EACH><<<blocks, 256, 0, st>>>(C, T, dC, B, dT, dV);
-  else bilinear_pairs_bwd_kernel<FBN_BILINEAR_INTERACTION><<<blocks, 256, 0, st>>>(C, T, dC, B, dT, dV);
+  if (type == FBN_BILINEAR_ALL) bilinear_pairs_bwd_kernel<FBN_BILINEAR_ALL><<<blocks, 256, 0, st>>>(C, T, dC, B, dT, dV, pk);
+  else if (type == FBN_BILINEAR_EACH) bilinear_pairs_bwd_kernel<FBN_BILINEAR_EACH><<<blocks, 256, 0, st>>>(C, T, dC, B, dT, dV, pk);
+  else bilinear_pairs_bwd_kernel<FBN_BILINEAR_INTERACTION><<<blocks, 256, 0, st>>>(C, T, dC, B, dT, dV, pk);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }

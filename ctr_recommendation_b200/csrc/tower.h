@@ -5,6 +5,15 @@
 
 namespace fbn {
 
+// Optional second destination of a producer kernel: the same values in tcgen05 operand format (tf32 hi|lo or bf16),
+// element (r, c) at r * pitch + c.  mode 0 = disabled.  Lets a tensor be converted by the kernel that produces it instead
+// of a separate pack pass.
+struct PackDst {
+  void* base = nullptr;
+  long long pitch = 0, lo_off = 0;
+  int mode = 0;
+};
+
 struct DropArgs {
   float p = 0.f;                 // 0 -> no dropout
   const uint8_t* mask = nullptr; // optional explicit keep-mask (B,N) uint8
@@ -19,7 +28,7 @@ int bn_train_stats(const float* H, long long B, int N, float* partial, float* me
                    cudaStream_t st);
 int bn_eval_stats(const float* run_mean, const float* run_var, int N, float* mean, float* rstd, cudaStream_t st);
 int bn_act(const float* H, const float* mean, const float* rstd, const float* g, const float* b, long long B, int N,
-           const DropArgs& d, float* A, cudaStream_t st);
+           const DropArgs& d, float* A, PackDst pk, cudaStream_t st);
 int head_fwd(const float* H, const float* mean, const float* rstd, const float* g, const float* b, const float* w3, const float* b3,
              long long B, const DropArgs& d, float* A, float* logit, float* prob, cudaStream_t st);
 int head_bwd_stats(const float* dprob, const float* prob, const float* A2, const float* Hd2, const float* mean, const float* rstd,
@@ -29,9 +38,10 @@ int bn_bwd_stats(const float* dA, const float* A, const float* Hd, const float* 
                  float scale, float* partial, float* dgamma, float* dbeta, cudaStream_t st);
 int bn_bwd_apply(const float* dA, const float* dlogit, const float* w3, const float* A, const float* Hd, const float* mean,
                  const float* rstd, const float* g, const float* dgamma, const float* dbeta, long long B, int N, float scale,
-                 int train, float* dH, cudaStream_t st);
-int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, cudaStream_t st);
-int bilinear_pairs_bwd(int type, const float* C, const float* T, const float* dC, long long B, float* dT, float* dV, cudaStream_t st);
+                 int train, float* dH, PackDst pk, cudaStream_t st);
+int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, PackDst pk, cudaStream_t st);
+int bilinear_pairs_bwd(int type, const float* C, const float* T, const float* dC, long long B, float* dT, float* dV, PackDst pk,
+                       cudaStream_t st);
 int reduce_splits(const float* partial, int parts, long long M, long long N, long long part_stride, unsigned long long nmask, float* out,
                   cudaStream_t st);
 
@@ -43,8 +53,8 @@ int embed_bwd_blocks(long long B);
 
 // embbwd.cu : deterministic sorted-segment embedding backward
 struct EmbGradArgs {
-  const int32_t* ids;      // (B,4) canonical item_id in .x
-  const int32_t* seq;      // (B,L) or nullptr
+  const void* item_id; int idx_dtype;   // raw batch columns (the index does not depend on the forward pass)
+  const void* seq; int seq_dtype;       // (B,L) or nullptr
   long long B; int L; long long rows;
   const float* dXitem;     // (B,128)
   const float* dXhist;     // (B,128), already divided by the history count
@@ -57,7 +67,8 @@ struct EmbGradArgs {
   float* sumsq_partial;    // per-CTA partial sums of squares
   float* sumsq_out;        // (1)
 };
-int emb_grad_rows(const EmbGradArgs& a, cudaStream_t st);
+int emb_index(const EmbGradArgs& a, cudaStream_t st);
+int emb_rows(const EmbGradArgs& a, cudaStream_t st);
 size_t emb_sort_temp_bytes(long long n, long long rows);
 int emb_grad_partial_count(long long rows);
 

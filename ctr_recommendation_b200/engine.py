@@ -87,6 +87,7 @@ class TrainStep:
         self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(model._item_grad.numel()), 16), dtype=torch.float32,
                                          device=dev)
+        self._side = torch.cuda.Stream(device=dev)
         self.loss_weight = 1.0 / self.world
         self._bs = self._batch_struct()
         self._graphs = None
@@ -112,17 +113,26 @@ class TrainStep:
         return bs
 
     def _fwd_bwd(self):
-        m, lib, st = self.model, self.lib, _lib.stream_ptr()
+        m, lib = self.model, self.lib
         P, G = m._params_struct(), m._grads_struct()
         ws = self.ws
+        # the occurrence index of the embedding backward only needs the batch ids: build it on a side stream while the
+        # forward pass runs (fork / join, also inside graph capture)
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            _lib.check(lib.fbn_embed_index(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), _lib.ptr(m._row_touched),
+                                           _lib.stream_ptr()), "fbn_embed_index")
+        st = _lib.stream_ptr()
         _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
                                    _lib.ptr(self.step_counter), _lib.ptr(self.prob), st), "fbn_forward")
         _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
                                     _lib.ptr(self.dprob), st), "fbn_bce_loss")
         dense_table = m._dense_table_grad
+        cur.wait_stream(self._side)            # join: the index is ready before the table gradient is summed
         _lib.check(lib.fbn_backward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, _lib.ptr(self.dprob),
                                     C.byref(G), _lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(m._item_grad),
-                                    _lib.ptr(m._row_touched), 1 if dense_table else 0, _lib.ptr(m._grad_sumsq), st), "fbn_backward")
+                                    _lib.ptr(m._row_touched), 1 if dense_table else 0, 1, _lib.ptr(m._grad_sumsq), st), "fbn_backward")
 
     def _update(self):
         m, o, lib, st = self.model, self.opt, self.lib, _lib.stream_ptr()

@@ -361,7 +361,7 @@ class MM_FiBiNET(nn.Module):
         P, G = self._params_struct(), self._grads_struct()
         rc = lib.fbn_backward(C.byref(P), C.byref(cur["bs"]), _lib.ptr(cur["ws"]), cur["ws"].numel(), int(cur["train"]),
                               cur["p_drop"], _lib.ptr(dprob), C.byref(G), _lib.ptr(self._gflat), self._gflat.numel(),
-                              _lib.ptr(self._item_grad), _lib.ptr(self._row_touched), 0 if (fused and not self._dense_table_grad) else 1,
+                              _lib.ptr(self._item_grad), _lib.ptr(self._row_touched), 0 if (fused and not self._dense_table_grad) else 1, 0,
                               _lib.ptr(self._grad_sumsq), _lib.stream_ptr())
         _lib.check(rc, "fbn_backward")
         if accumulate:

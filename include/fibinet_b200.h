@@ -146,8 +146,14 @@ int fbn_embed_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, siz
  * address, normally the flat buffer all pointers of g point into), item_emb grad] for the global clip. */
 int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train,
                  float dropout_p, const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat,
-                 int64_t dense_grad_n, float* item_grad, int32_t* row_touched, int zero_fill,
+                 int64_t dense_grad_n, float* item_grad, int32_t* row_touched, int zero_fill, int index_ready,
                  float* grad_sumsq, fbn_stream_t stream);
+
+/* The occurrence index fbn_backward needs for the embedding gradient (stable sort of the B + B*L row ids, per-row
+ * counts and offsets).  It depends on the batch ids only: run it on a second stream concurrently with fbn_forward and
+ * pass index_ready = 1 to fbn_backward (same row_touched pointer), or pass index_ready = 0 and let fbn_backward build it. */
+int fbn_embed_index(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int32_t* row_touched,
+                    fbn_stream_t stream);
 
 /* Fused BCELoss(mean) forward + loss_scale * d(loss)/d(prob) (torch semantics: log clamped at -100,
  * backward divides by max(p(1-p),1e-12)); loss_out (1,) / dprob_out (B,) may be NULL. */
