@@ -46,16 +46,16 @@ __global__ void __launch_bounds__(ER_WARPS * 32) emb_rows_kernel(const int32_t* 
       for (int o0 = 0; o0 < cnt; o0 += 32) {
         const int mine = (o0 + lane < cnt) ? __ldg(src + off + o0 + lane) : 0;
         const int n = min(32, cnt - o0);
-        for (int k = 0; k < n; k += 8) {            // 8 independent 512-byte row loads in flight, summed in source order
-          float4 v[8];
+        for (int k = 0; k < n; k += 4) {            // 4 independent 512-byte row loads in flight, summed in source order
+          float4 v[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int s = __shfl_sync(0xffffffffu, mine, min(k + u, 31));
             const float* p = s < B ? dXitem + (long long)s * D : dXhist + ((long long)(s - B) / L) * D;
             v[u] = (k + u < n) ? ld4(p + 4 * lane) : f4(0.f);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < 4; ++u)
             if (k + u < n) acc += v[u];
         }
       }

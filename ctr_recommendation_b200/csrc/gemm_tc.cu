@@ -36,6 +36,9 @@ struct TcArgs {
   int splits; long long strideSplit;
   unsigned long long kmask, nmask;
   int accumulate;
+  // batched launch (blockIdx.z = batch * splits + split): per-batch TMA coordinate offsets and output stride
+  int a_bc = 0, a_br = 0, b_bc = 0, b_br = 0;
+  long long strideC = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -135,6 +138,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Epilogue store: each thread holds 128 consecutive fp32 of ONE output row (TMEM lane = row), which would make every
+// store instruction of a warp touch 32 different rows (16 B each).  The warp instead transposes its 32 x 128 block through
+// shared memory (the pipeline stages are idle by then) and writes full 512-byte row segments, one row per instruction.
+constexpr int EPI_PITCH = 132;                      // floats per staged row (+4 pad)
+constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH * 4;  // 16.5 KB per epilogue warp
+
+__device__ __forceinline__ void epilogue_store(const float (&acc)[128], float* stage, int lane, long long row0, long long M,
+                                               float* cbase, long long ldc, const float* bias, int accumulate) {
+#pragma unroll
+  for (int j = 0; j < 128; j += 4)
+    *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  __syncwarp();
+  const float4 bv = bias ? ld4(bias + 4 * lane) : f4(0.f);
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    if (row0 + r >= M) break;
+    float4 o = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + 4 * lane) + bv;
+    float* cp = cbase + (long long)r * ldc + 4 * lane;
+    if (accumulate) o += *reinterpret_cast<const float4*>(cp);
+    st4(cp, o);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the GEMM kernel
 // ------------------------------------------------------------------------------------------------
@@ -169,8 +195,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM, sp = blockIdx.z;
+  const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM, sp = blockIdx.z % g.splits, bi = blockIdx.z / g.splits;
   if (g.nmask != ~0ull && !((g.nmask >> (n0 / 128)) & 1ull)) return;
+  const int acol = bi * g.a_bc, arow = bi * g.a_br, bcol = bi * g.b_bc, brow = bi * g.b_br;
 
   // K blocks of this split (contiguous range); blocks inside structurally-zero 128-column groups are skipped
   const int kblocks = (int)((g.K + Cfg::BK - 1) / Cfg::BK);
@@ -221,18 +248,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           uint8_t* sa = st + p * Cfg::TILE_BYTES;                       // stage = [A parts | B parts]
           uint8_t* sb = st + (Cfg::NPART + p) * Cfg::TILE_BYTES;
           if (!A_MN) {
-            tma_load_2d(sa, &tm.a[p], full + s, kc, m0);                // box: BK elements of K x 128 rows of M
+            tma_load_2d(sa, &tm.a[p], full + s, kc + acol, m0 + arow);  // box: BK elements of K x 128 rows of M
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BM / Cfg::EPB; ++j)                   // boxes: 128 B of M x BK rows of K
-              tma_load_2d(sa + j * Cfg::BOX_MN_BYTES, &tm.a[p], full + s, m0 + j * Cfg::EPB, kc);
+              tma_load_2d(sa + j * Cfg::BOX_MN_BYTES, &tm.a[p], full + s, m0 + j * Cfg::EPB + acol, kc + arow);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tm.b[p], full + s, kc, n0);
+            tma_load_2d(sb, &tm.b[p], full + s, kc + bcol, n0 + brow);
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BN / Cfg::EPB; ++j)
-              tma_load_2d(sb + j * Cfg::BOX_MN_BYTES, &tm.b[p], full + s, n0 + j * Cfg::EPB, kc);
+              tma_load_2d(sb + j * Cfg::BOX_MN_BYTES, &tm.b[p], full + s, n0 + j * Cfg::EPB + bcol, kc + brow);
           }
         }
         ++it;
@@ -305,15 +332,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_before();
       mbar_arrive(tempty + buf);
     }
-    if (row < g.M) {
-      float* crow = g.C + (long long)sp * g.strideSplit + row * g.ldc + n0;
-#pragma unroll
-      for (int j = 0; j < TC_BN; j += 4) {
-        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        if (g.bias) o += ld4(g.bias + n0 + j);
-        if (g.accumulate) o += *reinterpret_cast<const float4*>(crow + j);
-        st4(crow + j, o);
-      }
+    {
+      const long long row0 = (long long)m0 + q * 32;
+      float* cbase = g.C + (long long)bi * g.strideC + (long long)sp * g.strideSplit + row0 * g.ldc + n0;
+      epilogue_store(acc, reinterpret_cast<float*>(smem + (warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
+                     g.bias ? g.bias + n0 : nullptr, g.accumulate);
     }
   }
   tc_fence_before();
@@ -527,15 +550,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
     }
     const int ncol0 = n0 + half * 128;
     const bool col_on = ncol0 < g.N && (g.nmask == ~0ull || ((g.nmask >> (ncol0 / 128)) & 1ull));
-    if (row < g.M && col_on) {
-      float* crow = g.C + (long long)sp * g.strideSplit + row * g.ldc + ncol0;
-#pragma unroll
-      for (int j = 0; j < 128; j += 4) {
-        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        if (g.bias) o += ld4(g.bias + ncol0 + j);
-        if (g.accumulate) o += *reinterpret_cast<const float4*>(crow + j);
-        st4(crow + j, o);
-      }
+    if (col_on) {
+      const long long row0 = (long long)m0 + q * 32;
+      float* cbase = g.C + (long long)sp * g.strideSplit + row0 * g.ldc + ncol0;
+      epilogue_store(acc, reinterpret_cast<float*>(smem + (warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
+                     g.bias ? g.bias + ncol0 : nullptr, g.accumulate);
     }
   }
   tc_fence_before();
@@ -702,6 +721,37 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
   const bool b_mn = g.b_t == 0;   // B stored (K,N)
   uint8_t* sp = static_cast<uint8_t*>(scratch);
   size_t left = scratch_bytes;
+  // batched launch: pre-packed operands whose batch stride is a (row, column) offset inside one packed tensor become
+  // TMA coordinate offsets, so all batch x split CTAs run in ONE grid (the four bilinear transforms / weight gradients)
+  if (g.batch > 1 && g.batch <= 64 && g.pkA.data && g.pkB.data && g.N == TC_BN) {
+    const long long ra = a_mn ? g.K : g.M, ca = a_mn ? g.M : g.K, rb = b_mn ? g.K : g.N, cb = b_mn ? g.N : g.K;
+    const long long a_br = g.strideA / g.pkA.pitch, a_bc = g.strideA % g.pkA.pitch;
+    const long long b_br = g.strideB / g.pkB.pitch, b_bc = g.strideB % g.pkB.pitch;
+    const bool ok = (a_mn || a_bc == 0 || g.K % Cfg::BK == 0) && (b_mn || b_bc == 0 || g.K % Cfg::BK == 0) &&
+                    a_bc + ca <= g.pkA.pitch + (a_bc ? 0 : 0) && b_bc + cb <= g.pkB.pitch;
+    if (ok) {
+      TcMaps maps;
+      const long long nb1 = g.batch - 1;
+      for (int p = 0; p < Cfg::NPART; ++p) {
+        int rc = make_map(&maps.a[p], MODE, static_cast<uint8_t*>(g.pkA.data) + (size_t)p * g.pkA.lo_off * Cfg::ESZ, ra + nb1 * a_br,
+                          std::min(ca + nb1 * a_bc, g.pkA.pitch), g.pkA.pitch, a_mn);
+        if (rc) return rc;
+        rc = make_map(&maps.b[p], MODE, static_cast<uint8_t*>(g.pkB.data) + (size_t)p * g.pkB.lo_off * Cfg::ESZ, rb + nb1 * b_br,
+                      std::min(cb + nb1 * b_bc, g.pkB.pitch), g.pkB.pitch, b_mn);
+        if (rc) return rc;
+      }
+      if (Cfg::NPART == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
+      TcArgs t;
+      t.C = g.C; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
+      t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
+      t.a_bc = (int)a_bc; t.a_br = (int)a_br; t.b_bc = (int)b_bc; t.b_br = (int)b_br; t.strideC = g.strideC;
+      dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)(g.splits * g.batch));
+      if (a_mn && b_mn) return launch_tc<MODE, true, true>(maps, t, grid, st);
+      if (a_mn) return launch_tc<MODE, true, false>(maps, t, grid, st);
+      if (b_mn) return launch_tc<MODE, false, true>(maps, t, grid, st);
+      return launch_tc<MODE, false, false>(maps, t, grid, st);
+    }
+  }
   for (int bi = 0; bi < g.batch; ++bi) {
     Packed pa, pb;
     const long long ra = a_mn ? g.K : g.M, ca = a_mn ? g.M : g.K;

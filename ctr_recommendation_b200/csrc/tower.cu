@@ -416,8 +416,9 @@ __global__ void __launch_bounds__(256) bilinear_pairs_fwd_kernel(float* __restri
         if (TYPE == FBN_BILINEAR_ALL) p = v[i] * t[j - 2];
         else if (TYPE == FBN_BILINEAR_EACH) p = t[i - 1] * v[j];
         else p = t[active_q(i, j)] * v[j];
-        st4(crow + pair_block(i, j) * D, p);
+        // with a tcgen05 precision only the GEMMs read the pair blocks, and they read the packed copy
         if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, b * K1 + pair_block(i, j) * D + 4 * lane, p);
+        else st4(crow + pair_block(i, j) * D, p);
       }
   }
 }
@@ -475,8 +476,8 @@ __global__ void __launch_bounds__(256) bilinear_pairs_bwd_kernel(const float* __
     for (int f = 1; f < NF; ++f) st4(dV + b * (NA * D) + (f - 1) * D + 4 * lane, dv[f]);
 #pragma unroll
     for (int k = 0; k < nT; ++k) {
-      st4(dT + b * (nT * D) + k * D + 4 * lane, dt[k]);
-      if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, b * (nT * D) + k * D + 4 * lane, dt[k]);
+      if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, b * (nT * D) + k * D + 4 * lane, dt[k]);   // only GEMMs read dT
+      else st4(dT + b * (nT * D) + k * D + 4 * lane, dt[k]);
     }
   }
 }
