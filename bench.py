@@ -38,12 +38,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("FBN_BENCH_BATCH", "16384")), help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("FBN_BENCH_BATCH", "65536")),
+                    help="per-GPU batch (BASELINE config 2 sweeps 1K-64K; 65536 is its largest point)")
     ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"])
     ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through")
+    ap.add_argument("--bilinear", default="all", choices=["all", "each", "interaction"],
+                    help="bilinear_type (BASELINE config 2 sweep); the reference hard-codes 'all'")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train = the headline train step; infer = eval forward over the batch (Prediction.py loop body, BASELINE config 3)")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
@@ -127,7 +130,7 @@ def run_ours(args):
     lib = _lib.load()
     _lib.check(lib.fbn_check_device(local), "fbn_check_device")
     torch.manual_seed(2025)
-    model = build_model({"precision": args.precision}, {"embedding_dim": 128}).to(dev).train()
+    model = build_model({"precision": args.precision, "bilinear_type": args.bilinear}, {"embedding_dim": 128}).to(dev).train()
     if world > 1:
         fdist.broadcast_parameters(model)
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
@@ -195,8 +198,18 @@ def run_ours(args):
 
     def e2e(k):
         hb, hy = pool[k % len(pool)]
+        if engine is not None and not infer:
+            # every step's inputs cross PCIe inside the timed region; the copy of batch k+1 is issued (copy stream) right
+            # after step k is launched, as a prefetching loader would
+            if not engine._prefetched:
+                engine.prefetch(hb, hy)
+            loss = engine()
+            sched.step()
+            nb, ny = pool[(k + 1) % len(pool)]
+            engine.prefetch(nb, ny)
+            return loss.item()
         if engine is not None:
-            loss = step(hb, hy)     # TrainStep copies the pinned host batch into its static device buffers
+            loss = step(hb, hy)     # Scorer copies the pinned host batch into its static device buffers
         else:
             for name, t in hb.items():
                 stage[0][name].copy_(t, non_blocking=True)
@@ -218,6 +231,9 @@ def run_ours(args):
         ms_e2e = timed(e2e, args.steps)
 
     global_batch = args.batch * world
+    bil = "bilinear all" if args.bilinear == "all" else f"bilinear {args.bilinear} [not the reference's hard-coded 'all']"
+    workload = (f"FiBiNET {'train step' if not infer else 'eval forward'} (config/fibinet_config.yaml model: D=128, 6 fields, {bil}, "
+                f"MLP 2688-512-256-1), per-GPU batch {args.batch}, history L={L_HIST}, item ids {args.id_dist}, replicated tables")
     value = global_batch * args.steps / (ms / 1e3)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
     peaks = load_peaks()
@@ -226,8 +242,7 @@ def run_ours(args):
         "metric": METRIC if not infer else "inference samples/sec FiBiNET MicroLens-shape (Prediction.py path)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
-        "config": {"workload": f"FiBiNET train step (config/fibinet_config.yaml model: D=128, 6 fields, bilinear all, MLP 2688-512-256-1), "
-                               f"per-GPU batch {args.batch}, history L={L_HIST}, item ids {args.id_dist}, replicated tables",
+        "config": {"workload": workload,
                    "global_batch": global_batch, "per_gpu_batch": args.batch, "parallelism": f"dp{world}",
                    "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
                    "l2": "working set per step (table p/m/v/grad 188 MB + activations) exceeds the 126 MB L2; inputs cycle over "

@@ -88,6 +88,13 @@ class TrainStep:
         self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(model._item_grad.numel()), 16), dtype=torch.float32,
                                          device=dev)
         self._side = torch.cuda.Stream(device=dev)
+        # input prefetch: the next batch is copied host->device on a copy stream into a staging set while the current step
+        # computes (what the reference's DataLoader workers + pin_memory would give); the step then takes it with a D2D copy
+        self._copy = torch.cuda.Stream(device=dev)
+        self._stage = None
+        self._h2d_done = torch.cuda.Event()
+        self._stage_free = torch.cuda.Event()
+        self._prefetched = False
         self.loss_weight = 1.0 / self.world
         self._bs = self._batch_struct()
         self._graphs = None
@@ -192,13 +199,36 @@ class TrainStep:
         self.hyper_dev.copy_(h, non_blocking=True)
 
     # ------------------------------------------------------------------
-    def __call__(self, batch: dict, labels: torch.Tensor) -> torch.Tensor:
-        """One optimizer step on ``batch`` (host-pinned or device tensors).  Returns the mean BCE loss of this rank's
-        shard as a 1-element device tensor (read it with .item() only when you need it)."""
+    def prefetch(self, batch: dict, labels: torch.Tensor):
+        """Start the host->device copy of the NEXT batch on the copy stream; the following ``step()`` (no arguments)
+        consumes it.  Overlaps the input transfer with the current step's kernels."""
+        if self._stage is None:
+            t = self.inp.t
+            self._stage = _StaticBatch(self.B, self.L, t["item_id"].dtype, t["item_seq"].dtype if "item_seq" in t else torch.int64,
+                                       self.dev, with_mm="item_emb_d128" in t)
+        self._copy.wait_event(self._stage_free)          # the previous staged batch has been taken
+        with torch.cuda.stream(self._copy):
+            self._stage.load(batch, labels)
+            self._h2d_done.record(self._copy)
+        self._prefetched = True
+
+    def __call__(self, batch: dict | None = None, labels: torch.Tensor | None = None) -> torch.Tensor:
+        """One optimizer step on ``batch`` (host-pinned or device tensors), or on the batch handed to ``prefetch()`` when
+        called without arguments.  Returns the mean BCE loss of this rank's shard as a 1-element device tensor (read it
+        with .item() only when you need it)."""
         m = self.model
         if not m.training:
             raise RuntimeError("TrainStep needs model.train()")
-        self.inp.load(batch, labels)
+        if batch is None:
+            if not self._prefetched:
+                raise RuntimeError("TrainStep() without a batch needs a preceding prefetch()")
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._h2d_done)
+            self.inp.load(self._stage.t, self._stage.labels)      # device-to-device, ~15 us
+            self._stage_free.record(cur)
+            self._prefetched = False
+        else:
+            self.inp.load(batch, labels)
         self._write_hyper()
         if self._use_graph and self._graphs is None:
             self._capture()
