@@ -103,6 +103,9 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   pf = std::max<size_t>(pf, (size_t)1024 * 48);
   w.partial_floats = pf;
   w.partial = (float*)take(pf * f);
+  w.partial_side = (float*)take(pf * f);
+  w.partial_cate = (float*)take((size_t)2 * 148 * 4 * MAX_CATE * D * f);
+  w.partial_embsq = (float*)take(((size_t)cdiv(rows, 8) + 1024) * f);
   const int64_t nocc = Bp * (1 + Lp);
   w.keys_in = (int32_t*)take(nocc * 4);
   w.keys_out = (int32_t*)take(nocc * 4);
@@ -171,9 +174,10 @@ struct PkReg {
       if (p >= e[i].src && p < e[i].src + e[i].n) return e[i].pk.view_cols((long long)(p - e[i].src), esz());
     return Packed();
   }
-  int run(GemmArgs g, Workspace& w) const {
+  int run(GemmArgs g, Workspace& w) const { return run_on(g, w, st); }
+  int run_on(GemmArgs g, Workspace& w, cudaStream_t s) const {
     if (on()) { g.pkA = find(g.A); g.pkB = find(g.B); }
-    return gemm(g, prec, w.gemm_scratch, w.gemm_scratch_bytes, st);
+    return gemm(g, prec, w.gemm_scratch, w.gemm_scratch_bytes, s);
   }
 };
 static thread_local PkReg tl_reg;   // rebuilt at the start of every fbn_forward / fbn_backward call
@@ -354,6 +358,45 @@ static int pick_splits_pair(long long M, long long N, long long K, unsigned long
   return best;
 }
 
+// ---- branch parallelism inside the backward pass -------------------------------------------------
+// The weight-gradient GEMMs, bias / LayerNorm / SENET / cate_emb gradient reductions are leaves of the dependency graph:
+// they run on a library-owned side stream (fork = event on the caller's stream, join before the gradient norm), so the
+// critical path is only the data-gradient chain.  Works under CUDA-graph capture (event fork/join is capturable); the
+// stream and events are created on the first non-capturing call.
+struct SideCtx {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork_ev[6], join_ev;
+  int dev = -1;
+  bool ok = false;
+};
+static SideCtx g_side;
+static int g_use_side = 1;
+
+static bool side_ready(cudaStream_t main) {
+  if (!g_use_side) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (g_side.ok && g_side.dev == dev) return true;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+  if (cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+  for (auto& e : g_side.fork_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming);
+  g_side.dev = dev; g_side.ok = true;
+  return true;
+}
+// side stream waits for everything issued so far on `main`
+static int side_fork(cudaStream_t main, int slot) {
+  FBN_CHECK_CUDA(cudaEventRecord(g_side.fork_ev[slot], main));
+  FBN_CHECK_CUDA(cudaStreamWaitEvent(g_side.s, g_side.fork_ev[slot], 0));
+  return FBN_OK;
+}
+static int side_join(cudaStream_t main) {
+  FBN_CHECK_CUDA(cudaEventRecord(g_side.join_ev, g_side.s));
+  FBN_CHECK_CUDA(cudaStreamWaitEvent(main, g_side.join_ev, 0));
+  return FBN_OK;
+}
+
 static EmbGradArgs make_emb_args(const fbn_params_t* p, const fbn_batch_t* b, Workspace& w, int32_t* row_touched) {
   EmbGradArgs eg{};
   eg.item_id = b->item_id; eg.idx_dtype = b->idx_dtype;
@@ -361,7 +404,7 @@ static EmbGradArgs make_emb_args(const fbn_params_t* p, const fbn_batch_t* b, Wo
   eg.B = b->batch; eg.L = (int)b->seq_len; eg.rows = p->item_rows;
   eg.dXitem = w.dXitem; eg.dXhist = w.dXhist; eg.keys_in = w.keys_in; eg.keys_out = w.keys_out; eg.vals_in = w.vals_in;
   eg.vals_out = w.vals_out; eg.row_count = row_touched ? row_touched : w.row_cnt; eg.row_off = w.row_off; eg.cub_tmp = w.cub_tmp;
-  eg.cub_bytes = w.cub_bytes; eg.sumsq_partial = w.partial;
+  eg.cub_bytes = w.cub_bytes; eg.sumsq_partial = w.partial_embsq;
   return eg;
 }
 
@@ -378,7 +421,7 @@ extern "C" int fbn_embed_index(const fbn_params_t* p, const fbn_batch_t* b, void
 }
 
 static int wgrad(const float* dOut, long long ldo, const float* In, long long ldi, long long B, long long M, long long N,
-                 unsigned long long nmask, int precision, Workspace& w, float* out, cudaStream_t st) {
+                 unsigned long long nmask, int precision, Workspace& w, float* out, cudaStream_t st, float* scratch) {
   // out[M,N] = dOut[B,M]^T * In[B,N]
   GemmArgs g;
   g.A = dOut; g.lda = ldo; g.a_t = 1; g.B = In; g.ldb = ldi; g.b_t = 0; g.M = M; g.N = N; g.K = B; g.ldc = N;
@@ -386,9 +429,9 @@ static int wgrad(const float* dOut, long long ldo, const float* In, long long ld
   if (precision != FBN_PREC_FP32 && M > 128 && N >= 256) g.splits = pick_splits_pair(M, N, B, nmask, w.partial_floats);
   g.nmask = nmask;
   FBN_REQUIRE((size_t)g.splits * M * N <= w.partial_floats, FBN_ERR_ARG, "internal: split-K scratch too small");
-  g.C = w.partial; g.strideSplit = M * N;
-  RC(tl_reg.run(g, w));
-  return reduce_splits(w.partial, g.splits, M, N, M * N, nmask, out, st);
+  g.C = scratch; g.strideSplit = M * N;
+  RC(tl_reg.run_on(g, w, st));
+  return reduce_splits(scratch, g.splits, M, N, M * N, nmask, out, st);
 }
 
 extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
@@ -424,8 +467,12 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
                     st));
   RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
                    tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
-  RC(colsum(w.dH2, B, H2, w.partial, g->b2, st));
-  RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, st));
+  const bool par = side_ready(st);
+  cudaStream_t ls = par ? g_side.s : st;          // stream of the leaf computations
+  float* lp = par ? w.partial_side : w.partial;   // and their scratch
+  if (par) RC(side_fork(st, 0));
+  RC(colsum(w.dH2, B, H2, lp, g->b2, ls));
+  RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, ls, lp));
   {
     GemmArgs d;  // dA1 = dH2 * w2
     d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
@@ -435,8 +482,9 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
   RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
                    tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
-  RC(colsum(w.dH1, B, H1, w.partial, g->b1, st));
-  RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, st));
+  if (par) RC(side_fork(st, 1));
+  RC(colsum(w.dH1, B, H1, lp, g->b1, ls));
+  RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, ls, lp));
   {
     GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
     d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
@@ -466,55 +514,58 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     }
   }
   {
-    // dW[idx] = sum_t V_src^T dT_t  (split-K over the batch, fixed-order reduction)
+    // dW[idx] = sum_t V_src^T dT_t  (split-K over the batch, fixed-order reduction) -- a leaf: side stream
+    if (par) RC(side_fork(st, 2));
     GemmArgs d;
     d.a_t = 1; d.lda = K1; d.b_t = 0; d.ldb = nT * D; d.M = D; d.N = D; d.K = B; d.ldc = D;
     const int S = pick_splits(nT, B);
-    d.splits = S; d.strideSplit = (long long)D * D; d.strideC = (long long)S * D * D; d.C = w.partial;
+    d.splits = S; d.strideSplit = (long long)D * D; d.strideC = (long long)S * D * D; d.C = lp;
     FBN_REQUIRE((size_t)nT * S * D * D <= w.partial_floats, FBN_ERR_ARG, "internal: bilinear scratch too small");
     if (type == FBN_BILINEAR_ALL) {
       d.A = w.C + 2 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
-      RC(tl_reg.run(d, w));
-      RC(reduce_splits(w.partial, 4 * S, D, D, (long long)D * D, ~0ull, g->bil_w, st));
+      RC(tl_reg.run_on(d, w, ls));
+      RC(reduce_splits(lp, 4 * S, D, D, (long long)D * D, ~0ull, g->bil_w, ls));
     } else if (type == FBN_BILINEAR_EACH) {
       d.A = w.C + 1 * D; d.strideA = D; d.B = w.dT; d.strideB = D; d.batch = 4;
-      RC(tl_reg.run(d, w));
-      FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * D * D, st));  // W_0 multiplies the zero field
+      RC(tl_reg.run_on(d, w, ls));
+      FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * D * D, ls));  // W_0 multiplies the zero field
       for (int t = 0; t < 4; ++t)
-        RC(reduce_splits(w.partial + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull, g->bil_w + (long long)(t + 1) * D * D, st));
+        RC(reduce_splits(lp + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull, g->bil_w + (long long)(t + 1) * D * D, ls));
     } else {
-      FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * (NF - 1) * D * D, st));  // pairs (0,j)
+      FBN_CHECK_CUDA(cudaMemsetAsync(g->bil_w, 0, sizeof(float) * (NF - 1) * D * D, ls));  // pairs (0,j)
       int q = 0;
       for (int i = 1; i < NF - 1; ++i) {
         const int nj = NF - 1 - i;
-        d.A = w.C + i * D; d.strideA = 0; d.B = w.dT + q * D; d.strideB = D; d.batch = nj; d.C = w.partial + (long long)q * S * D * D;
-        RC(tl_reg.run(d, w));
+        d.A = w.C + i * D; d.strideA = 0; d.B = w.dT + q * D; d.strideB = D; d.batch = nj; d.C = lp + (long long)q * S * D * D;
+        RC(tl_reg.run_on(d, w, ls));
         q += nj;
       }
       for (int t = 0; t < 10; ++t)
-        RC(reduce_splits(w.partial + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull,
-                         g->bil_w + (long long)(NF - 1 + t) * D * D, st));
+        RC(reduce_splits(lp + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull,
+                         g->bil_w + (long long)(NF - 1 + t) * D * D, ls));
     }
   }
   // ---- SENET + field stack + projection ----
   EmbedBwdArgs e{};
   e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
   e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.ln_g = p->ln_g; e.B = B; e.cate_rows = (int)p->cate_rows;
-  e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial;
+  e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial_cate;
   e.pkdy = tl_reg.dst(w.dy, B, D, w.pk_dy);
   const int eb = embed_bwd_blocks(B);
-  FBN_REQUIRE((size_t)eb * p->cate_rows * D <= w.partial_floats, FBN_ERR_ARG, "internal: cate scratch too small");
+  FBN_REQUIRE((size_t)eb * p->cate_rows * D <= (size_t)2 * 148 * 4 * MAX_CATE * D, FBN_ERR_ARG, "internal: cate scratch too small");
   RC(launch_embed_senet_bwd(e, eb, st));
-  RC(launch_reduce_partials(w.partial, g->cate_emb, eb, p->cate_rows * D, 0, st));
-  RC(launch_senet_param_grads(w.sestat, B, w.partial, g->se_w1, g->se_b1, g->se_w2, g->se_b2, st));
-  RC(colprod2(w.dln, w.xhat, B, D, w.partial, g->ln_g, g->ln_b, st));
-  RC(colsum(w.dy, B, D, w.partial, g->mm_b, st));
-  RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, st));
+  if (par) RC(side_fork(st, 3));
+  RC(launch_reduce_partials(w.partial_cate, g->cate_emb, eb, p->cate_rows * D, 0, ls));
+  RC(launch_senet_param_grads(w.sestat, B, lp, g->se_w1, g->se_b1, g->se_w2, g->se_b2, ls));
+  RC(colprod2(w.dln, w.xhat, B, D, lp, g->ln_g, g->ln_b, ls));
+  RC(colsum(w.dy, B, D, lp, g->mm_b, ls));
+  RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, ls, lp));
   // ---- embedding table rows ----
   EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
   eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_out = grad_sumsq + 1;
   if (!index_ready) RC(emb_index(eg, st));
   RC(emb_rows(eg, st));
+  if (par) RC(side_join(st));     // every dense gradient is complete from here on
   if (dense_grad_flat) {
     FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");
     RC(sumsq(dense_grad_flat, dense_grad_n, w.partial, grad_sumsq, st));
@@ -614,6 +665,7 @@ namespace fbn { void set_tc_pair(int on); }
 extern "C" int fbn_set_option(const char* name, int value) {
   FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
+  if (strcmp(name, "side_streams") == 0) { g_use_side = value; return FBN_OK; }
   set_error("fbn_set_option: unknown option '%s'", name);
   return FBN_ERR_ARG;
 }

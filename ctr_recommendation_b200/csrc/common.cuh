@@ -177,8 +177,11 @@ struct Workspace {
   float* dln;        // (B,128)
   float* dy;         // (B,128)
   float* sestat;     // (B,24)
-  float* partial;    // reduction partials
+  float* partial;    // reduction partials (main stream)
   size_t partial_floats;
+  float* partial_side;   // same size: scratch of the leaf computations that run on the library's side stream
+  float* partial_cate;   // per-CTA cate_emb gradient partials (produced on the main stream, reduced on the side stream)
+  float* partial_embsq;  // per-CTA sum-of-squares partials of the table gradient
   // embedding backward
   int32_t* keys_in;  // (B*(L+1))
   int32_t* keys_out;
