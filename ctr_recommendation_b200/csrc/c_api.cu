@@ -242,6 +242,45 @@ extern "C" size_t fbn_workspace_offset(int64_t batch, int64_t seq_len, int64_t i
   return (size_t)-1;
 }
 
+// ---- branch parallelism inside the backward pass -------------------------------------------------
+// The weight-gradient GEMMs, bias / LayerNorm / SENET / cate_emb gradient reductions are leaves of the dependency graph:
+// they run on a library-owned side stream (fork = event on the caller's stream, join before the gradient norm), so the
+// critical path is only the data-gradient chain.  Works under CUDA-graph capture (event fork/join is capturable); the
+// stream and events are created on the first non-capturing call.
+struct SideCtx {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork_ev[6], join_ev;
+  int dev = -1;
+  bool ok = false;
+};
+static SideCtx g_side;
+static int g_use_side = 1;
+
+static bool side_ready(cudaStream_t main) {
+  if (!g_use_side) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (g_side.ok && g_side.dev == dev) return true;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+  if (cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+  for (auto& e : g_side.fork_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming);
+  g_side.dev = dev; g_side.ok = true;
+  return true;
+}
+// side stream waits for everything issued so far on `main`
+static int side_fork(cudaStream_t main, int slot) {
+  FBN_CHECK_CUDA(cudaEventRecord(g_side.fork_ev[slot], main));
+  FBN_CHECK_CUDA(cudaStreamWaitEvent(g_side.s, g_side.fork_ev[slot], 0));
+  return FBN_OK;
+}
+static int side_join(cudaStream_t main) {
+  FBN_CHECK_CUDA(cudaEventRecord(g_side.join_ev, g_side.s));
+  FBN_CHECK_CUDA(cudaStreamWaitEvent(main, g_side.join_ev, 0));
+  return FBN_OK;
+}
+
 // ---- bilinear transforms T = V_src * W_idx ---------------------------------------------------
 static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStream_t st) {
   const int type = p->bilinear_type;
@@ -307,14 +346,19 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   tl_reg.prec = p->precision; tl_reg.st = st;
   const unsigned long long fmask = 0x3Eull;                       // MLP-input blocks 1..5: the SENET-weighted fields
   const int nW = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
+  // the weights are converted on the side stream while the gather kernel runs
+  const bool parf = tl_reg.on() && side_ready(st);
+  if (parf) { RC(side_fork(st, 4)); tl_reg.st = g_side.s; }
   RC(tl_reg.pack(p->w1, H1, K1, w.pk_w1, active_mask()));
   RC(tl_reg.pack(p->w2, H2, H1, w.pk_w2));
   RC(tl_reg.pack(p->bil_w, (long long)nW * D, D, w.pk_bil));
+  tl_reg.st = st;
 
   // activations are converted to the operand format by the kernels that produce them (no separate pack pass)
   const PackDst pkC = tl_reg.dst(w.C, B, K1, w.pk_C);
   RC(run_embed_fwd(p, b, w, 1, st, pkC, tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm)));
   (void)fmask;
+  if (parf) RC(side_join(st));
   RC(bilinear_transform_fwd(p, w, st));
   RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, pkC, st));
 
@@ -356,45 +400,6 @@ static int pick_splits_pair(long long M, long long N, long long K, unsigned long
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
-}
-
-// ---- branch parallelism inside the backward pass -------------------------------------------------
-// The weight-gradient GEMMs, bias / LayerNorm / SENET / cate_emb gradient reductions are leaves of the dependency graph:
-// they run on a library-owned side stream (fork = event on the caller's stream, join before the gradient norm), so the
-// critical path is only the data-gradient chain.  Works under CUDA-graph capture (event fork/join is capturable); the
-// stream and events are created on the first non-capturing call.
-struct SideCtx {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork_ev[6], join_ev;
-  int dev = -1;
-  bool ok = false;
-};
-static SideCtx g_side;
-static int g_use_side = 1;
-
-static bool side_ready(cudaStream_t main) {
-  if (!g_use_side) return false;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return false;
-  if (g_side.ok && g_side.dev == dev) return true;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
-  if (cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
-  for (auto& e : g_side.fork_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming);
-  g_side.dev = dev; g_side.ok = true;
-  return true;
-}
-// side stream waits for everything issued so far on `main`
-static int side_fork(cudaStream_t main, int slot) {
-  FBN_CHECK_CUDA(cudaEventRecord(g_side.fork_ev[slot], main));
-  FBN_CHECK_CUDA(cudaStreamWaitEvent(g_side.s, g_side.fork_ev[slot], 0));
-  return FBN_OK;
-}
-static int side_join(cudaStream_t main) {
-  FBN_CHECK_CUDA(cudaEventRecord(g_side.join_ev, g_side.s));
-  FBN_CHECK_CUDA(cudaStreamWaitEvent(main, g_side.join_ev, 0));
-  return FBN_OK;
 }
 
 static EmbGradArgs make_emb_args(const fbn_params_t* p, const fbn_batch_t* b, Workspace& w, int32_t* row_touched) {
