@@ -664,13 +664,14 @@ extern "C" int fbn_time_gemm(const float* A, const float* Bm, float* C, int64_t 
   return FBN_OK;
 }
 
-namespace fbn { void set_tc_pair(int on); }
+namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); }
 
 // runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles
 extern "C" int fbn_set_option(const char* name, int value) {
   FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
   if (strcmp(name, "side_streams") == 0) { g_use_side = value; return FBN_OK; }
+  if (strcmp(name, "tc_persistent") == 0) { fbn::set_tc_persistent(value); return FBN_OK; }
   set_error("fbn_set_option: unknown option '%s'", name);
   return FBN_ERR_ARG;
 }

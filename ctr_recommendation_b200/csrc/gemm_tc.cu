@@ -348,6 +348,216 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent single-CTA kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the linearised
+// (batch x split x M-tile x N-tile) space.  Barriers, TMEM and the TMA/MMA rings are set up once per CTA; the producer and
+// the MMA issuer run ahead across tile boundaries while the epilogue warps drain / store the previous tile (the two TMEM
+// accumulators alternate per chunk exactly as inside a tile).  This is what the many small contractions of the step need
+// (K = 128 bilinear transforms: 4 k-blocks per tile -- set-up and epilogue used to dominate them: 7.6 % tensor activity).
+// The epilogue transposes through DEDICATED staging smem (the stages may already be refilled for the next tile).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+struct TcpCfg {
+  static constexpr int STAGES = MODE == FBN_PREC_TF32X3 ? 2 : 4;
+  static constexpr int STAGE_BYTES = TcCfg<MODE>::STAGE_BYTES;
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int NBAR = 2 * STAGES + 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
+
+struct TileInfo { int n0, m0, sp, bi, kb0, kb1, nact; bool skip; };
+
+template <int MODE>
+__device__ __forceinline__ TileInfo tile_info(const TcArgs& g, long long t, int nN, int nM, int kblocks, int per) {
+  using Cfg = TcCfg<MODE>;
+  TileInfo ti;
+  const int x = (int)(t % nN);
+  const long long r = t / nN;
+  const int y = (int)(r % nM), z = (int)(r / nM);
+  ti.n0 = x * TC_BN; ti.m0 = y * TC_BM; ti.sp = z % g.splits; ti.bi = z / g.splits;
+  ti.skip = g.nmask != ~0ull && !((g.nmask >> (ti.n0 / 128)) & 1ull);
+  ti.kb0 = ti.sp * per; ti.kb1 = min(kblocks, ti.kb0 + per);
+  int nact = 0;
+  for (int kb = ti.kb0; kb < ti.kb1; ++kb)
+    nact += (g.kmask == ~0ull || ((g.kmask >> ((kb * Cfg::BK) / 128)) & 1ull)) ? 1 : 0;
+  ti.nact = nact;
+  return ti;
+}
+
+template <int MODE, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_constant__ TcMaps tm, const TcArgs g, long long ntiles,
+                                                                 int nN, int nM) {
+  using Cfg = TcCfg<MODE>;
+  using PC = TcpCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi = smem + PC::STAGES * PC::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + PC::EPI_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + PC::STAGES;
+  uint64_t* tfull = bars + 2 * PC::STAGES;
+  uint64_t* tempty = bars + 2 * PC::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + PC::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (int)((g.K + Cfg::BK - 1) / Cfg::BK);
+  const int per = (kblocks + g.splits - 1) / g.splits;
+  auto active = [&](int kb) { return g.kmask == ~0ull || ((g.kmask >> ((kb * Cfg::BK) / 128)) & 1ull); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PC::STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < Cfg::NPART; ++p) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.a[p])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.b[p])) : "memory");
+      }
+      int it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileInfo ti = tile_info<MODE>(g, t, nN, nM, kblocks, per);
+        if (ti.skip) continue;
+        const int acol = ti.bi * g.a_bc, arow = ti.bi * g.a_br, bcol = ti.bi * g.b_bc, brow = ti.bi * g.b_br;
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+          if (!active(kb)) continue;
+          const int s = it % PC::STAGES;
+          const uint32_t ph = (it / PC::STAGES) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, PC::STAGE_BYTES);
+          uint8_t* st = smem + s * PC::STAGE_BYTES;
+          const int kc = kb * Cfg::BK;
+#pragma unroll
+          for (int p = 0; p < Cfg::NPART; ++p) {
+            uint8_t* sa = st + p * Cfg::TILE_BYTES;
+            uint8_t* sb = st + (Cfg::NPART + p) * Cfg::TILE_BYTES;
+            if (!A_MN) {
+              tma_load_2d(sa, &tm.a[p], full + s, kc + acol, ti.m0 + arow);
+            } else {
+#pragma unroll
+              for (int j = 0; j < TC_BM / Cfg::EPB; ++j)
+                tma_load_2d(sa + j * Cfg::BOX_MN_BYTES, &tm.a[p], full + s, ti.m0 + j * Cfg::EPB + acol, kc + arow);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tm.b[p], full + s, kc + bcol, ti.n0 + brow);
+            } else {
+#pragma unroll
+              for (int j = 0; j < TC_BN / Cfg::EPB; ++j)
+                tma_load_2d(sb + j * Cfg::BOX_MN_BYTES, &tm.b[p], full + s, ti.n0 + j * Cfg::EPB + bcol, kc + brow);
+            }
+          }
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Cfg::FMT, TC_BM, TC_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
+      constexpr bool base32 = MODE == FBN_PREC_TF32X3;
+      constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
+      constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
+      int it = 0, chunk = 0;       // global ring positions (continue across tiles)
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileInfo ti = tile_info<MODE>(g, t, nN, nM, kblocks, per);
+        if (ti.skip || ti.nact == 0) continue;
+        int done = 0;
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+          if (!active(kb)) continue;
+          const int s = it % PC::STAGES;
+          const uint32_t ph = (it / PC::STAGES) & 1;
+          const int buf = chunk & 1, pos = done % TC_CHUNK;
+          if (pos == 0) {
+            mbar_wait(tempty + buf, ((chunk >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(buf * TC_BN);
+          const uint32_t sa = smem_u32(smem + s * PC::STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa, lbo_a, sbo_a, lay_a);
+          const uint64_t b_hi = make_desc(sa + Cfg::NPART * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+            const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+            if (Cfg::NPART == 2) {
+              const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
+              const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+              umma<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);
+              umma<MODE>(tacc, a_hi + k * adv_a, b_lo + k * adv_b, idesc, 1u);
+              umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
+            } else {
+              umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
+            }
+          }
+          tc_commit(empty + s);
+          ++done;
+          ++it;
+          if (pos == TC_CHUNK - 1 || done == ti.nact) {
+            tc_commit(tfull + buf);
+            ++chunk;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);
+    int chunk = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const TileInfo ti = tile_info<MODE>(g, t, nN, nM, kblocks, per);
+      if (ti.skip) continue;
+      float acc[TC_BN];
+#pragma unroll
+      for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+      const int nchunks = (ti.nact + TC_CHUNK - 1) / TC_CHUNK;
+      for (int c = 0; c < nchunks; ++c, ++chunk) {
+        const int buf = chunk & 1;
+        mbar_wait(tfull + buf, (chunk >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN + c0), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty + buf);
+      }
+      const long long row0 = (long long)ti.m0 + q * 32;
+      float* cbase = g.C + (long long)ti.bi * g.strideC + (long long)ti.sp * g.strideSplit + row0 * g.ldc + ti.n0;
+      epilogue_store(acc, stage, lane, row0, g.M, cbase, g.ldc, g.bias ? g.bias + ti.n0 : nullptr, g.accumulate);
+      __syncwarp();        // the staging rows are reused by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): one 256 x 256 output tile per 2-CTA cluster.
 //   Each CTA stages ITS 128 rows of A and ITS 128-row half of the B tile (64 KB per stage for tf32x3, as above) but the
 //   pair's tensor cores multiply 256 x 256 per instruction, so the L2 -> smem traffic per MMA is halved -- the 1-CTA
@@ -685,9 +895,28 @@ bool gemm_tc_supported(const GemmArgs& g, int precision) {
   return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16) && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch >= 1;
 }
 
+static int g_tc_persistent = 1;   // fbn_set_option("tc_persistent", 0) -> one tile per CTA
+void set_tc_persistent(int on) { g_tc_persistent = on; }
+
+template <int MODE, bool A_MN, bool B_MN>
+static int launch_tcp(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st) {
+  using PC = TcpCfg<MODE>;
+  static bool attr = false;
+  if (!attr) {
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM));
+    attr = true;
+  }
+  const long long ntiles = (long long)grid.x * grid.y * grid.z;
+  const int ctas = (int)std::min<long long>(ntiles, num_sms());
+  gemm_tcp_kernel<MODE, A_MN, B_MN><<<ctas, TC_THREADS, PC::SMEM, st>>>(maps, t, ntiles, (int)grid.x, (int)grid.y);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
 template <int MODE, bool A_MN, bool B_MN>
 static int launch_tc(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st) {
   using Cfg = TcCfg<MODE>;
+  if (g_tc_persistent) return launch_tcp<MODE, A_MN, B_MN>(maps, t, grid, st);
   static bool attr = false;
   if (!attr) {
     FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
