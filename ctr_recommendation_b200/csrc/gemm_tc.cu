@@ -366,13 +366,15 @@ struct TcpCfg {
 
 struct TileInfo { int n0, m0, sp, bi, kb0, kb1, nact; bool skip; };
 
+// tile order (fastest -> slowest): N tile, batch x split, M tile -- tiles that run at the same time share their A rows
+// (the four bilinear transforms of a row block read adjacent 512-byte column blocks of the same rows)
 template <int MODE>
-__device__ __forceinline__ TileInfo tile_info(const TcArgs& g, long long t, int nN, int nM, int kblocks, int per) {
+__device__ __forceinline__ TileInfo tile_info(const TcArgs& g, long long t, int nN, int nZ, int kblocks, int per) {
   using Cfg = TcCfg<MODE>;
   TileInfo ti;
   const int x = (int)(t % nN);
   const long long r = t / nN;
-  const int y = (int)(r % nM), z = (int)(r / nM);
+  const int z = (int)(r % nZ), y = (int)(r / nZ);
   ti.n0 = x * TC_BN; ti.m0 = y * TC_BM; ti.sp = z % g.splits; ti.bi = z / g.splits;
   ti.skip = g.nmask != ~0ull && !((g.nmask >> (ti.n0 / 128)) & 1ull);
   ti.kb0 = ti.sp * per; ti.kb1 = min(kblocks, ti.kb0 + per);
@@ -385,7 +387,7 @@ __device__ __forceinline__ TileInfo tile_info(const TcArgs& g, long long t, int 
 
 template <int MODE, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_constant__ TcMaps tm, const TcArgs g, long long ntiles,
-                                                                 int nN, int nM) {
+                                                                 int nN, int nZ) {
   using Cfg = TcCfg<MODE>;
   using PC = TcpCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
       }
       int it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const TileInfo ti = tile_info<MODE>(g, t, nN, nM, kblocks, per);
+        const TileInfo ti = tile_info<MODE>(g, t, nN, nZ, kblocks, per);
         if (ti.skip) continue;
         const int acol = ti.bi * g.a_bc, arow = ti.bi * g.a_br, bcol = ti.bi * g.b_bc, brow = ti.bi * g.b_br;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
       constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
       int it = 0, chunk = 0;       // global ring positions (continue across tiles)
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const TileInfo ti = tile_info<MODE>(g, t, nN, nM, kblocks, per);
+        const TileInfo ti = tile_info<MODE>(g, t, nN, nZ, kblocks, per);
         if (ti.skip || ti.nact == 0) continue;
         int done = 0;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
     float* stage = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);
     int chunk = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const TileInfo ti = tile_info<MODE>(g, t, nN, nM, kblocks, per);
+      const TileInfo ti = tile_info<MODE>(g, t, nN, nZ, kblocks, per);
       if (ti.skip) continue;
       float acc[TC_BN];
 #pragma unroll
@@ -895,7 +897,7 @@ bool gemm_tc_supported(const GemmArgs& g, int precision) {
   return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16) && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch >= 1;
 }
 
-static int g_tc_persistent = 1;   // fbn_set_option("tc_persistent", 0) -> one tile per CTA
+static int g_tc_persistent = 0;   // fbn_set_option("tc_persistent", 1) -> persistent tile loop (measured: no gain, kept as an option)
 void set_tc_persistent(int on) { g_tc_persistent = on; }
 
 template <int MODE, bool A_MN, bool B_MN>
@@ -908,7 +910,7 @@ static int launch_tcp(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream
   }
   const long long ntiles = (long long)grid.x * grid.y * grid.z;
   const int ctas = (int)std::min<long long>(ntiles, num_sms());
-  gemm_tcp_kernel<MODE, A_MN, B_MN><<<ctas, TC_THREADS, PC::SMEM, st>>>(maps, t, ntiles, (int)grid.x, (int)grid.y);
+  gemm_tcp_kernel<MODE, A_MN, B_MN><<<ctas, TC_THREADS, PC::SMEM, st>>>(maps, t, ntiles, (int)grid.x, (int)grid.z);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
