@@ -29,7 +29,9 @@ GRAD_FIELDS = ["cate_emb", "mm_w", "mm_b", "ln_g", "ln_b", "se_w1", "se_b1", "se
 
 class Params(C.Structure):
     _fields_ = [("item_emb", _vp), ("item_rows", _i64), ("cate_emb", _vp), ("cate_rows", _i64)] + \
-               [(n, _vp) for n in PARAM_FIELDS[2:]] + [("bilinear_type", _i32), ("precision", _i32)]
+               [(n, _vp) for n in PARAM_FIELDS[2:]] + [("bilinear_type", _i32), ("precision", _i32),
+                                                       ("n_shards", _i32), ("shard_rank", _i32), ("shard_rows", _i64),
+                                                       ("shard", _vp * 16)]
 
 
 class Grads(C.Structure):
@@ -41,8 +43,14 @@ class Batch(C.Structure):
                 ("item_seq", _vp), ("item_mm", _vp), ("mm_table", _vp), ("idx_dtype", _i32), ("seq_dtype", _i32)]
 
 
+class ShardPlan(C.Structure):
+    _fields_ = [("n_shards", _i32), ("rank", _i32), ("item_rows", _i64), ("shard_rows", _i64), ("cap", _i64),
+                ("merge_cap", _i64), ("xchg", _vp * 16)]
+
+
 class AdamHyper(C.Structure):
-    _fields_ = [("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("step", _i32)]
+    _fields_ = [("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("step", _i32),
+                ("one_minus_beta1", _f), ("one_minus_beta2", _f)]
 
 
 _SIGNATURES = {
@@ -71,6 +79,16 @@ _SIGNATURES = {
     "fbn_gemm_scratch_bytes": (_sz, [_i64, _i64, _i64, C.c_int]),
     "fbn_time_gemm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, _u64, C.c_int, _vp, _sz, _vp, _sz, C.c_int,
                                 C.POINTER(C.c_float), _vp]),
+    "fbn_shard_xchg_bytes": (_sz, [_i64]),
+    "fbn_shard_ws_bytes": (_sz, [_i64, _i64, C.c_int, _i64]),
+    "fbn_shard_index": (C.c_int, [C.POINTER(ShardPlan), C.POINTER(Batch), _vp, _sz, _vp]),
+    "fbn_shard_local_sum": (C.c_int, [C.POINTER(ShardPlan), C.POINTER(Batch), _vp, _vp, _vp, _sz, _vp]),
+    "fbn_shard_merge": (C.c_int, [C.POINTER(ShardPlan), _vp, _sz, _vp, _vp, _vp, _vp]),
+    "fbn_shard_adam_rows": (C.c_int, [C.POINTER(ShardPlan), _vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(AdamHyper), _vp, _vp]),
+    "fbn_shard_stats": (C.c_int, [C.POINTER(ShardPlan), _vp, _sz, C.POINTER(C.c_int32), _vp]),
+    "fbn_ipc_export": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "fbn_ipc_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "fbn_ipc_close": (C.c_int, [_vp]),
     "fbn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "fbn_launch_count": (_u64, []),
     "fbn_last_error": (C.c_char_p, []),

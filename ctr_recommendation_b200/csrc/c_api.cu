@@ -198,8 +198,18 @@ using namespace fbn;
     if (_rc) return _rc; \
   } while (0)
 
+// rows the workspace is sized for: the dense per-row index of the replicated table does not exist in row-sharded mode
+static inline int64_t ws_rows(const fbn_params_t* p) { return p->n_shards > 0 ? 1 : p->item_rows; }
+
 static int check_common(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes) {
   FBN_REQUIRE(p && b && ws, FBN_ERR_ARG, "null params / batch / workspace");
+  FBN_REQUIRE(p->n_shards >= 0 && p->n_shards <= FBN_MAX_SHARDS, FBN_ERR_ARG, "n_shards must be in [0,%d]", FBN_MAX_SHARDS);
+  if (p->n_shards > 0) {
+    FBN_REQUIRE(p->shard_rank >= 0 && p->shard_rank < p->n_shards && p->shard_rows * p->n_shards >= p->item_rows &&
+                    p->item_rows < (1LL << 31), FBN_ERR_SHAPE, "inconsistent shard description");
+    for (int r = 0; r < p->n_shards; ++r)
+      FBN_REQUIRE(p->shard[r] && aligned16(p->shard[r]), FBN_ERR_ALIGN, "shard pointer %d missing / unaligned", r);
+  }
   FBN_REQUIRE(b->batch >= 1, FBN_ERR_SHAPE, "batch must be >= 1");
   FBN_REQUIRE(b->seq_len >= 0 && b->seq_len <= MAX_L, FBN_ERR_SHAPE, "seq_len must be in [0,%d]", MAX_L);
   FBN_REQUIRE(p->cate_rows >= 1 && p->cate_rows <= MAX_CATE, FBN_ERR_SHAPE, "cate_rows must be in [1,%d]", MAX_CATE);
@@ -216,7 +226,7 @@ static int check_common(const fbn_params_t* p, const fbn_batch_t* b, void* ws, s
   for (const void* q : ptrs) FBN_REQUIRE(aligned16(q), FBN_ERR_ALIGN, "a tensor pointer is not 16-byte aligned");
   FBN_REQUIRE(p->se_w1 && p->se_b1 && p->se_w2 && p->se_b2 && p->b3, FBN_ERR_ARG, "null parameter pointer");
   Workspace w;
-  carve_workspace(w, nullptr, b->batch, b->seq_len, p->item_rows);
+  carve_workspace(w, nullptr, b->batch, b->seq_len, ws_rows(p));
   FBN_REQUIRE(ws_bytes >= w.total_bytes, FBN_ERR_ARG, "workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
   return FBN_OK;
 }
@@ -320,6 +330,8 @@ static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace&
   e.ids = w.ids; e.seq32 = w.seq; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.xmm = w.xmm; e.rstd = w.rstd; e.cnt = w.cnt;
   e.C = w.C;
   e.pkC = pkC; e.pkX = pkX;
+  e.nshard = p->n_shards;
+  for (int r = 0; r < p->n_shards; ++r) e.shard[r] = p->shard[r];
   return launch_embed_senet_fwd(e, st);
 }
 
@@ -327,7 +339,7 @@ static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace&
 extern "C" int fbn_embed_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int save, fbn_stream_t stream) {
   RC(check_common(p, b, ws, ws_bytes));
   Workspace w;
-  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  carve_workspace(w, ws, b->batch, b->seq_len, ws_rows(p));
   return run_embed_fwd(p, b, w, save, (cudaStream_t)stream);
 }
 
@@ -339,7 +351,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   FBN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FBN_ERR_ARG, "dropout_p must be in [0,1)");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
-  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  carve_workspace(w, ws, b->batch, b->seq_len, ws_rows(p));
   const long long B = b->batch;
 
   tl_reg = PkReg();
@@ -420,7 +432,7 @@ extern "C" int fbn_embed_index(const fbn_params_t* p, const fbn_batch_t* b, void
                                fbn_stream_t stream) {
   RC(check_common(p, b, ws, ws_bytes));
   Workspace w;
-  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  carve_workspace(w, ws, b->batch, b->seq_len, ws_rows(p));
   EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
   return emb_index(eg, (cudaStream_t)stream);
 }
@@ -444,11 +456,13 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
                             float* item_grad, int32_t* row_touched, int zero_fill, int index_ready, float* grad_sumsq,
                             fbn_stream_t stream) {
   RC(check_common(p, b, ws, ws_bytes));
-  FBN_REQUIRE(dprob && g && item_grad && grad_sumsq, FBN_ERR_ARG, "fbn_backward: null pointer");
+  FBN_REQUIRE(dprob && g && grad_sumsq, FBN_ERR_ARG, "fbn_backward: null pointer");
+  FBN_REQUIRE(item_grad || p->n_shards > 0, FBN_ERR_ARG, "fbn_backward: item_grad may only be NULL for a row-sharded table");
+  FBN_REQUIRE(!(item_grad && p->n_shards > 0), FBN_ERR_ARG, "fbn_backward: a row-sharded table takes its gradient through fbn_shard_*");
   FBN_REQUIRE(aligned16(item_grad), FBN_ERR_ALIGN, "item_grad is not 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
-  carve_workspace(w, ws, b->batch, b->seq_len, p->item_rows);
+  carve_workspace(w, ws, b->batch, b->seq_len, ws_rows(p));
   const long long B = b->batch;
   const int prec = p->precision;
   const float scale = (train && dropout_p > 0.f) ? 1.0f / (1.0f - dropout_p) : 1.0f;
@@ -566,10 +580,12 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   RC(colsum(w.dy, B, D, lp, g->mm_b, ls));
   RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, ls, lp));
   // ---- embedding table rows ----
-  EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
-  eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_out = grad_sumsq + 1;
-  if (!index_ready) RC(emb_index(eg, st));
-  RC(emb_rows(eg, st));
+  if (item_grad) {
+    EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
+    eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_out = grad_sumsq + 1;
+    if (!index_ready) RC(emb_index(eg, st));
+    RC(emb_rows(eg, st));
+  }
   if (par) RC(side_join(st));     // every dense gradient is complete from here on
   if (dense_grad_flat) {
     FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");

@@ -20,6 +20,15 @@ constexpr int EMB_SPW = 2;  // samples per warp per iteration (register-blocks t
 
 // smem: Wt[128][128] (k-major copy of mm_w so lane j reads W[4j..4j+3][k] as one float4)
 //       xs[EMB_WARPS][128][EMB_SPW]
+// row g of the item table: the local (replicated) table, or -- row-sharded mode -- the owner's slice, read over NVLink
+template <bool SHARDED>
+__device__ __forceinline__ const float* item_row(const EmbedFwdArgs& a, long long id) {
+  if (!SHARDED) return a.item_emb + id * D;
+  const unsigned g = (unsigned)id, n = (unsigned)a.nshard;
+  return a.shard[g % n] + (long long)(g / n) * D;
+}
+
+template <bool SHARDED>
 __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(EmbedFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* Wt = smem;
@@ -64,7 +73,7 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
         vw = min(max(vw, 0LL), (long long)a.cate_rows - 1);
         f_like[s] = ld4(a.cate_emb + lk * D + 4 * lane);
         f_view[s] = ld4(a.cate_emb + vw * D + 4 * lane);
-        f_item[s] = ld4(a.item_emb + iid * D + 4 * lane);
+        f_item[s] = ld4(item_row<SHARDED>(a, iid) + 4 * lane);
         if (a.item_mm) {
           xm = ld4s(a.item_mm + b * D + 4 * lane);
         } else {
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
                 if (l + u >= n) id[u] = 0;
               }
 #pragma unroll
-              for (int u = 0; u < 8; ++u) r[u] = id[u] ? ld4(a.item_emb + (long long)id[u] * D + 4 * lane) : f4(0.f);
+              for (int u = 0; u < 8; ++u) r[u] = id[u] ? ld4(item_row<SHARDED>(a, id[u]) + 4 * lane) : f4(0.f);
 #pragma unroll
               for (int u = 0; u < 8; ++u)
                 if (id[u]) { acc += r[u]; ++nvalid; }
@@ -215,7 +224,8 @@ int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = embed_fwd_smem();
   if (!attr_set) {
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const long long ngroups = (a.B + EMB_SPW - 1) / EMB_SPW;
@@ -223,7 +233,8 @@ int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
   const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (72 KB smem each)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  embed_senet_fwd_kernel<<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);
+  if (a.nshard > 0) embed_senet_fwd_kernel<true><<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);
+  else embed_senet_fwd_kernel<false><<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }

@@ -20,6 +20,8 @@ struct EmbedFwdArgs {
   float* X5; float* sgate; float* xhat; float* xmm; float* rstd; float* cnt; float* C;
   PackDst pkC;         // packed copy of the field blocks of C
   PackDst pkX;         // packed copy of the item_emb_d128 rows (B,128)
+  int nshard;          // > 0: row-sharded item table, row g = shard[g % nshard] + (g / nshard) * 128 (peer-mapped pointers)
+  const float* shard[FBN_MAX_SHARDS];
 };
 
 struct EmbedBwdArgs {

@@ -3,6 +3,8 @@
 // Reference: torch.nn.utils.clip_grad_norm_(.., 10.0) + torch.optim.Adam(lr, weight_decay) as invoked at
 // src/train_fibinet.py:78,119,121 (single-tensor Adam math of torch/optim/adam.py, L2 decay folded
 // into the gradient, bias corrections from the scheduler-cycled beta1).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tower.h"
 
@@ -69,19 +71,20 @@ __global__ void clip_coef_kernel(const float* __restrict__ sums, int n, float ma
   out[1] = fminf(1.0f, max_norm / (total + 1e-6f));  // clip_grad.py: clamp(max_norm/(total+1e-6), max=1)
 }
 
-struct AdamHyper { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt; };
+struct AdamHyper { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, omb1, omb2; };
 
 __device__ __forceinline__ AdamHyper resolve_hyper(const AdamHyper& h, const float* dev) {
   if (!dev) return h;
   AdamHyper r;
   r.lr = dev[0]; r.beta1 = dev[1]; r.beta2 = dev[2]; r.eps = dev[3]; r.wd = dev[4]; r.step_size = dev[5]; r.bc2_sqrt = dev[6];
+  r.omb1 = dev[8]; r.omb2 = dev[9];
   return r;
 }
 
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, const AdamHyper& h) {
   g = fmaf(h.wd, p, g);                              // grad.add(param, alpha=weight_decay)
-  m = m + (1.0f - h.beta1) * (g - m);                // exp_avg.lerp_(grad, 1-beta1)
-  v = v * h.beta2 + (1.0f - h.beta2) * (g * g);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  m = m + h.omb1 * (g - m);                          // exp_avg.lerp_(grad, 1-beta1)      (1-beta evaluated in double by torch)
+  v = v * h.beta2 + h.omb2 * (g * g);                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
   const float denom = sqrtf(v) / h.bc2_sqrt + h.eps; // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
   p = p - h.step_size * (m / denom);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
@@ -120,6 +123,17 @@ __global__ void __launch_bounds__(256) adam_dense_kernel(float* __restrict__ p, 
   }
 }
 
+// 1 - beta as torch computes it: in double, from the decimal literal the user wrote.  An fp32 beta is the rounding of such a
+// literal; the shortest decimal that rounds to it (<= 9 digits) recovers the double, e.g. 0.999f -> 0.999 -> 1e-3.
+float one_minus(float beta) {
+  char buf[32];
+  for (int prec = 1; prec <= 9; ++prec) {
+    snprintf(buf, sizeof(buf), "%.*g", prec, (double)beta);
+    if ((float)atof(buf) == beta) return (float)(1.0 - atof(buf));
+  }
+  return 1.0f - beta;
+}
+
 static AdamHyper make_hyper(const fbn_adam_t& a) {
   AdamHyper h;
   h.lr = a.lr; h.beta1 = a.beta1; h.beta2 = a.beta2; h.eps = a.eps; h.wd = a.weight_decay;
@@ -127,13 +141,16 @@ static AdamHyper make_hyper(const fbn_adam_t& a) {
   const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
   h.step_size = (float)((double)a.lr / bc1);
   h.bc2_sqrt = (float)sqrt(bc2);
+  h.omb1 = a.one_minus_beta1 > 0.f ? a.one_minus_beta1 : one_minus(a.beta1);
+  h.omb2 = a.one_minus_beta2 > 0.f ? a.one_minus_beta2 : one_minus(a.beta2);
   return h;
 }
 
 // OneCycleLR (cos, two phases, cycle_momentum) evaluated on the device from a step counter, so that a
 // whole training step can be replayed from a CUDA graph: hyper[0..6] as AdamHyper, counter += 1.
 __global__ void onecycle_hyper_kernel(int* step_counter, int total_steps, float max_lr, float pct_start, float div_factor,
-                                      float final_div, float base_m, float max_m, float beta2, float eps, float wd, float* hyper) {
+                                      float final_div, float base_m, float max_m, float beta2, float eps, float wd, float omb2,
+                                      float* hyper) {
   const int s = *step_counter;  // 0-based scheduler step == number of optimizer steps already taken
   const double init = (double)max_lr / div_factor, minlr = init / final_div;
   const double e1 = (double)pct_start * total_steps - 1.0, e2 = total_steps - 1.0;
@@ -155,6 +172,8 @@ __global__ void onecycle_hyper_kernel(int* step_counter, int total_steps, float 
   hyper[5] = (float)(lr / (1.0 - pow(b1, (double)t)));
   hyper[6] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
   hyper[7] = (float)t;
+  hyper[8] = (float)(1.0 - b1);
+  hyper[9] = omb2;
   *step_counter = t;
 }
 
@@ -200,7 +219,8 @@ extern "C" int fbn_onecycle_hyper(int32_t* step_counter, int total_steps, float 
                                   float weight_decay, float* hyper_dev, fbn_stream_t stream) {
   FBN_REQUIRE(step_counter && hyper_dev && total_steps > 1, FBN_ERR_ARG, "fbn_onecycle_hyper: bad arguments");
   onecycle_hyper_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter, total_steps, max_lr, pct_start, div_factor, final_div_factor,
-                                                            base_momentum, max_momentum, beta2, eps, weight_decay, hyper_dev);
+                                                            base_momentum, max_momentum, beta2, eps, weight_decay,
+                                                            one_minus(beta2), hyper_dev);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }

@@ -75,5 +75,6 @@ int emb_grad_partial_count(long long rows);
 // optim.cu
 int sumsq(const float* x, long long n, float* partial, float* out, cudaStream_t st);
 int sumsq_partial_count(long long n);
+float one_minus(float beta);   // 1 - beta the way torch evaluates it (double arithmetic on the decimal literal)
 
 }  // namespace fbn

@@ -57,10 +57,14 @@ def shard_batch(batch: dict, labels, rank: int, world: int):
 def broadcast_parameters(model, src: int = 0):
     """One-time replication at start-up (the reference re-broadcasts every forward).  Also switches the
     model to dense table gradients (every row written) so that the table all-reduce is well defined."""
-    model._dense_table_grad = True
+    sharded = getattr(model, "_shard", None) is not None
+    if not sharded:
+        model._dense_table_grad = True
     if not (dist.is_available() and dist.is_initialized()):
         return
-    for t in list(model.parameters()) + list(model.buffers()):
+    for name, t in list(model.named_parameters()) + list(model.named_buffers()):
+        if sharded and name == "item_emb.weight":
+            continue        # every rank owns a different slice of a row-sharded table
         dist.broadcast(t.data, src)
 
 

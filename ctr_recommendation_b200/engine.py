@@ -67,26 +67,22 @@ class TrainStep:
         dev = model._flat.device
         self.dev = dev
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        if self.world > 1:
+        if self.world > 1 and model._shard is None:
             model._dense_table_grad = True
         self.inp = _StaticBatch(batch_size, seq_len, idx_dtype, seq_dtype, dev, with_mm=not use_mm_table)
         if use_mm_table and model._mm_table is None:
             raise ValueError("use_mm_table=True needs model.attach_mm_table(...)")
         self.B, self.L = batch_size, seq_len
-        rows = model.item_emb.weight.shape[0]
         self.ws = model._workspace(batch_size, seq_len)
-        if model._item_grad is None or model._item_grad.device != dev:
-            model._item_grad = torch.zeros(rows, D, dtype=torch.float32, device=dev)
-            model._row_touched = torch.zeros(rows, dtype=torch.int32, device=dev)
-            model._grad_sumsq = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._alloc_table_grad()
         self.prob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.dprob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.hyper_dev = torch.zeros(8, dtype=torch.float32, device=dev)
-        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(model._item_grad.numel()), 16), dtype=torch.float32,
-                                         device=dev)
+        self.hyper_dev = torch.zeros(12, dtype=torch.float32, device=dev)
+        self.hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+        self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(max(self._table_grad_numel(), model._flat.numel())), 16),
+                                         dtype=torch.float32, device=dev)
         self._side = torch.cuda.Stream(device=dev)
         # input prefetch: the next batch is copied host->device on a copy stream into a staging set while the current step
         # computes (what the reference's DataLoader workers + pin_memory would give); the step then takes it with a D2D copy
@@ -103,6 +99,26 @@ class TrainStep:
         self.kernels_per_step = 0
 
     # ------------------------------------------------------------------
+    def _alloc_table_grad(self):
+        model, dev = self.model, self.dev
+        if model._shard is not None:
+            raise TypeError("row-sharded item table: use ShardedTrainStep")
+        rows = model.item_emb.weight.shape[0]
+        if model._item_grad is None or model._item_grad.device != dev:
+            model._item_grad = torch.zeros(rows, D, dtype=torch.float32, device=dev)
+            model._row_touched = torch.zeros(rows, dtype=torch.int32, device=dev)
+            model._grad_sumsq = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def _table_grad_numel(self):
+        return self.model._item_grad.numel()
+
+    def _stages(self):
+        """The step as a list of (device work, collective that follows it or None); consecutive stages without a collective
+        between them are captured into one CUDA graph."""
+        if self.world == 1:
+            return [(self._fwd_bwd, None), (self._update, None)]
+        return [(self._fwd_bwd, self._allreduce), (self._update, None)]
+
     def _batch_struct(self):
         t = self.inp.t
         bs = _lib.Batch()
@@ -171,19 +187,24 @@ class TrainStep:
         for b, k in zip((m.mlp[1].running_mean, m.mlp[1].running_var, m.mlp[5].running_mean, m.mlp[5].running_var), keep):
             b.copy_(k)                         # the warm-up forward must not count as a training step
         self.step_counter.zero_()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # group the stages into graphs: a new graph starts after every collective
+        groups, cur_fns = [], []
+        for fn, coll in self._stages():
+            cur_fns.append(fn)
+            if coll is not None:
+                groups.append((cur_fns, coll))
+                cur_fns = []
+        if cur_fns:
+            groups.append((cur_fns, None))
         n0 = self.lib.fbn_launch_count()
-        if self.world == 1:
-            with torch.cuda.graph(g1):
-                self._fwd_bwd()
-                self._update()
-            self._graphs = (g1, None)
-        else:
-            with torch.cuda.graph(g1):
-                self._fwd_bwd()
-            with torch.cuda.graph(g2):
-                self._update()
-            self._graphs = (g1, g2)
+        graphs = []
+        for fns, coll in groups:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for fn in fns:
+                    fn()
+            graphs.append((g, coll))
+        self._graphs = graphs
         self.kernels_per_step = int(self.lib.fbn_launch_count() - n0)   # library kernels inside the captured step
 
     def _write_hyper(self):
@@ -196,6 +217,7 @@ class TrainStep:
         h[5] = lr / (1.0 - b1 ** t)
         h[6] = math.sqrt(1.0 - b2 ** t)
         h[7] = float(t)
+        h[8], h[9] = 1.0 - b1, 1.0 - b2          # evaluated in double like torch, rounded to fp32 by the store
         self.hyper_dev.copy_(h, non_blocking=True)
 
     # ------------------------------------------------------------------
@@ -233,16 +255,15 @@ class TrainStep:
         if self._use_graph and self._graphs is None:
             self._capture()
         if self._use_graph:
-            g1, g2 = self._graphs
-            g1.replay()
-            if g2 is not None:
-                self._allreduce()
-                g2.replay()
+            for g, coll in self._graphs:
+                g.replay()
+                if coll is not None:
+                    coll()
         else:
-            self._fwd_bwd()
-            if self.world > 1:
-                self._allreduce()
-            self._update()
+            for fn, coll in self._stages():
+                fn()
+                if coll is not None:
+                    coll()
         m.mlp[1].num_batches_tracked += 1
         m.mlp[5].num_batches_tracked += 1
         self._steps += 1
@@ -253,6 +274,111 @@ class TrainStep:
         m = self.model
         dist.all_reduce(m._gflat, op=dist.ReduceOp.SUM)
         dist.all_reduce(m._item_grad, op=dist.ReduceOp.SUM)
+
+
+class ShardedTrainStep(TrainStep):
+    """TrainStep for a row-sharded item table (``feature_map={"table_sharding": "row", ...}``, sharded.py).
+
+    Per step and rank:  [index || forward, loss, backward, local segment sums -> exchange block]
+                        -> all-reduce of the dense gradients (also the barrier that publishes the exchange blocks)
+                        -> [owner-side merge of the N partial lists over NVLink, slice sum of squares]
+                        -> all-reduce of that scalar (clip; also releases the exchange blocks)
+                        -> [clip coefficient, Adam on the slice (dense-exact, or ``lazy=True``: touched rows only), dense Adam]
+                        -> barrier (the next forward reads the updated rows remotely).
+    With one rank the same kernels run back to back in one graph (the single-GPU tests cover the whole path)."""
+
+    def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
+                 seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True,
+                 lazy: bool = False, merge_cap: int | None = None):
+        if model._shard is None:
+            raise TypeError("ShardedTrainStep needs a model built with table_sharding='row'")
+        self.lazy = bool(lazy)
+        self._merge_cap = merge_cap
+        super().__init__(model, optimizer, batch_size, seq_len, idx_dtype, seq_dtype, max_norm, use_mm_table, graph)
+        st = model._shard
+        if st.world != self.world:
+            raise ValueError(f"the table is sharded over {st.world} ranks but the process group has {self.world}")
+        self.plan = st.ensure_exchange(batch_size * (1 + seq_len), self.dev, merge_cap)
+        off = lambda name: self.lib.fbn_workspace_offset(self.B, self.L, 1, name.encode())
+        self._dX = (C.c_void_p(self.ws.data_ptr() + off("dXitem")), C.c_void_p(self.ws.data_ptr() + off("dXhist")))
+        self._sq_local = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+    def _alloc_table_grad(self):
+        m, dev = self.model, self.dev
+        R = m._shard.shard_rows
+        m._grad_sumsq = torch.zeros(2, dtype=torch.float32, device=dev)
+        if self.lazy:
+            m._item_grad, m._row_touched = None, None
+        else:
+            m._item_grad = torch.zeros(R, D, dtype=torch.float32, device=dev)
+            m._row_touched = torch.zeros(R, dtype=torch.int32, device=dev)
+
+    def _table_grad_numel(self):
+        return 0
+
+    def _stages(self):
+        if self.world == 1:
+            return [(self._fwd_bwd, None), (self._merge, None), (self._update, None)]
+        return [(self._fwd_bwd, self._allreduce), (self._merge, self._allreduce_sumsq), (self._update, self._barrier)]
+
+    def _fwd_bwd(self):
+        m, lib, st = self.model, self.lib, self.model._shard
+        P, G = m._params_struct(), m._grads_struct()
+        ws, sws = self.ws, st.sws
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):     # ids only: runs beside the forward pass
+            _lib.check(lib.fbn_shard_index(C.byref(self.plan), C.byref(self._bs), _lib.ptr(sws), sws.numel(), _lib.stream_ptr()),
+                       "fbn_shard_index")
+        s = _lib.stream_ptr()
+        _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
+                                   _lib.ptr(self.step_counter), _lib.ptr(self.prob), s), "fbn_forward")
+        _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
+                                    _lib.ptr(self.dprob), s), "fbn_bce_loss")
+        _lib.check(lib.fbn_backward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, _lib.ptr(self.dprob),
+                                    C.byref(G), _lib.ptr(m._gflat), m._gflat.numel(), None, None, 0, 1, _lib.ptr(m._grad_sumsq), s),
+                   "fbn_backward")
+        cur.wait_stream(self._side)
+        _lib.check(lib.fbn_shard_local_sum(C.byref(self.plan), C.byref(self._bs), self._dX[0], self._dX[1], _lib.ptr(sws), sws.numel(), s),
+                   "fbn_shard_local_sum")
+
+    def _merge(self):
+        m, lib, st, s = self.model, self.lib, self.model._shard, _lib.stream_ptr()
+        if self.world > 1:     # norm of the all-reduced dense gradients
+            _lib.check(lib.fbn_sumsq(_lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(self.sumsq_scratch), _lib.ptr(m._grad_sumsq), s))
+        _lib.check(lib.fbn_shard_merge(C.byref(self.plan), _lib.ptr(st.sws), st.sws.numel(), _lib.ptr(m._item_grad), _lib.ptr(m._row_touched),
+                                       _lib.ptr(self._sq_local), s), "fbn_shard_merge")
+
+    def _update(self):
+        m, o, lib, st, s = self.model, self.opt, self.lib, self.model._shard, _lib.stream_ptr()
+        m._grad_sumsq[1:2].copy_(self._sq_local)
+        clip = None
+        if self.max_norm is not None:
+            _lib.check(lib.fbn_clip_coef(_lib.ptr(m._grad_sumsq), 2, float(self.max_norm), _lib.ptr(o._clip), s), "fbn_clip_coef")
+            clip = _lib.ptr(o._clip)
+        w = m.item_emb.weight.data
+        if self.lazy:
+            _lib.check(lib.fbn_shard_adam_rows(C.byref(self.plan), _lib.ptr(st.sws), st.sws.numel(), _lib.ptr(w), _lib.ptr(o._m_item),
+                                               _lib.ptr(o._v_item), clip, None, _lib.ptr(self.hyper_dev), s), "fbn_shard_adam_rows")
+        else:
+            _lib.check(lib.fbn_adam_table(_lib.ptr(w), _lib.ptr(o._m_item), _lib.ptr(o._v_item), _lib.ptr(m._item_grad),
+                                          _lib.ptr(m._row_touched), w.shape[0], clip, None, _lib.ptr(self.hyper_dev), s), "fbn_adam_table")
+        _lib.check(lib.fbn_adam_dense(_lib.ptr(m._flat), _lib.ptr(o._m_flat), _lib.ptr(o._v_flat), _lib.ptr(m._gflat), m._flat.numel(),
+                                      clip, None, _lib.ptr(self.hyper_dev), s), "fbn_adam_dense")
+        self.step_counter += 1
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.model._gflat, op=dist.ReduceOp.SUM)
+
+    def _allreduce_sumsq(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._sq_local, op=dist.ReduceOp.SUM)
+
+    def _barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._bar, op=dist.ReduceOp.SUM)
 
 
 class Scorer:

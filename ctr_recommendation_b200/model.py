@@ -121,7 +121,10 @@ class MM_FiBiNET(nn.Module):
 
     ``feature_map`` is accepted and ignored like in the reference; when it is a dict it may carry
     B200-side options (the reference's callers pass None):  {"precision": "fp32"|"tf32x3"|"bf16",
-    "bilinear_type": "all"|"each"|"interaction", "dropout": float}.  ``model_cfg`` keys other than
+    "bilinear_type": "all"|"each"|"interaction", "dropout": float, "table_sharding": "row", "item_rows": V,
+    "shard_rank": r, "shard_world": N}.  With ``table_sharding="row"`` the item table is partitioned by ``id % N`` over the
+    N ranks of the process group (see sharded.py): ``item_emb`` then holds this rank's (ceil(V/N),128) slice and training
+    goes through engine.ShardedTrainStep.  ``model_cfg`` keys other than
     ``embedding_dim`` are ignored exactly as the reference ignores them unless
     ``model_cfg["honor_config"]`` is true, in which case bilinear_type / net_dropout are honoured.
     """
@@ -143,8 +146,33 @@ class MM_FiBiNET(nn.Module):
         if self.precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {list(_lib.PRECISIONS)}")
         mm_input_dim = 128
+        self._shard = None
+        sharding = opts.get("table_sharding", None)
+        if sharding not in (None, "none", "replicated", "row"):
+            raise ValueError("table_sharding must be 'row' or None")
+        item_rows = int(opts.get("item_rows", ITEM_ROWS))
         # creation order == the reference's (same RNG consumption, same state_dict order)
-        self.item_emb = nn.Embedding(ITEM_ROWS, self.emb_dim, padding_idx=0)
+        if sharding == "row":
+            from . import sharded
+            import torch.distributed as dist
+            on = dist.is_available() and dist.is_initialized()
+            rank = int(opts.get("shard_rank", dist.get_rank() if on else 0))
+            world = int(opts.get("shard_world", dist.get_world_size() if on else 1))
+            self._shard = sharded.ShardState(item_rows, rank, world)
+            R = self._shard.shard_rows
+            if item_rows <= (1 << 22):
+                # same RNG consumption and the same values as the replicated table: initialise all rows, keep my slice
+                full = nn.Embedding(item_rows, self.emb_dim, padding_idx=0)
+                self.item_emb = nn.Embedding(R, self.emb_dim, _weight=sharded.slice_of_full(full.weight.data, rank, world))
+                del full
+            else:
+                g = torch.Generator().manual_seed(0x5EED + 7919 * rank)
+                self.item_emb = nn.Embedding(R, self.emb_dim, _weight=torch.randn(R, self.emb_dim, generator=g))
+                if rank == 0:
+                    with torch.no_grad():
+                        self.item_emb.weight[0].zero_()      # global row 0 = padding
+        else:
+            self.item_emb = nn.Embedding(item_rows, self.emb_dim, padding_idx=0)
         self.user_emb = nn.Embedding(USER_ROWS, self.emb_dim)   # allocated, never used
         self.cate_emb = nn.Embedding(CATE_ROWS, self.emb_dim)
         self.mm_proj = nn.Sequential(nn.Linear(mm_input_dim, self.emb_dim), nn.LayerNorm(self.emb_dim), nn.ReLU())
@@ -226,6 +254,12 @@ class MM_FiBiNET(nn.Module):
         P = _lib.Params()
         P.item_emb = self.item_emb.weight.data_ptr()
         P.item_rows = self.item_emb.weight.shape[0]
+        if self._shard is not None:
+            st = self._shard
+            P.item_rows = st.item_rows
+            P.n_shards, P.shard_rank, P.shard_rows = st.world, st.rank, st.shard_rows
+            for r, q in enumerate(st.ensure_table(self.item_emb.weight)):
+                P.shard[r] = q
         P.cate_rows = self.cate_emb.weight.shape[0]
         for (field, plist), (off, _) in zip(self._dense_params(), self._layout):
             setattr(P, field, self._flat.data_ptr() + 4 * off)
@@ -243,12 +277,15 @@ class MM_FiBiNET(nn.Module):
             setattr(G, field, self._gflat.data_ptr() + 4 * off)
         return G
 
+    def _ws_rows(self) -> int:
+        return 1 if self._shard is not None else self.item_emb.weight.shape[0]
+
     def _workspace(self, B: int, L: int):
         key = (B, L)
         ws = self._ws.get(key)
         if ws is None:
             lib = _lib.load()
-            nbytes = lib.fbn_workspace_bytes(B, L, self.item_emb.weight.shape[0])
+            nbytes = lib.fbn_workspace_bytes(B, L, self._ws_rows())
             if len(self._ws) >= 4:           # bound the cache (distinct tail-batch sizes)
                 self._ws.pop(next(iter(self._ws)))
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.item_emb.weight.device)
@@ -258,7 +295,7 @@ class MM_FiBiNET(nn.Module):
     def workspace_view(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Debug/test accessor: a named activation of the most recent forward (see fbn_workspace_offset)."""
         B, L, ws = self._cur["B"], self._cur["L"], self._cur["ws"]
-        off = _lib.load().fbn_workspace_offset(B, L, self.item_emb.weight.shape[0], name.encode())
+        off = _lib.load().fbn_workspace_offset(B, L, self._ws_rows(), name.encode())
         if off == C.c_size_t(-1).value:
             raise KeyError(name)
         n = 1
@@ -346,6 +383,9 @@ class MM_FiBiNET(nn.Module):
 
     def _run_backward(self, dprob: torch.Tensor):
         lib = _lib.load()
+        if self._shard is not None:
+            raise RuntimeError("row-sharded item table: loss.backward() through autograd is not supported -- the table gradient "
+                               "is exchanged between ranks; train with engine.ShardedTrainStep")
         cur = self._cur
         dev = cur["ws"].device
         rows = self.item_emb.weight.shape[0]

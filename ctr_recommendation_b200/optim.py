@@ -99,7 +99,7 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         h = _lib.AdamHyper(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                           float(g["weight_decay"]), self._step)
+                           float(g["weight_decay"]), self._step, 1.0 - float(g["betas"][0]), 1.0 - float(g["betas"][1]))
         clip = _lib.ptr(self._clip) if self._max_norm is not None else None
         st = _lib.stream_ptr()
         w = m.item_emb.weight.data

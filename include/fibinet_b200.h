@@ -87,7 +87,20 @@ typedef struct {
   float* b3;         /* mlp.8.bias (1) */
   int32_t bilinear_type; /* FBN_BILINEAR_* */
   int32_t precision;     /* FBN_PREC_* */
+  /* Row-sharded item table (BASELINE config 5; no counterpart in the reference, whose nn.DataParallel replicates
+   * the table, src/train_fibinet.py:69-70).  n_shards == 0: item_emb is the whole (item_rows,128) table.
+   * n_shards >= 1: global row g lives on rank g % n_shards at local row g / n_shards; shard[r] is the (peer-mapped,
+   * see fbn_ipc_*) base of rank r's (shard_rows,128) slice and item_emb == shard[shard_rank].  The forward gather then
+   * reads rows straight out of the owning GPU's HBM over NVLink -- no all-to-all, no staging copy.  In this mode the
+   * workspace is sized with item_rows = 1 (fbn_workspace_bytes) and fbn_backward leaves the table gradient to
+   * fbn_shard_*. */
+  int32_t n_shards;
+  int32_t shard_rank;
+  int64_t shard_rows;
+  const float* shard[16];
 } fbn_params_t;
+
+#define FBN_MAX_SHARDS 16
 
 /* Gradients of the dense parameters, same naming (item_emb's gradient is handled separately). */
 typedef struct {
@@ -167,9 +180,12 @@ int fbn_clip_coef(const float* sumsq, int n, float max_norm, float* out, fbn_str
 /* Hyper-parameters of torch.optim.Adam as the reference builds it (src/train_fibinet.py:78):
  * L2 weight decay folded into the gradient, bias corrections from the current beta1 (OneCycleLR
  * cycles it, :84-92).  step is the 1-based step count.  Every Adam entry point takes either this
- * struct (host values) or hyper_dev, a device array {lr, beta1, beta2, eps, wd, lr/(1-beta1^t),
- * sqrt(1-beta2^t), t} (CUDA-graph replay; filled by fbn_onecycle_hyper or by the host). */
-typedef struct { float lr, beta1, beta2, eps, weight_decay; int32_t step; } fbn_adam_t;
+ * struct (host values) or hyper_dev, a device array of 10 floats {lr, beta1, beta2, eps, wd, lr/(1-beta1^t),
+ * sqrt(1-beta2^t), t, 1-beta1, 1-beta2} (CUDA-graph replay; filled by fbn_onecycle_hyper or by the host).
+ * one_minus_beta1/2: torch evaluates `1 - beta` in double precision before it becomes an fp32 kernel scalar (for
+ * beta2 = 0.999 that differs from 1.0f - 0.999f by 1.3e-5 relative); pass those doubles rounded to float, or 0 to
+ * let the library derive them from the fp32 betas. */
+typedef struct { float lr, beta1, beta2, eps, weight_decay; int32_t step; float one_minus_beta1, one_minus_beta2; } fbn_adam_t;
 
 /* Dense-exact Adam over the whole embedding table, consuming the gradient rows produced by
  * fbn_backward: g = (touched ? grad[row] : 0) * coef + wd*p, then the Adam update, for EVERY row
@@ -189,6 +205,52 @@ int fbn_adam_dense(float* p, float* m, float* v, const float* grad, int64_t n, c
 int fbn_onecycle_hyper(int32_t* step_counter, int total_steps, float max_lr, float pct_start,
                        float div_factor, float final_div_factor, float base_momentum, float max_momentum,
                        float beta2, float eps, float weight_decay, float* hyper_dev, fbn_stream_t stream);
+
+/* ---- row-sharded item table: gradient exchange over peer memory --------------------------------------------------
+ * One process per GPU.  Every rank owns an "exchange block" of fbn_shard_xchg_bytes(cap) bytes (cap = the largest
+ * B*(1+L) of any rank) that all peers map with fbn_ipc_open.  Per step:
+ *   fbn_shard_index      ids only: occurrence keys (owner, local row), stable radix sort, run heads -> the rank's unique
+ *                        rows grouped by owner (may run concurrently with fbn_forward);
+ *   fbn_backward         with item_grad == NULL (dX rows stay in the workspace: "dXitem", "dXhist");
+ *   fbn_shard_local_sum  one warp per unique row sums its occurrences in source order into the exchange block;
+ *   -- any inter-rank barrier (the dense-gradient all-reduce is one) --
+ *   fbn_shard_merge      the OWNER pulls, over NVLink, every peer's partial rows for its slice, merges the N sorted lists
+ *                        by rank (stable: contributions are added in rank order, bitwise reproducible) and writes either a
+ *                        dense (shard_rows,128) gradient + touched flags (dense-exact Adam via fbn_adam_table) or a compact
+ *                        (row, gradient) list (lazy row Adam via fbn_shard_adam_rows); sumsq_out (1,) = sum(g^2) of the slice;
+ *   -- all-reduce of the sum of squares (clip) = barrier: the exchange blocks may be rewritten --
+ *   fbn_adam_table / fbn_shard_adam_rows on the local slice;
+ *   -- barrier before the next forward reads the updated rows remotely --                                              */
+typedef struct {
+  int32_t n_shards, rank;
+  int64_t item_rows;    /* global rows V */
+  int64_t shard_rows;   /* ceil(V / n_shards) */
+  int64_t cap;          /* occurrence capacity of every rank's exchange block */
+  int64_t merge_cap;    /* capacity (items) of the owner-side merge lists; <= n_shards * cap */
+  void* xchg[FBN_MAX_SHARDS]; /* peer-mapped exchange blocks; xchg[rank] is the local one */
+} fbn_shard_plan_t;
+size_t fbn_shard_xchg_bytes(int64_t cap);
+size_t fbn_shard_ws_bytes(int64_t cap, int64_t merge_cap, int n_shards, int64_t shard_rows);
+int fbn_shard_index(const fbn_shard_plan_t* s, const fbn_batch_t* b, void* sws, size_t sws_bytes, fbn_stream_t stream);
+int fbn_shard_local_sum(const fbn_shard_plan_t* s, const fbn_batch_t* b, const float* dXitem, const float* dXhist, void* sws,
+                        size_t sws_bytes, fbn_stream_t stream);
+/* dense_grad (shard_rows,128) + touched (shard_rows,) int32 [zeroed inside], or both NULL for the compact list kept in sws */
+int fbn_shard_merge(const fbn_shard_plan_t* s, void* sws, size_t sws_bytes, float* dense_grad, int32_t* touched,
+                    float* sumsq_out, fbn_stream_t stream);
+/* Lazy row Adam over the compact list of the last fbn_shard_merge: only touched rows move (g = grad*coef + wd*p, torch
+ * single-tensor op order, bias corrections from the global step) -- extension, the reference's Adam is dense. */
+int fbn_shard_adam_rows(const fbn_shard_plan_t* s, void* sws, size_t sws_bytes, float* p, float* m, float* v, const float* clip,
+                        const fbn_adam_t* h, const float* hyper_dev, fbn_stream_t stream);
+/* debug / tests: copies {U, owner_start[0..n], T, Um, overflow flag} of the last step to host_out (>= 24 int32); synchronises */
+int fbn_shard_stats(const fbn_shard_plan_t* s, void* sws, size_t sws_bytes, int32_t* host_out, fbn_stream_t stream);
+
+/* CUDA IPC plumbing for the peer-mapped buffers above (legacy cudaIpc*: memory must come from cudaMalloc, e.g. torch's
+ * default caching allocator without expandable_segments).  export: handle (64 bytes) of the allocation containing dev_ptr
+ * and dev_ptr's byte offset inside it.  open: maps the allocation into this process (peer access enabled lazily) and
+ * returns its base; open each distinct handle once per process.  close: unmaps a base returned by open. */
+int fbn_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
+int fbn_ipc_open(const void* handle, void** base_out);
+int fbn_ipc_close(void* base);
 
 /* sum of squares of n floats, deterministic; partial needs fbn_sumsq_partial_floats(n) floats;
  * out (1,) overwritten. */

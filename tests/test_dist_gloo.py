@@ -18,10 +18,10 @@ class _FakeModel:
         self._grad_sumsq = torch.zeros(2)
         self._dense_table_grad = False
 
-    def parameters(self):
+    def named_parameters(self):
         return []
 
-    def buffers(self):
+    def named_buffers(self):
         return []
 
 
@@ -47,6 +47,29 @@ def _worker(rank, world, port, out):
     assert abs(wgt - weight) < 1e-12 and shard["item_seq"].shape == (hi - lo, 3)
     pred = fdist.gather_predictions(lab * 2)
     assert torch.equal(pred, torch.arange(n).float() * 2)            # rank order == original row order
+    # row-sharded table host logic: slices -> all_gather -> the full table again; a model built with table_sharding="row"
+    # holds exactly its slice of the replicated initialisation
+    from ctr_recommendation_b200 import build_model, sharded
+    V = 1001
+    full = torch.arange(V * 4, dtype=torch.float32).reshape(V, 4)
+    mine = sharded.slice_of_full(full, rank, world)
+    assert mine.shape[0] == sharded.shard_rows(V, world)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    assert torch.equal(sharded.full_from_slices(parts, V), full)
+    torch.manual_seed(5)
+    rep = build_model({"item_rows": V}, {"embedding_dim": 128})
+    torch.manual_seed(5)
+    shd = build_model({"table_sharding": "row", "item_rows": V}, {"embedding_dim": 128})     # rank / world from the process group
+    assert (shd._shard.rank, shd._shard.world) == (rank, world)
+    assert torch.equal(shd.item_emb.weight.data, sharded.slice_of_full(rep.item_emb.weight.data, rank, world))
+    assert torch.equal(shd.mlp[0].weight.data, rep.mlp[0].weight.data)      # same RNG consumption as the replicated build
+
+    class _M:
+        pass
+    holder = _M()
+    holder._shard, holder.item_emb = shd._shard, shd.item_emb
+    assert torch.equal(sharded.gather_full_table(holder), rep.item_emb.weight.data)
     if rank == 0:
         out.put("ok")
     dist.barrier()

@@ -125,3 +125,55 @@ def test_loader_matches_reference_loader(tmp_path):
     coll = ours.BatchCollator(None, 20, a.column_index, str(tmp_path / "item_info.parquet"))
     with pytest.raises(KeyError):
         coll.lookup(np.array([1, 999999]))
+
+
+def test_row_partition_roundtrip():
+    """Row-sharded table partition (sharded.py): owner = g % N, local = g // N, slices interleave back to the table."""
+    import torch
+    from ctr_recommendation_b200 import sharded
+    from oracle import shard_numpy as sorc
+    for V in (2, 7, 64, 91718):
+        for N in (1, 2, 3, 8, 16):
+            R = sharded.shard_rows(V, N)
+            assert R == sorc.shard_rows(V, N) and R * N >= V > (R - 1) * N
+            g = np.arange(V)
+            o, l = sharded.owner_of(g, N), sharded.local_row(g, N)
+            assert np.array_equal(sharded.global_row(o, l, N), g) and l.max() < R
+            oo, ll = sorc.owner_local(g, N)
+            assert np.array_equal(o, oo) and np.array_equal(l, ll)
+            full = torch.arange(V * 2, dtype=torch.float32).reshape(V, 2)
+            slices = [sharded.slice_of_full(full, r, N) for r in range(N)]
+            assert all(s.shape == (R, 2) for s in slices)
+            assert np.array_equal(slices[N - 1].numpy(), sorc.slice_of(full.numpy(), N - 1, N))
+            assert torch.equal(sharded.full_from_slices(slices, V), full)
+
+
+def test_sharded_model_has_no_autograd_backward_and_needs_its_engine():
+    import torch
+    from ctr_recommendation_b200 import build_model, FusedAdam
+    from ctr_recommendation_b200.engine import TrainStep, ShardedTrainStep
+    m = build_model({"table_sharding": "row", "shard_rank": 2, "shard_world": 4, "item_rows": 1000}, {"embedding_dim": 128})
+    assert m.item_emb.weight.shape == (250, 128) and m._shard.shard_rows == 250
+    with pytest.raises(ValueError):
+        build_model({"table_sharding": "column"}, {"embedding_dim": 128})
+    plain = build_model(None, {"embedding_dim": 128})
+    with pytest.raises(TypeError):
+        ShardedTrainStep(plain, FusedAdam(plain), 8)
+
+
+def test_lazy_adam_oracle_matches_dense_adam_on_touched_rows():
+    """oracle/shard_numpy.lazy_adam_rows == oracle Adam (pinned against torch.optim.Adam by the golden vectors) on the rows
+    it touches, and is the identity elsewhere."""
+    from oracle import fibinet_numpy as orc
+    from oracle import shard_numpy as sorc
+    rng = np.random.default_rng(3)
+    p0 = rng.standard_normal((40, 8)).astype(np.float32)
+    g = rng.standard_normal((40, 8)).astype(np.float32)
+    touched = rng.random(40) < 0.4
+    P = {"w": p0.copy()}
+    opt = orc.Adam(lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    opt.step(P, {"w": g})
+    z = np.zeros_like(p0)
+    p, m, v = sorc.lazy_adam_rows(p0, z, z, g, touched, 3e-3, 0.9, 0.999, 1e-8, 1e-5, step=1)
+    assert np.array_equal(p[touched], P["w"][touched]) and np.array_equal(m[touched], opt.state["w"]["m"][touched])
+    assert np.array_equal(p[~touched], p0[~touched]) and np.all(m[~touched] == 0) and np.all(v[~touched] == 0)
