@@ -49,6 +49,11 @@ def parse():
                     help="bilinear_type (BASELINE config 2 sweep); the reference hard-codes 'all'")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train = the headline train step; infer = eval forward over the batch (Prediction.py loop body, BASELINE config 3)")
+    ap.add_argument("--sharding", default="replicated", choices=["replicated", "row"],
+                    help="row = item table partitioned by id %% N over the ranks (BASELINE config 5): remote gather over NVLink, "
+                         "owner-side gradient merge (engine.ShardedTrainStep)")
+    ap.add_argument("--item-rows", type=int, default=0, help="rows of the item table (default: the reference's 91718)")
+    ap.add_argument("--lazy", action="store_true", help="row sharding: lazy row Adam (touched rows only) instead of dense-exact Adam")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
 
@@ -111,10 +116,17 @@ def make_pool(args, rank, n):
     from oracle import synth
     table = synth.make_item_mm_table(seed=11)
     pool = []
+    big = args.item_rows > synth.V_ITEM
+    g = torch.Generator().manual_seed(4242 + rank)
     for i in range(n):
         b, y = synth.make_batch(seed=2025 + 1000 * rank + i, batch=args.batch, max_len=L_HIST, id_dist=args.id_dist,
                                 index_dtype=np.float64, mm_table=table, edge_cases=False)
         b.pop("user_id")
+        if big:    # scaled synthetic table: ids uniform over [1, V); the padding pattern of the history is kept
+            V = args.item_rows
+            b["item_id"] = torch.randint(1, V, (args.batch,), generator=g).numpy().astype(np.float64)
+            seq = torch.randint(1, V, (args.batch, L_HIST), generator=g).numpy()
+            b["item_seq"] = np.where(b["item_seq"] != 0, seq, 0).astype(np.int64)
         host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items()}
         pool.append((host, torch.from_numpy(y).pin_memory()))
     return pool
@@ -130,7 +142,15 @@ def run_ours(args):
     lib = _lib.load()
     _lib.check(lib.fbn_check_device(local), "fbn_check_device")
     torch.manual_seed(2025)
-    model = build_model({"precision": args.precision, "bilinear_type": args.bilinear}, {"embedding_dim": 128}).to(dev).train()
+    sharded = args.sharding == "row"
+    fm = {"precision": args.precision, "bilinear_type": args.bilinear}
+    if args.item_rows:
+        fm["item_rows"] = args.item_rows
+    if sharded:
+        fm["table_sharding"] = "row"
+        if args.eager or args.mode == "infer":
+            raise SystemExit("--sharding row is benchmarked through ShardedTrainStep (train mode, no --eager)")
+    model = build_model(fm, {"embedding_dim": 128}).to(dev).train()
     if world > 1:
         fdist.broadcast_parameters(model)
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
@@ -143,12 +163,16 @@ def run_ours(args):
     stage = ({k: torch.empty_like(v, device=dev) for k, v in pool[0][0].items()}, torch.empty_like(pool[0][1], device=dev))
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool[0][0].values()) + pool[0][1].numel() * 4
 
-    from ctr_recommendation_b200.engine import Scorer, TrainStep
+    from ctr_recommendation_b200.engine import Scorer, ShardedTrainStep, TrainStep
     infer = args.mode == "infer"
     if infer:
         model.eval()
-    engine = None if args.eager else (Scorer(model, args.batch, L_HIST, idx_dtype=torch.float64) if infer else
-                                      TrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0))
+    if sharded:
+        engine = ShardedTrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0, lazy=args.lazy,
+                                  merge_cap=4 * args.batch * (1 + L_HIST))
+    else:
+        engine = None if args.eager else (Scorer(model, args.batch, L_HIST, idx_dtype=torch.float64) if infer else
+                                          TrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0))
 
     def step(batch, labels):
         if infer:                    # scoring: forward only, predictions read back by the caller
@@ -233,17 +257,24 @@ def run_ours(args):
     global_batch = args.batch * world
     bil = "bilinear all" if args.bilinear == "all" else f"bilinear {args.bilinear} [not the reference's hard-coded 'all']"
     workload = (f"FiBiNET {'train step' if not infer else 'eval forward'} (config/fibinet_config.yaml model: D=128, 6 fields, {bil}, "
-                f"MLP 2688-512-256-1), per-GPU batch {args.batch}, history L={L_HIST}, item ids {args.id_dist}, replicated tables")
+                f"MLP 2688-512-256-1), per-GPU batch {args.batch}, history L={L_HIST}, item ids {args.id_dist}, " +
+                (f"item table of {model._shard.item_rows} rows row-sharded over {world} ranks (remote gather over NVLink, owner-side "
+                 f"gradient merge, {'lazy row' if args.lazy else 'dense-exact'} Adam)" if sharded else "replicated tables"))
     value = global_batch * args.steps / (ms / 1e3)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
     peaks = load_peaks()
-    kernels = kernel_rooflines(args, model, dev_pool[0], peaks, lib) if (rank == 0 and not infer) else {}
+    kernels = kernel_rooflines(args, model, dev_pool[0], peaks, lib) if (rank == 0 and not infer and not sharded) else {}
+    if sharded:
+        st_ = model._shard.stats()
+        if st_["overflow"]:
+            raise SystemExit("row sharding: merge capacity overflow")
     out = {
         "metric": METRIC if not infer else "inference samples/sec FiBiNET MicroLens-shape (Prediction.py path)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": workload,
-                   "global_batch": global_batch, "per_gpu_batch": args.batch, "parallelism": f"dp{world}",
+                   "global_batch": global_batch, "per_gpu_batch": args.batch,
+                   "parallelism": f"dp{world}" + ("+row-sharded item table" if sharded else ""),
                    "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
                    "l2": "working set per step (table p/m/v/grad 188 MB + activations) exceeds the 126 MB L2; inputs cycle over "
                          f"{args.pool} distinct batches"},

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "segsum.cuh"
 #include "tower.h"
 
 namespace fbn {
@@ -57,6 +58,9 @@ struct ShardWs {
   float* mgrad;     // (min(merge_cap, shard_rows), 128) compact list: summed gradient
   float* sq_partial;
   int sq_blocks;
+  float* lsq_partial;  // per-CTA scratch of the local segment sums (their sum of squares is not used)
+  int lsum_blocks;
+  void* seg_scratch;   // hot-row work lists of segsum.cuh
   void* cub_tmp; size_t cub_bytes;
   size_t total;
 };
@@ -90,6 +94,9 @@ static void carve_shard_ws(ShardWs& w, void* base, long long cap, long long merg
   w.mgrad = (float*)take((size_t)std::min(merge_cap, shard_rows) * D * sizeof(float));
   w.sq_blocks = sum_blocks();
   w.sq_partial = (float*)take((size_t)w.sq_blocks * sizeof(float));
+  w.lsum_blocks = 16 * num_sms();
+  w.lsq_partial = (float*)take((size_t)w.lsum_blocks * sizeof(float));
+  w.seg_scratch = take(seg_scratch_bytes(cap));
   size_t a = 0, b = 0, c = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr,
                                   (int)std::max<long long>(cap, 1), 0, key_bits_for((long long)n * shard_rows));
@@ -167,36 +174,6 @@ __global__ void shard_hdr_kernel(const int32_t* __restrict__ keys, const int32_t
       hdr[0] = uidx[n];
       ustart[uidx[n]] = pos;
     }
-  }
-}
-
-// one warp per unique row: sum its occurrences in source order (same inner loop as emb_rows_kernel, embbwd.cu)
-__global__ void __launch_bounds__(SH_WARPS * 32) shard_local_sum_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ustart,
-                                                                        const int32_t* __restrict__ src, const float* __restrict__ dXitem,
-                                                                        const float* __restrict__ dXhist, long long B, int L,
-                                                                        float* __restrict__ ugrad) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int U = hdr[0];
-  for (long long u = (long long)blockIdx.x * SH_WARPS + warp; u < U; u += (long long)gridDim.x * SH_WARPS) {
-    const int off = ustart[u], cnt = ustart[u + 1] - off;
-    float4 acc = f4(0.f);
-    for (int o0 = 0; o0 < cnt; o0 += 32) {
-      const int mine = (o0 + lane < cnt) ? __ldg(src + off + o0 + lane) : 0;
-      const int n = min(32, cnt - o0);
-      for (int k = 0; k < n; k += 4) {
-        float4 v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int s = __shfl_sync(0xffffffffu, mine, min(k + q, 31));
-          const float* p = s < B ? dXitem + (long long)s * D : dXhist + ((long long)(s - B) / L) * D;
-          v[q] = (k + q < n) ? ld4(p + 4 * lane) : f4(0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (k + q < n) acc += v[q];
-      }
-    }
-    st4(ugrad + u * D + 4 * lane, acc);
   }
 }
 
@@ -419,10 +396,16 @@ extern "C" int fbn_shard_local_sum(const fbn_shard_plan_t* s, const fbn_batch_t*
   const void* seq = (b->seq_len > 0 && b->item_seq) ? b->item_seq : nullptr;
   const long long n = b->batch * (1 + (seq ? b->seq_len : 0));
   Xchg x = xchg_view(s->xchg[s->rank], s->cap);
-  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, SH_WARPS), 8LL * num_sms()));
-  shard_local_sum_kernel<<<blocks, SH_WARPS * 32, 0, (cudaStream_t)stream>>>(x.hdr, w.ustart, w.vals_out, dXitem, dXhist, b->batch,
-                                                                             b->seq_len > 0 ? (int)b->seq_len : 1, x.ugrad);
-  FBN_CHECK_LAUNCH();
+  // one warp per unique row sums its occurrences in source order; hot rows are chunked (segsum.cuh) -- the same value,
+  // bit for bit, as the replicated table's emb_rows for that row
+  SegArgs g{};
+  g.off = w.ustart; g.cnt = nullptr; g.nseg_dev = x.hdr; g.nseg = 0; g.src = w.vals_out;
+  g.dXitem = dXitem; g.dXhist = dXhist; g.B = b->batch; g.L = b->seq_len > 0 ? (int)b->seq_len : 1;
+  g.out = x.ugrad; g.zero_fill = 0; g.sq_partial = w.lsq_partial;
+  g.hot = seg_carve(w.seg_scratch, s->cap);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, SEG_WARPS), w.lsum_blocks));
+  FBN_CHECK_CUDA(seg_sum_launch(g, blocks, s->cap, (cudaStream_t)stream));
+  g_launches += 3;
   return FBN_OK;
 }
 

@@ -124,7 +124,8 @@ def _virtual_exchange(env, world, V, B, L, seed, id_dist, lazy, integer_grads=Fa
 
 
 @pytest.mark.parametrize("world,V,B,L,id_dist", [(1, 5000, 300, 20, "zipf"), (2, 91718, 1024, 20, "zipf"), (3, 1000, 777, 20, "uniform"),
-                                                 (8, 91718, 512, 20, "uniform"), (8, 64, 256, 5, "uniform"), (4, 3001, 100, 0, "zipf")])
+                                                 (8, 91718, 512, 20, "uniform"), (8, 64, 256, 5, "uniform"), (4, 3001, 100, 0, "zipf"),
+                                                 (2, 5000, 4096, 20, "zipf")])     # last: hot rows (> 256 occurrences, chunked sums)
 @pytest.mark.parametrize("integer_grads", [True, False])
 def test_shard_exchange_vs_oracle(env, world, V, B, L, id_dist, integer_grads):
     res = _virtual_exchange(env, world, V, B, L, seed=500 + world, id_dist=id_dist, lazy=False, integer_grads=integer_grads)
