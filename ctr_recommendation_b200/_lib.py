@@ -89,6 +89,8 @@ _SIGNATURES = {
     "fbn_ipc_export": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
     "fbn_ipc_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
     "fbn_ipc_close": (C.c_int, [_vp]),
+    "fbn_time_stage": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_char_p, _vp, _sz, C.c_int, C.POINTER(C.c_float), _vp]),
+    "fbn_stage_report": (C.c_int, [C.c_char_p, _sz]),
     "fbn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "fbn_launch_count": (_u64, []),
     "fbn_last_error": (C.c_char_p, []),

@@ -3,6 +3,9 @@
 // per phase (and can be captured into a CUDA graph by the host).
 #include <algorithm>
 #include <stdarg.h>
+#include <string>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -182,6 +185,20 @@ struct PkReg {
 };
 static thread_local PkReg tl_reg;   // rebuilt at the start of every fbn_forward / fbn_backward call
 
+// Optional stage timing (fbn_set_option("stage_events", 1), eager launches only): a CUDA event is recorded on the calling
+// stream at every stage boundary of fbn_forward / fbn_backward; fbn_stage_report turns them into per-stage milliseconds.
+struct StageLog { bool on = false; std::vector<std::pair<std::string, cudaEvent_t>> ev; };
+static StageLog g_stage;
+static int stage_mark(const char* name, cudaStream_t st) {
+  if (!g_stage.on) return FBN_OK;
+  cudaEvent_t e;
+  FBN_CHECK_CUDA(cudaEventCreate(&e));
+  FBN_CHECK_CUDA(cudaEventRecord(e, st));
+  g_stage.ev.emplace_back(name, e);
+  return FBN_OK;
+}
+void set_stage_events(int on) { g_stage.on = on != 0; }
+
 // launchers defined in embed.cu
 struct EmbedFwdArgs;
 struct EmbedBwdArgs;
@@ -192,6 +209,7 @@ struct EmbedBwdArgs;
 
 using namespace fbn;
 
+#define STAGE(name) RC(stage_mark(name, st))
 #define RC(x)            \
   do {                   \
     int _rc = (x);       \
@@ -368,30 +386,38 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
 
   // activations are converted to the operand format by the kernels that produce them (no separate pack pass)
   const PackDst pkC = tl_reg.dst(w.C, B, K1, w.pk_C);
+  STAGE("fwd:start");
   RC(run_embed_fwd(p, b, w, 1, st, pkC, tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm)));
   (void)fmask;
   if (parf) RC(side_join(st));
+  STAGE("fwd:embed+senet (join weight packing)");
   RC(bilinear_transform_fwd(p, w, st));
+  STAGE("fwd:bilinear transforms");
   RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, pkC, st));
+  STAGE("fwd:bilinear pairs");
 
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   GemmArgs g1;
   g1.A = w.C; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = K1; g1.lda = K1; g1.ldb = K1; g1.ldc = H1;
   g1.b_t = 1; g1.kmask = active_mask();
   RC(tl_reg.run(g1, w));
+  STAGE("fwd:mlp1 gemm");
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
   DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
   RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst(w.A1, B, H1, w.pk_A1), st));
+  STAGE("fwd:bn1 stats+act");
 
   GemmArgs g2;
   g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2;
   g2.b_t = 1;
   RC(tl_reg.run(g2, w));
+  STAGE("fwd:mlp2 gemm");
   if (train) RC(bn_train_stats(w.Hd2, B, H2, w.partial, mean2, rstd2, p->bn2_mean, p->bn2_var, st));
   else RC(bn_eval_stats(p->bn2_mean, p->bn2_var, H2, mean2, rstd2, st));
   DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2; d2.step_dev = step_counter_dev;
   RC(head_fwd(w.Hd2, mean2, rstd2, p->bn2_g, p->bn2_b, p->w3, p->b3, B, d2, w.A2, w.logit, w.prob, st));
+  STAGE("fwd:bn2 stats+head");
   if (prob_out) FBN_CHECK_CUDA(cudaMemcpyAsync(prob_out, w.prob, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
   return FBN_OK;
 }
@@ -482,10 +508,12 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   const unsigned long long amask = active_mask();
 
   // ---- head + layer 2 ----
+  STAGE("bwd:start");
   RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
                     st));
   RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
                    tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
+  STAGE("bwd:head + bn2");
   const bool par = side_ready(st);
   cudaStream_t ls = par ? g_side.s : st;          // stream of the leaf computations
   float* lp = par ? w.partial_side : w.partial;   // and their scratch
@@ -497,10 +525,12 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
     RC(tl_reg.run(d, w));
   }
+  STAGE("bwd:mlp2 dgrad (+side: wgrad2)");
   // ---- layer 1 ----
   RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
   RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
                    tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
+  STAGE("bwd:bn1");
   if (par) RC(side_fork(st, 1));
   RC(colsum(w.dH1, B, H1, lp, g->b1, ls));
   RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, ls, lp));
@@ -509,10 +539,12 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
     RC(tl_reg.run(d, w));
   }
+  STAGE("bwd:mlp1 dgrad (+side: wgrad1)");
   // ---- bilinear ----
   const int type = p->bilinear_type;
   const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
   RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, tl_reg.dst(w.dT, B, (long long)nT * D, w.pk_dT), st));
+  STAGE("bwd:bilinear pairs");
   {
     GemmArgs d;  // dV[src] += dT_t * W^T
     d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
@@ -532,6 +564,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
         }
     }
   }
+  STAGE("bwd:bilinear dgrad");
   {
     // dW[idx] = sum_t V_src^T dT_t  (split-K over the batch, fixed-order reduction) -- a leaf: side stream
     if (par) RC(side_fork(st, 2));
@@ -573,6 +606,7 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   const int eb = embed_bwd_blocks(B);
   FBN_REQUIRE((size_t)eb * p->cate_rows * D <= (size_t)2 * 148 * 4 * MAX_CATE * D, FBN_ERR_ARG, "internal: cate scratch too small");
   RC(launch_embed_senet_bwd(e, eb, st));
+  STAGE("bwd:embed+senet");
   if (par) RC(side_fork(st, 3));
   RC(launch_reduce_partials(w.partial_cate, g->cate_emb, eb, p->cate_rows * D, 0, ls));
   RC(launch_senet_param_grads(w.sestat, B, lp, g->se_w1, g->se_b1, g->se_w2, g->se_b2, ls));
@@ -586,11 +620,84 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     if (!index_ready) RC(emb_index(eg, st));
     RC(emb_rows(eg, st));
   }
+  STAGE("bwd:table rows");
   if (par) RC(side_join(st));     // every dense gradient is complete from here on
+  STAGE("bwd:join side stream (leaf gradients)");
   if (dense_grad_flat) {
     FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");
     RC(sumsq(dense_grad_flat, dense_grad_n, w.partial, grad_sumsq, st));
   }
+  STAGE("bwd:dense sumsq");
+  return FBN_OK;
+}
+
+// Per-stage device times of the calls made since the last report (see stage_mark): "name<TAB>ms" lines.  Synchronises.
+extern "C" int fbn_stage_report(char* buf, size_t buf_bytes) {
+  FBN_REQUIRE(buf && buf_bytes > 0, FBN_ERR_ARG, "fbn_stage_report: null buffer");
+  FBN_CHECK_CUDA(cudaDeviceSynchronize());
+  std::string out;
+  for (size_t i = 1; i < g_stage.ev.size(); ++i) {
+    float ms = 0.f;
+    if (g_stage.ev[i].first.find(":start") == std::string::npos) {
+      FBN_CHECK_CUDA(cudaEventElapsedTime(&ms, g_stage.ev[i - 1].second, g_stage.ev[i].second));
+      char line[160];
+      snprintf(line, sizeof(line), "%s\t%.4f\n", g_stage.ev[i].first.c_str(), ms);
+      out += line;
+    }
+  }
+  for (auto& e : g_stage.ev) cudaEventDestroy(e.second);
+  g_stage.ev.clear();
+  snprintf(buf, buf_bytes, "%s", out.c_str());
+  return FBN_OK;
+}
+
+// Benchmark helper: mean CUDA-event duration of ONE stage of the forward pass exactly as fbn_forward runs it (same operands,
+// same strides, same launch configuration), after a complete fbn_forward on the same workspace.  stage: "bil_gemm"
+// (bilinear transforms), "bil_pairs" (Hadamard pairs into C), "embed" (gather + SENET), "mlp1" (MLP-1 forward GEMM).
+extern "C" int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, const char* stage, void* flush,
+                              size_t flush_bytes, int iters, float* ms_out, fbn_stream_t stream) {
+  RC(check_common(p, b, ws, ws_bytes));
+  FBN_REQUIRE(stage && ms_out && iters > 0, FBN_ERR_ARG, "fbn_time_stage: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve_workspace(w, ws, b->batch, b->seq_len, ws_rows(p));
+  const long long B = b->batch;
+  tl_reg = PkReg();
+  tl_reg.prec = p->precision; tl_reg.st = st;
+  const int nW = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
+  tl_reg.describe(p->w1, H1, K1, w.pk_w1);
+  tl_reg.describe(p->w2, H2, H1, w.pk_w2);
+  tl_reg.describe(p->bil_w, (long long)nW * D, D, w.pk_bil);
+  const PackDst pkC = tl_reg.dst(w.C, B, K1, w.pk_C);
+  const PackDst pkX = tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm);
+  const std::string s(stage);
+  cudaEvent_t e0, e1;
+  FBN_CHECK_CUDA(cudaEventCreate(&e0));
+  FBN_CHECK_CUDA(cudaEventCreate(&e1));
+  float total = 0.f;
+  for (int it = 0; it < iters + 1; ++it) {
+    if (flush) FBN_CHECK_CUDA(cudaMemsetAsync(flush, it, flush_bytes, st));
+    FBN_CHECK_CUDA(cudaEventRecord(e0, st));
+    if (s == "bil_gemm") RC(bilinear_transform_fwd(p, w, st));
+    else if (s == "bil_pairs") RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, pkC, st));
+    else if (s == "embed") RC(run_embed_fwd(p, b, w, 1, st, pkC, pkX));
+    else if (s == "mlp1") {
+      GemmArgs g1;
+      g1.A = w.C; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = K1; g1.lda = K1; g1.ldb = K1; g1.ldc = H1;
+      g1.b_t = 1; g1.kmask = active_mask();
+      RC(tl_reg.run(g1, w));
+    } else {
+      FBN_REQUIRE(false, FBN_ERR_ARG, "fbn_time_stage: unknown stage '%s'", stage);
+    }
+    FBN_CHECK_CUDA(cudaEventRecord(e1, st));
+    FBN_CHECK_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    FBN_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (it > 0) total += ms;      // first iteration = warm-up
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = total / iters;
   return FBN_OK;
 }
 
@@ -688,6 +795,7 @@ extern "C" int fbn_set_option(const char* name, int value) {
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
   if (strcmp(name, "side_streams") == 0) { g_use_side = value; return FBN_OK; }
   if (strcmp(name, "tc_persistent") == 0) { fbn::set_tc_persistent(value); return FBN_OK; }
+  if (strcmp(name, "stage_events") == 0) { set_stage_events(value); return FBN_OK; }
   set_error("fbn_set_option: unknown option '%s'", name);
   return FBN_ERR_ARG;
 }

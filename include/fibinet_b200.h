@@ -291,6 +291,14 @@ size_t fbn_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K, int precision);
 int fbn_time_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int a_t, int b_t, uint64_t kmask,
                   int precision, void* scratch, size_t scratch_bytes, void* flush, size_t flush_bytes, int iters, float* ms_out,
                   fbn_stream_t stream);
+/* Benchmark helper: mean CUDA-event duration (ms) of one stage of the forward pass exactly as fbn_forward launches it, after a
+ * complete fbn_forward on the same workspace: "embed", "bil_gemm", "bil_pairs", "mlp1".  `flush` is overwritten before
+ * every timed launch (L2 eviction).  Synchronises the stream. */
+int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, const char* stage, void* flush,
+                   size_t flush_bytes, int iters, float* ms_out, fbn_stream_t stream);
+/* With fbn_set_option("stage_events", 1) (eager launches only, not under graph capture) fbn_forward / fbn_backward record a CUDA
+ * event at every stage boundary; this writes "stage<TAB>milliseconds" lines for the calls since the last report.  Synchronises. */
+int fbn_stage_report(char* buf, size_t buf_bytes);
 /* runtime knobs: "tc_pair" (1 = CTA-pair 256x256 tcgen05 tiles for large GEMMs [default], 0 = single-CTA 128x128) */
 int fbn_set_option(const char* name, int value);
 /* number of kernels this library has launched so far in this process (host-side counter) */
