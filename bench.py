@@ -54,6 +54,7 @@ def parse():
                          "owner-side gradient merge (engine.ShardedTrainStep)")
     ap.add_argument("--item-rows", type=int, default=0, help="rows of the item table (default: the reference's 91718)")
     ap.add_argument("--lazy", action="store_true", help="row sharding: lazy row Adam (touched rows only) instead of dense-exact Adam")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
 
@@ -141,6 +142,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib = _lib.load()
     _lib.check(lib.fbn_check_device(local), "fbn_check_device")
+    for kv in args.opt:
+        name, val = kv.split("=")
+        _lib.check(lib.fbn_set_option(name.encode(), int(val)), f"fbn_set_option({kv})")
     torch.manual_seed(2025)
     sharded = args.sharding == "row"
     fm = {"precision": args.precision, "bilinear_type": args.bilinear}

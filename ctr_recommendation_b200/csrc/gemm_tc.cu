@@ -897,8 +897,15 @@ bool gemm_tc_supported(const GemmArgs& g, int precision) {
   return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16) && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch >= 1;
 }
 
-static int g_tc_persistent = 0;   // fbn_set_option("tc_persistent", 1) -> persistent tile loop (measured: no gain, kept as an option)
+// fbn_set_option("tc_persistent", v): 1 = every single-CTA launch runs the persistent tile loop (epilogue of tile i overlapped with
+// the loads / MMAs of tile i+1), -1 = never, 0 (default) = per-launch heuristic below.
+// Measured on B200 (tools/shortk_probe.py, tools/stage_probe.py, B = 65536): the four batched bilinear transforms (K = N = 128)
+// 115 -> 86 us (tf32x3), 75 -> 43 us (bf16); bf16 short-K GEMMs beat even the CTA-pair kernel (data gradient 1: 394 -> 279 us,
+// MLP-2 forward 51 -> 41, data gradient 2: 70 -> 45) because with one bf16 pass the epilogue, not the tensor pipe, is the limit;
+// tf32x3 long-K GEMMs lose (MLP-1 forward 533 -> 727 us), so they keep one tile per CTA / CTA pairs.
+static int g_tc_persistent = 0;
 void set_tc_persistent(int on) { g_tc_persistent = on; }
+static bool use_persistent(bool heuristic) { return g_tc_persistent > 0 || (g_tc_persistent == 0 && heuristic); }
 
 template <int MODE, bool A_MN, bool B_MN>
 static int launch_tcp(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st) {
@@ -916,9 +923,9 @@ static int launch_tcp(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream
 }
 
 template <int MODE, bool A_MN, bool B_MN>
-static int launch_tc(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st) {
+static int launch_tc(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream_t st, bool persist = false) {
   using Cfg = TcCfg<MODE>;
-  if (g_tc_persistent) return launch_tcp<MODE, A_MN, B_MN>(maps, t, grid, st);
+  if (use_persistent(persist)) return launch_tcp<MODE, A_MN, B_MN>(maps, t, grid, st);
   static bool attr = false;
   if (!attr) {
     FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -977,10 +984,12 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
       t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
       t.a_bc = (int)a_bc; t.a_br = (int)a_br; t.b_bc = (int)b_bc; t.b_br = (int)b_br; t.strideC = g.strideC;
       dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)(g.splits * g.batch));
-      if (a_mn && b_mn) return launch_tc<MODE, true, true>(maps, t, grid, st);
-      if (a_mn) return launch_tc<MODE, true, false>(maps, t, grid, st);
-      if (b_mn) return launch_tc<MODE, false, true>(maps, t, grid, st);
-      return launch_tc<MODE, false, false>(maps, t, grid, st);
+      // short K, many tiles (the bilinear transforms / their data gradients): the tile loop hides the epilogue
+      const bool persist = g.K <= 256 && g.splits == 1 && (long long)grid.x * grid.y * grid.z >= 2LL * num_sms();
+      if (a_mn && b_mn) return launch_tc<MODE, true, true>(maps, t, grid, st, persist);
+      if (a_mn) return launch_tc<MODE, true, false>(maps, t, grid, st, persist);
+      if (b_mn) return launch_tc<MODE, false, true>(maps, t, grid, st, persist);
+      return launch_tc<MODE, false, false>(maps, t, grid, st, persist);
     }
   }
   for (int bi = 0; bi < g.batch; ++bi) {
@@ -1023,7 +1032,10 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     // CTA pairs (256 x 256 tiles, half the L2 traffic per MMA) once they can fill most of the 148 SMs; small problems
     // keep the 128 x 128 single-CTA tiles (4x as many CTAs)
     const long long pair_ctas = 2 * cdiv(g.M, 256) * cdiv(g.N, TC2_BN) * g.splits;
-    if (g_tc_pair && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {
+    // one bf16 pass with K <= 512 is epilogue-bound: the persistent single-CTA tile loop beats the pair kernel there
+    const long long single_tiles = cdiv(g.M, TC_BM) * (g.N / TC_BN);
+    const bool persist = MODE == FBN_PREC_BF16 && g.splits == 1 && g.K <= 512 && single_tiles >= 2LL * num_sms();
+    if (g_tc_pair && !use_persistent(persist) && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {
       dim3 grid2((unsigned)(2 * cdiv(g.M, 256)), (unsigned)cdiv(g.N, TC2_BN), (unsigned)g.splits);
       if (a_mn && b_mn) rc = launch_tc2<MODE, true, true>(maps, t, grid2, st);
       else if (a_mn) rc = launch_tc2<MODE, true, false>(maps, t, grid2, st);
@@ -1033,10 +1045,10 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
       continue;
     }
     dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)g.splits);
-    if (a_mn && b_mn) rc = launch_tc<MODE, true, true>(maps, t, grid, st);
-    else if (a_mn) rc = launch_tc<MODE, true, false>(maps, t, grid, st);
-    else if (b_mn) rc = launch_tc<MODE, false, true>(maps, t, grid, st);
-    else rc = launch_tc<MODE, false, false>(maps, t, grid, st);
+    if (a_mn && b_mn) rc = launch_tc<MODE, true, true>(maps, t, grid, st, persist);
+    else if (a_mn) rc = launch_tc<MODE, true, false>(maps, t, grid, st, persist);
+    else if (b_mn) rc = launch_tc<MODE, false, true>(maps, t, grid, st, persist);
+    else rc = launch_tc<MODE, false, false>(maps, t, grid, st, persist);
     if (rc) return rc;
   }
   return FBN_OK;

@@ -299,7 +299,9 @@ int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t
 /* With fbn_set_option("stage_events", 1) (eager launches only, not under graph capture) fbn_forward / fbn_backward record a CUDA
  * event at every stage boundary; this writes "stage<TAB>milliseconds" lines for the calls since the last report.  Synchronises. */
 int fbn_stage_report(char* buf, size_t buf_bytes);
-/* runtime knobs: "tc_pair" (1 = CTA-pair 256x256 tcgen05 tiles for large GEMMs [default], 0 = single-CTA 128x128) */
+/* runtime knobs: "tc_pair" (1 = CTA-pair 256x256 tcgen05 tiles for large GEMMs [default], 0 = single-CTA 128x128),
+ * "tc_persistent" (0 = per-launch heuristic [default]: persistent tile loop for short-K / bf16 epilogue-bound GEMMs,
+ * 1 = always, -1 = never), "stage_events" (see fbn_stage_report) */
 int fbn_set_option(const char* name, int value);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 uint64_t fbn_launch_count(void);

@@ -41,3 +41,61 @@ def test_tcgen05_gemm_layouts(precision, tol, a_t, b_t, M, N, K):
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err <= tol, err
+
+
+@pytest.fixture
+def knobs():
+    from ctr_recommendation_b200 import _lib
+    lib = _lib.load()
+    yield lib
+    lib.fbn_set_option(b"tc_pair", 1)
+    lib.fbn_set_option(b"tc_persistent", 0)
+
+
+@pytest.mark.parametrize("pair,persistent", [(1, 0), (0, -1), (0, 1), (1, 1)])
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 3e-6), ("bf16", 6e-3)])
+@pytest.mark.parametrize("a_t,b_t,M,N,K", [(False, True, 40000, 256, 512), (False, False, 40000, 512, 256), (False, False, 39000, 128, 128),
+                                           (True, False, 512, 384, 5000), (False, True, 300, 512, 2688)])
+def test_tcgen05_kernel_variants(knobs, pair, persistent, precision, tol, a_t, b_t, M, N, K):
+    """Every tcgen05 kernel variant the dispatcher can pick -- CTA pairs, one tile per CTA, the persistent tile loop (forced on /
+    off / chosen by the heuristic at these sizes) -- against an fp64 matmul."""
+    from ctr_recommendation_b200.functional import gemm
+    knobs.fbn_set_option(b"tc_pair", pair)
+    knobs.fbn_set_option(b"tc_persistent", persistent)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Bm = torch.randn(K, N, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = (A.double() @ Bm.double() + bias.double()).float()
+    a_in = A.t().contiguous() if a_t else A
+    b_in = Bm.t().contiguous() if b_t else Bm
+    out = gemm(a_in, b_in, bias, a_t=a_t, b_t=b_t, precision=precision)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= tol, err
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+def test_model_step_identical_under_kernel_variants(knobs, precision):
+    """The train forward/backward of a batch large enough for the persistent-kernel heuristic (B = 40000: 4 x 313 bilinear tiles)
+    gives the same probabilities and gradients whichever GEMM kernel variant runs (same MMA order per tile -> bitwise)."""
+    from gpu_common import make_model, to_dev, named_grads
+    from oracle import synth
+    B = 40000
+    batch, labels = synth.make_batch(seed=31, batch=B, id_dist="uniform", index_dtype=np.float64, edge_cases=False)
+    outs = []
+    for pair, persistent in ((1, 0), (1, -1), (0, 1)):
+        knobs.fbn_set_option(b"tc_pair", pair)
+        knobs.fbn_set_option(b"tc_persistent", persistent)
+        model = make_model(train=True, precision=precision)
+        model.dropout_p = 0.0
+        y = model(to_dev(batch))
+        torch.nn.BCELoss()(y, torch.from_numpy(labels).cuda()).backward()
+        outs.append((y.detach().clone(), {k: torch.from_numpy(v) for k, v in named_grads(model).items()}))
+        del model
+    for y, g in outs[1:]:
+        assert torch.allclose(y, outs[0][0], rtol=0, atol=2e-6 if precision == "tf32x3" else 2e-3)
+        for k in g:
+            ref = outs[0][1][k]
+            err = (g[k] - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+            assert err <= (1e-5 if precision == "tf32x3" else 5e-2), (k, err)
