@@ -35,9 +35,12 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
   float* xs_all = smem + D * D;
   __shared__ float s_se[SE_R * NF + SE_R + NF * SE_R + NF];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // k-major copy of mm_w, float4 columns XOR-swizzled by k so that the transposing stores below are 4-way instead of 32-way
+  // bank-conflicted (the prologue is paid by every CTA and dominates small batches)
+#pragma unroll 8
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
-    int j = i >> 7, k = i & 127;  // mm_w[j][k], coalesced read
-    Wt[k * D + j] = __ldg(a.mm_w + i);
+    const int j = i >> 7, k = i & 127;  // mm_w[j][k], coalesced read
+    Wt[k * D + ((((j >> 2) ^ (k & 31)) << 2) | (j & 3))] = __ldg(a.mm_w + i);
   }
   if (threadIdx.x < SE_R * NF) s_se[threadIdx.x] = a.se_w1[threadIdx.x];
   if (threadIdx.x < SE_R) s_se[SE_R * NF + threadIdx.x] = a.se_b1[threadIdx.x];
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
 #pragma unroll
         for (int s = 0; s < EMB_SPW; ++s) xv[s] = xs[k * EMB_SPW + s];
       }
-      const float4 wv = *reinterpret_cast<const float4*>(Wt + k * D + 4 * lane);
+      const float4 wv = *reinterpret_cast<const float4*>(Wt + k * D + 4 * (lane ^ (k & 31)));
 #pragma unroll
       for (int s = 0; s < EMB_SPW; ++s) {
         y[s].x = fmaf(xv[s], wv.x, y[s].x); y[s].y = fmaf(xv[s], wv.y, y[s].y);
@@ -230,7 +233,7 @@ int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
   }
   const long long ngroups = (a.B + EMB_SPW - 1) / EMB_SPW;
   long long blocks = (ngroups + EMB_WARPS - 1) / EMB_WARPS;
-  const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (72 KB smem each)
+  const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (72 KB smem each; 3 per SM measured slower: 342 vs 320 us)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (a.nshard > 0) embed_senet_fwd_kernel<true><<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);

@@ -248,3 +248,16 @@ def test_sharded_lazy_adam_vs_oracle(env):
     assert rel_err(ob._m_item.cpu().numpy()[touched], m[touched]) <= 1e-5
     assert rel_err(ob._v_item.cpu().numpy()[touched], v[touched]) <= 1e-5
     assert np.all(ob._m_item.cpu().numpy()[~touched] == 0)
+
+
+def test_sharded_scorer_matches_replicated(env):
+    """Inference (Prediction.py loop body) over a row-sharded table == the replicated model, bit for bit."""
+    from ctr_recommendation_b200.engine import Scorer
+    a, b = _plain_model(env), _sharded_model(env)
+    a.eval(); b.eval()
+    B = 1000
+    sa, sb = Scorer(a, B, 20, idx_dtype=torch.int64), Scorer(b, B, 20, idx_dtype=torch.int64)
+    for s in range(2):
+        batch, _ = synth.make_batch(seed=60 + s, batch=B, id_dist="zipf", index_dtype=np.int64)
+        dev = env["to_dev"]({k: v for k, v in batch.items() if k != "user_id"})
+        assert torch.equal(sa(dev), sb(dev))

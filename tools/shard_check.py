@@ -127,6 +127,55 @@ def main():
         print(f"shard_check scale: V={V} rows over {world} ranks ({V / world * 512 * 3 / 2**30:.1f} GiB p/m/v per GPU), per-GPU batch {Bp}, "
               f"lazy row Adam: {ms.item() / args.steps:.3f} ms/step, {sps / 1e6:.2f} M samples/s; U={st['U']} T={st['T']} Um={st['Um']} "
               f"loss {loss:.4f}", flush=True)
+    # ---- 3. where the time goes: the stages of the sharded step, eager, CUDA events (all ranks run them at the same time,
+    #         so the remote loads of every rank share the NVLink fabric as they do in the real step)
+    import ctypes as C
+    from ctr_recommendation_b200 import _lib
+    lib = _lib.load()
+    eng._use_graph = False
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")
+    b0, y0 = pool[0]
+    eng.inp.load(b0, y0)
+    eng._write_hyper()
+
+    def timed(fn, reps=5):
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            if world > 1:
+                dist.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            fn()
+            t1.record()
+            torch.cuda.synchronize()
+            tot += t0.elapsed_time(t1)
+        return tot / reps
+    P = big._params_struct()
+    msf = C.c_float(0)
+    if world > 1:
+        dist.barrier()
+    _lib.check(lib.fbn_time_stage(C.byref(P), C.byref(eng._bs), _lib.ptr(eng.ws), eng.ws.numel(), b"embed", _lib.ptr(flush), flush.numel(),
+                                  5, C.byref(msf), _lib.stream_ptr()), "fbn_time_stage")
+    t_gather = float(msf.value)
+    eng._fwd_bwd()
+    if world > 1:
+        dist.barrier()
+    t_merge = timed(eng._merge)
+    t_update = timed(eng._update)
+    nvalid = int((b0["item_seq"] != 0).sum().item()) + Bp
+    remote = nvalid * 512 * (world - 1) / world
+    st = big._shard.stats()
+    pulled = st["T"] * 512 * (world - 1) / world
+    res = torch.tensor([t_gather, t_merge, t_update], device="cuda")
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        tg, tm, tu = (float(x) for x in res)
+        print(f"shard_check stages (max over ranks, B={Bp}/GPU): gather+SENET fwd {tg * 1e3:.0f} us ({remote / 1e6:.0f} MB of remote rows/GPU"
+              f" = {remote / tg / 1e6:.0f} GB/s over NVLink, {(nvalid * 512 + Bp * 12000) / tg / 1e6:.0f} GB/s total); owner-side merge "
+              f"{tm * 1e3:.0f} us ({pulled / 1e6:.0f} MB of partial rows pulled = {pulled / tm / 1e6:.0f} GB/s); clip + lazy row Adam "
+              f"({st['Um']} rows, {st['Um'] * 3072 / 1e6:.0f} MB) + dense Adam {tu * 1e3:.0f} us", flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
