@@ -85,7 +85,7 @@ int emb_rows(const EmbGradArgs& a, cudaStream_t st) {
   SegArgs s{};
   s.off = a.row_off; s.cnt = a.row_count; s.nseg_dev = nullptr; s.nseg = a.rows; s.src = a.vals_out;
   s.dXitem = a.dXitem; s.dXhist = a.dXhist; s.B = a.B; s.L = a.L > 0 ? a.L : 1;
-  s.out = a.grad; s.zero_fill = a.zero_fill; s.sq_partial = a.sumsq_partial;
+  s.out = a.grad; s.zero_fill = a.zero_fill; s.sq_partial = a.sumsq_partial; s.nseg_bound = a.rows;
   s.hot = seg_carve(static_cast<char*>(a.cub_tmp) + sort_bytes(n, a.rows), n);
   FBN_CHECK_CUDA(seg_sum_launch(s, nb, n, st));
   g_launches += 3;

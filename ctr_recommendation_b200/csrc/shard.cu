@@ -239,7 +239,11 @@ __global__ void merge_rank_kernel(long long cap, int n, const int32_t* __restric
   }
 }
 
-// one warp per merged item; head warps add the <= N partial rows of their local row in rank order (remote 512-byte loads)
+// One warp per block of 32 merged items.  A warp owns the runs (equal local rows, <= N items, in rank order) whose head lies in
+// its block and walks their items as one stream, MS_ILP at a time: MS_ILP independent 512-byte (remote) row loads in flight, then
+// the adds in stream order with a store at every run end.  (One row per warp in flight was latency-bound: 437 GB/s over NVLink.)
+constexpr int MS_ILP = 8;
+
 __global__ void __launch_bounds__(SH_WARPS * 32) merge_sum_kernel(PeerPtrs peers, long long cap, int32_t* mhdr, long long merge_cap,
                                                                   const int32_t* __restrict__ mkey, const int32_t* __restrict__ mval,
                                                                   const int32_t* __restrict__ mflags, const int32_t* __restrict__ midx,
@@ -249,26 +253,57 @@ __global__ void __launch_bounds__(SH_WARPS * 32) merge_sum_kernel(PeerPtrs peers
   __shared__ float s_sq[SH_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = mhdr[0];
+  const int icap = (int)cap;
   float sq = 0.f;
-  for (long long t = (long long)blockIdx.x * SH_WARPS + warp; t < T; t += (long long)gridDim.x * SH_WARPS) {
-    if (!mflags[t]) continue;   // warp-uniform
-    const int row = mkey[t];
+  for (long long t0 = ((long long)blockIdx.x * SH_WARPS + warp) * 32; t0 < T; t0 += (long long)gridDim.x * SH_WARPS * 32) {
+    // this block and a 32-item look-ahead (a run never exceeds FBN_MAX_SHARDS = 16 items)
+    const long long ta = t0 + lane, tb = t0 + 32 + lane;
+    const int f0 = ta < T ? mflags[ta] : 0, f1 = tb < T ? mflags[tb] : 0;
+    const int k0 = ta < T ? mkey[ta] : 0;
+    const int v0 = ta < T ? mval[ta] : 0, v1 = tb < T ? mval[tb] : 0;
+    const int x0 = ta < T ? midx[ta] : 0;
+    const unsigned h0 = __ballot_sync(0xffffffffu, f0 != 0), h1 = __ballot_sync(0xffffffffu, f1 != 0);
+    if (h0 == 0) continue;                                   // (only possible past the end of the list)
+    const int p_begin = __ffs(h0) - 1;
+    const int p_end = h1 ? 32 + __ffs(h1) - 1 : (int)min((long long)64, (long long)T - t0);
+    auto flag_at = [&](int rel) { return rel < 32 ? (int)((h0 >> rel) & 1u) : (int)((h1 >> (rel - 32)) & 1u); };
+    int head_rel = p_begin;
     float4 acc = f4(0.f);
-    for (long long k = t; k < T && mkey[k] == row; ++k) {
-      const int v = mval[k];
-      const int r = (int)(v / cap);
-      const long long j = v - (long long)r * cap;
-      acc += ld4s(xchg_view(peers.x[r], cap).ugrad + j * D + 4 * lane);
+    for (int p = p_begin; p < p_end; p += MS_ILP) {
+      float4 v[MS_ILP];
+#pragma unroll
+      for (int u = 0; u < MS_ILP; ++u) {
+        const int rel = p + u;
+        const int val = rel < 32 ? __shfl_sync(0xffffffffu, v0, rel & 31) : __shfl_sync(0xffffffffu, v1, rel & 31);
+        if (rel < p_end) {
+          const int r = val / icap;
+          const long long j = val - r * icap;
+          v[u] = ld4s(xchg_view(peers.x[r], cap).ugrad + j * D + 4 * lane);
+        } else {
+          v[u] = f4(0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < MS_ILP; ++u) {
+        const int rel = p + u;
+        if (rel < p_end) {
+          if (flag_at(rel)) { head_rel = rel; acc = f4(0.f); }
+          acc += v[u];
+          if (rel + 1 == p_end || flag_at(rel + 1)) {        // run complete: rel is its last item
+            const int row = __shfl_sync(0xffffffffu, k0, head_rel & 31);   // heads of my runs are always inside my block
+            if (dense_grad) {
+              st4(dense_grad + (long long)row * D + 4 * lane, acc);
+              if (lane == 0) touched[row] = 1;
+            } else {
+              const int um = __shfl_sync(0xffffffffu, x0, head_rel & 31);
+              st4(mgrad + (long long)um * D + 4 * lane, acc);
+              if (lane == 0) mrow[um] = row;
+            }
+            sq += warp_sum(hsum4(acc * acc));
+          }
+        }
+      }
     }
-    if (dense_grad) {
-      st4(dense_grad + (long long)row * D + 4 * lane, acc);
-      if (lane == 0) touched[row] = 1;
-    } else {
-      const int um = midx[t];
-      st4(mgrad + (long long)um * D + 4 * lane, acc);
-      if (lane == 0) mrow[um] = row;
-    }
-    sq += warp_sum(hsum4(acc * acc));
   }
   if (lane == 0) s_sq[warp] = sq;
   __syncthreads();
@@ -401,7 +436,7 @@ extern "C" int fbn_shard_local_sum(const fbn_shard_plan_t* s, const fbn_batch_t*
   SegArgs g{};
   g.off = w.ustart; g.cnt = nullptr; g.nseg_dev = x.hdr; g.nseg = 0; g.src = w.vals_out;
   g.dXitem = dXitem; g.dXhist = dXhist; g.B = b->batch; g.L = b->seq_len > 0 ? (int)b->seq_len : 1;
-  g.out = x.ugrad; g.zero_fill = 0; g.sq_partial = w.lsq_partial;
+  g.out = x.ugrad; g.zero_fill = 0; g.sq_partial = w.lsq_partial; g.nseg_bound = s->item_rows;
   g.hot = seg_carve(w.seg_scratch, s->cap);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, SEG_WARPS), w.lsum_blocks));
   FBN_CHECK_CUDA(seg_sum_launch(g, blocks, s->cap, (cudaStream_t)stream));
