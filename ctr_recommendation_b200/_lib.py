@@ -50,7 +50,7 @@ class ShardPlan(C.Structure):
 
 class AdamHyper(C.Structure):
     _fields_ = [("lr", _f), ("beta1", _f), ("beta2", _f), ("eps", _f), ("weight_decay", _f), ("step", _i32),
-                ("one_minus_beta1", _f), ("one_minus_beta2", _f)]
+                ("one_minus_beta1", _f), ("one_minus_beta2", _f), ("decoupled", _i32)]
 
 
 _SIGNATURES = {

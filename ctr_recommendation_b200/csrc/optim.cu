@@ -71,18 +71,19 @@ __global__ void clip_coef_kernel(const float* __restrict__ sums, int n, float ma
   out[1] = fminf(1.0f, max_norm / (total + 1e-6f));  // clip_grad.py: clamp(max_norm/(total+1e-6), max=1)
 }
 
-struct AdamHyper { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, omb1, omb2; };
+struct AdamHyper { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, omb1, omb2, decay_mul; };   // decay_mul != 0: AdamW
 
 __device__ __forceinline__ AdamHyper resolve_hyper(const AdamHyper& h, const float* dev) {
   if (!dev) return h;
   AdamHyper r;
   r.lr = dev[0]; r.beta1 = dev[1]; r.beta2 = dev[2]; r.eps = dev[3]; r.wd = dev[4]; r.step_size = dev[5]; r.bc2_sqrt = dev[6];
-  r.omb1 = dev[8]; r.omb2 = dev[9];
+  r.omb1 = dev[8]; r.omb2 = dev[9]; r.decay_mul = dev[10];
   return r;
 }
 
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, const AdamHyper& h) {
-  g = fmaf(h.wd, p, g);                              // grad.add(param, alpha=weight_decay)
+  if (h.decay_mul != 0.f) p *= h.decay_mul;          // AdamW: param.mul_(1 - lr * weight_decay)
+  else g = fmaf(h.wd, p, g);                         // Adam: grad.add(param, alpha=weight_decay)
   m = m + h.omb1 * (g - m);                          // exp_avg.lerp_(grad, 1-beta1)      (1-beta evaluated in double by torch)
   v = v * h.beta2 + h.omb2 * (g * g);                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
   const float denom = sqrtf(v) / h.bc2_sqrt + h.eps; // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
@@ -143,6 +144,7 @@ static AdamHyper make_hyper(const fbn_adam_t& a) {
   h.bc2_sqrt = (float)sqrt(bc2);
   h.omb1 = a.one_minus_beta1 > 0.f ? a.one_minus_beta1 : one_minus(a.beta1);
   h.omb2 = a.one_minus_beta2 > 0.f ? a.one_minus_beta2 : one_minus(a.beta2);
+  h.decay_mul = a.decoupled ? (float)(1.0 - (double)a.lr * (double)a.weight_decay) : 0.f;
   return h;
 }
 
@@ -174,6 +176,7 @@ __global__ void onecycle_hyper_kernel(int* step_counter, int total_steps, float 
   hyper[7] = (float)t;
   hyper[8] = (float)(1.0 - b1);
   hyper[9] = omb2;
+  hyper[10] = 0.f;   // coupled L2 decay (the reference's torch.optim.Adam)
   *step_counter = t;
 }
 

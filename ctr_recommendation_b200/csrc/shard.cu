@@ -331,10 +331,11 @@ __global__ void shard_sum_partials_kernel(const float* __restrict__ x, int n, fl
 
 // ---------------------------------------------------------------------------------------------------- lazy row Adam
 
-struct RowAdamHyper { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, omb1, omb2; };
+struct RowAdamHyper { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, omb1, omb2, decay_mul; };
 
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const RowAdamHyper& h) {
-  g = fmaf(h.wd, p, g);                              // same op order as adam1 (optim.cu)
+  if (h.decay_mul != 0.f) p *= h.decay_mul;          // same op order as adam1 (optim.cu)
+  else g = fmaf(h.wd, p, g);
   m = m + h.omb1 * (g - m);
   v = v * h.beta2 + h.omb2 * (g * g);
   const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(SH_WARPS * 32) adam_rows_kernel(const int32_t*
                                                                   const float* __restrict__ clip, RowAdamHyper hv,
                                                                   const float* __restrict__ hdev) {
   RowAdamHyper h = hv;
-  if (hdev) { h.lr = hdev[0]; h.beta1 = hdev[1]; h.beta2 = hdev[2]; h.eps = hdev[3]; h.wd = hdev[4]; h.step_size = hdev[5]; h.bc2_sqrt = hdev[6]; h.omb1 = hdev[8]; h.omb2 = hdev[9]; }
+  if (hdev) { h.lr = hdev[0]; h.beta1 = hdev[1]; h.beta2 = hdev[2]; h.eps = hdev[3]; h.wd = hdev[4]; h.step_size = hdev[5]; h.bc2_sqrt = hdev[6]; h.omb1 = hdev[8]; h.omb2 = hdev[9]; h.decay_mul = hdev[10]; }
   const float coef = clip ? clip[1] : 1.0f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Um = mhdr[1];
@@ -490,6 +491,7 @@ extern "C" int fbn_shard_adam_rows(const fbn_shard_plan_t* s, void* sws, size_t 
     hv.bc2_sqrt = (float)sqrt(1.0 - pow((double)h->beta2, (double)h->step));
     hv.omb1 = h->one_minus_beta1 > 0.f ? h->one_minus_beta1 : one_minus(h->beta1);
     hv.omb2 = h->one_minus_beta2 > 0.f ? h->one_minus_beta2 : one_minus(h->beta2);
+    hv.decay_mul = h->decoupled ? (float)(1.0 - (double)h->lr * (double)h->weight_decay) : 0.f;
   }
   const long long upper = std::min<long long>(s->merge_cap, s->shard_rows);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(upper, SH_WARPS), 8LL * num_sms()));

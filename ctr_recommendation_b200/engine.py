@@ -218,6 +218,7 @@ class TrainStep:
         h[6] = math.sqrt(1.0 - b2 ** t)
         h[7] = float(t)
         h[8], h[9] = 1.0 - b1, 1.0 - b2          # evaluated in double like torch, rounded to fp32 by the store
+        h[10] = (1.0 - lr * float(g["weight_decay"])) if self.opt.decoupled else 0.0     # AdamW decay multiplier
         self.hyper_dev.copy_(h, non_blocking=True)
 
     # ------------------------------------------------------------------

@@ -21,7 +21,7 @@ from . import _lib
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled_weight_decay=False):
         from .model import MM_FiBiNET
         inner = model.module if hasattr(model, "module") else model
         if not isinstance(inner, MM_FiBiNET):
@@ -29,6 +29,9 @@ class FusedAdam(torch.optim.Optimizer):
         params = [p for n, p in inner.named_parameters() if not n.startswith("user_emb.")]
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.model = inner
+        # False: torch.optim.Adam (L2 folded into the gradient) = what the reference builds; True: torch.optim.AdamW
+        # (`optimizer: adamw` of config/fibinet_config.yaml, which the reference never honours)
+        self.decoupled = bool(decoupled_weight_decay)
         inner._fused_optimizer = self
         self._step = 0
         self._max_norm = None
@@ -99,7 +102,8 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         h = _lib.AdamHyper(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                           float(g["weight_decay"]), self._step, 1.0 - float(g["betas"][0]), 1.0 - float(g["betas"][1]))
+                           float(g["weight_decay"]), self._step, 1.0 - float(g["betas"][0]), 1.0 - float(g["betas"][1]),
+                           int(self.decoupled))
         clip = _lib.ptr(self._clip) if self._max_norm is not None else None
         st = _lib.stream_ptr()
         w = m.item_emb.weight.data

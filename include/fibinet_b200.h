@@ -180,12 +180,15 @@ int fbn_clip_coef(const float* sumsq, int n, float max_norm, float* out, fbn_str
 /* Hyper-parameters of torch.optim.Adam as the reference builds it (src/train_fibinet.py:78):
  * L2 weight decay folded into the gradient, bias corrections from the current beta1 (OneCycleLR
  * cycles it, :84-92).  step is the 1-based step count.  Every Adam entry point takes either this
- * struct (host values) or hyper_dev, a device array of 10 floats {lr, beta1, beta2, eps, wd, lr/(1-beta1^t),
- * sqrt(1-beta2^t), t, 1-beta1, 1-beta2} (CUDA-graph replay; filled by fbn_onecycle_hyper or by the host).
+ * struct (host values) or hyper_dev, a device array of 12 floats {lr, beta1, beta2, eps, wd, lr/(1-beta1^t),
+ * sqrt(1-beta2^t), t, 1-beta1, 1-beta2, decay multiplier, 0} (CUDA-graph replay; filled by fbn_onecycle_hyper or by the host).
  * one_minus_beta1/2: torch evaluates `1 - beta` in double precision before it becomes an fp32 kernel scalar (for
  * beta2 = 0.999 that differs from 1.0f - 0.999f by 1.3e-5 relative); pass those doubles rounded to float, or 0 to
- * let the library derive them from the fp32 betas. */
-typedef struct { float lr, beta1, beta2, eps, weight_decay; int32_t step; float one_minus_beta1, one_minus_beta2; } fbn_adam_t;
+ * let the library derive them from the fp32 betas.
+ * decoupled != 0: torch.optim.AdamW semantics instead (p *= 1 - lr*wd, then Adam on the raw gradient) -- what `optimizer: adamw`
+ * in config/fibinet_config.yaml names but the reference never builds (src/train_fibinet.py:78 constructs torch.optim.Adam);
+ * hyper_dev[10] = 1 - lr*wd (0 = coupled L2). */
+typedef struct { float lr, beta1, beta2, eps, weight_decay; int32_t step; float one_minus_beta1, one_minus_beta2; int32_t decoupled; } fbn_adam_t;
 
 /* Dense-exact Adam over the whole embedding table, consuming the gradient rows produced by
  * fbn_backward: g = (touched ? grad[row] : 0) * coef + wd*p, then the Adam update, for EVERY row

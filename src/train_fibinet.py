@@ -60,7 +60,10 @@ def main():
     lr = float(model_cfg.get("learning_rate", 1e-3))
     weight_decay = float(model_cfg.get("weight_decay", 1e-5))
     epochs = int(model_cfg.get("epochs", 30))
-    optimizer = FusedAdam(model, lr=lr, weight_decay=weight_decay)     # torch.optim.Adam semantics (L2-coupled)
+    # torch.optim.Adam semantics (L2-coupled) like the reference, which ignores `optimizer: adamw`; with honor_config: true
+    # the key is honoured (decoupled weight decay)
+    adamw = bool(model_cfg.get("honor_config", False)) and str(model_cfg.get("optimizer", "adam")).lower() == "adamw"
+    optimizer = FusedAdam(model, lr=lr, weight_decay=weight_decay, decoupled_weight_decay=adamw)
     steps_per_epoch = len(train_loader)
     scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=lr * 10, epochs=epochs, steps_per_epoch=steps_per_epoch,
                                                     pct_start=0.3, div_factor=25.0, final_div_factor=1000.0)

@@ -214,6 +214,49 @@ def test_fused_adam_step_exact_given_same_gradients(gpu):
             oopt.state[k]["v"] = mom[k][1].cpu().numpy().copy()
 
 
+@pytest.mark.parametrize("engine", [False, True])
+def test_fused_adamw_vs_oracle(gpu, engine):
+    """`optimizer: adamw` (decoupled weight decay; honoured only with honor_config) against the oracle's AdamW, which is pinned to
+    torch.optim.AdamW on CPU (test_oracle_adamw_matches_torch): same gradients in, same weights out, eager and CUDA-graph paths."""
+    from ctr_recommendation_b200 import FusedAdam, clip_grad_norm_
+    from ctr_recommendation_b200.engine import TrainStep
+    B = 256
+    model = gpu["make_model"](train=True)
+    model.dropout_p = 0.0
+    opt = FusedAdam(model, lr=2e-3, weight_decay=1e-2, decoupled_weight_decay=True)
+    oopt = orc.Adam(lr=2e-3, weight_decay=1e-2, decoupled=True)
+    P = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    batch, labels = synth.make_batch(seed=77, batch=B, index_dtype=np.float64)
+    dev, y = gpu["to_dev"]({k: v for k, v in batch.items() if k != "user_id"}), torch.from_numpy(labels).cuda()
+    if engine:
+        TrainStep(model, opt, B, 20, idx_dtype=torch.float64)(dev, y)
+    else:
+        torch.nn.BCELoss()(model(dev), y).backward()
+        clip_grad_norm_(model, 10.0)
+        opt.step()
+    torch.cuda.synchronize()
+    names = {id(q): n for n, q in model.named_parameters()}
+    G = {}
+    for (field, plist), (off, _) in zip(model._dense_params(), model._layout):     # the flat gradient buffer both paths fill
+        o = off
+        for q in plist:
+            n = q.numel()
+            G[names[id(q)]] = model._gflat[o:o + n].view(q.shape).cpu().numpy().copy()
+            o += (n + 3) // 4 * 4
+    G["item_emb.weight"] = (model._item_grad * (model._row_touched > 0).unsqueeze(1)).cpu().numpy()
+    orc.clip_grad_norm_(G, 10.0)
+    oopt.step(P, G)
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    for k in G:
+        d = np.abs(sd[k].astype(np.float64) - P[k])
+        assert d.max() <= 2e-3 * 2e-3 + 1e-7, f"{k}: {d.max():.3e}"
+    w0 = synth.make_weights(seed=7)["item_emb.weight"]
+    untouched = (model._row_touched == 0).cpu().numpy()
+    untouched[0] = False
+    # decoupled decay: untouched rows shrink by exactly the factor 1 - lr*wd (no lr-sized Adam step as with coupled L2)
+    assert np.abs(sd["item_emb.weight"][untouched] - w0[untouched] * np.float32(1 - 2e-3 * 1e-2)).max() <= 1e-7
+
+
 @pytest.mark.parametrize("tag,id_dist", [("train_u", "uniform"), ("train_z", "zipf")])
 def test_train_steps_torch_adam_golden(gpu, golden, tag, id_dist):
     """reference call sequence verbatim: torch.optim.Adam + torch clip_grad_norm_ + OneCycleLR on our module."""

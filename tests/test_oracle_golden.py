@@ -155,3 +155,20 @@ def test_auc_matches_sklearn_and_single_class():
     s = np.round(rng.random(5000), 2)   # many ties
     assert abs(orc.auc(y, s) - roc_auc_score(y, s)) < 1e-12
     assert orc.auc(np.ones(10), rng.random(10)) == 0.5   # src/utils.py:25-27
+
+
+def test_oracle_adamw_matches_torch():
+    """The oracle's decoupled option (used to check FusedAdam(decoupled_weight_decay=True)) against torch.optim.AdamW on CPU."""
+    import torch
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal((37, 16)).astype(np.float32)
+    P = {"w": p0.copy()}
+    opt = orc.Adam(lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, decoupled=True)
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    topt = torch.optim.AdamW([tp], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    for s in range(4):
+        g = rng.standard_normal(p0.shape).astype(np.float32)
+        opt.step(P, {"w": g})
+        tp.grad = torch.from_numpy(g.copy())
+        topt.step()
+        assert np.abs(P["w"] - tp.detach().numpy()).max() <= 2e-7
