@@ -38,11 +38,15 @@ def main():
     per = B // world
     eng = TrainStep(model, opt, per, 20, idx_dtype=torch.float64)
     batches = [synth.make_batch(seed=700 + s, batch=B, id_dist="zipf", index_dtype=np.float64) for s in range(steps)]
+    grads_dp = []
     for b, y in batches:
         tb = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in b.items() if k != "user_id"}
         shard, ys, w = fdist.shard_batch(tb, torch.from_numpy(y), rank, world)
         eng({k: v.pin_memory() for k, v in shard.items()}, ys.pin_memory())
         sched.step()
+        if len(grads_dp) == 0:      # the all-reduced gradients of the first step (identical weights on both sides)
+            torch.cuda.synchronize()
+            grads_dp.append((model._gflat.clone(), model._item_grad.clone()))
     torch.cuda.synchronize()
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     # replicas identical?
@@ -57,6 +61,7 @@ def main():
         sopt = FusedAdam(single, lr=1e-3, weight_decay=1e-5)
         ssched = torch.optim.lr_scheduler.OneCycleLR(sopt, max_lr=1e-2, total_steps=20)
         single._dense_table_grad = True
+        first, grad_worst = True, 0.0
         for b, y in batches:
             tb = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in b.items() if k != "user_id"}
             ty = torch.from_numpy(y).cuda()
@@ -69,6 +74,12 @@ def main():
                 g, it = single._gflat.clone(), single._item_grad.clone()
                 gsum = g if gsum is None else gsum + g
                 isum = it if isum is None else isum + it
+            if first:
+                first = False
+                for name, a, b_ in (("dense", grads_dp[0][0], gsum), ("item_emb", grads_dp[0][1], isum)):
+                    rel = (a.double() - b_.double()).abs().max().item() / max(b_.abs().max().item(), 1e-30)
+                    assert rel <= 1e-5, ("first-step gradient", name, rel)
+                    grad_worst = max(grad_worst, rel)
             single._gflat.copy_(gsum)
             single._item_grad.copy_(isum)
             single._grad_sumsq[0] = (gsum.double() ** 2).sum().float()
@@ -82,13 +93,15 @@ def main():
             # above updates them once per shard, so they are not comparable
             if "num_batches" in k or "running" in k or k in ("mlp.0.bias", "mlp.4.bias"):
                 continue
+            # After 3 Adam steps two exact implementations differ by whole lr-sized steps on the elements whose gradient is at
+            # rounding-noise level (Adam normalises; DESIGN section 2, finding 1): the weights are held to a MEAN difference of a
+            # small fraction of one step (max lr over the run = 1e-2 * cycle ~ 5e-4 here), the first-step gradients to 1e-5.
             d = (v.double() - sd[k].double()).abs()
-            rel = d.mean().item() / max(v.abs().max().item(), 1e-30)
+            rel = d.mean().item()
             worst = max(worst, rel)
-            # running stats follow replica 0 in DataParallel; here every rank keeps its own shard's -> compare rank 0's only loosely
-            tol = 2e-6
-            assert rel <= tol, (k, rel)
-        print(f"dp_check OK: {world} ranks, replicas identical, worst mean rel diff vs single-process emulation {worst:.2e}")
+            assert rel <= 0.05 * 5e-4, (k, rel)
+        print(f"dp_check OK: {world} ranks, replicas identical, first-step all-reduced gradients within {grad_worst:.2e} (rel) of the "
+              f"single-process DataParallel emulation, worst mean |weight diff| after {steps} steps {worst:.2e}")
     dist.barrier()
     dist.destroy_process_group()
 
