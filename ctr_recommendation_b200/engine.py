@@ -300,6 +300,7 @@ class ShardedTrainStep(TrainStep):
         if st.world != self.world:
             raise ValueError(f"the table is sharded over {st.world} ranks but the process group has {self.world}")
         self.plan = st.ensure_exchange(batch_size * (1 + seq_len), self.dev, merge_cap)
+        self._sws = st.sws          # this engine's private scratch (a model may drive several engines, e.g. a tail batch)
         off = lambda name: self.lib.fbn_workspace_offset(self.B, self.L, 1, name.encode())
         self._dX = (C.c_void_p(self.ws.data_ptr() + off("dXitem")), C.c_void_p(self.ws.data_ptr() + off("dXhist")))
         self._sq_local = torch.zeros(1, dtype=torch.float32, device=self.dev)
@@ -308,10 +309,10 @@ class ShardedTrainStep(TrainStep):
     def _alloc_table_grad(self):
         m, dev = self.model, self.dev
         R = m._shard.shard_rows
-        m._grad_sumsq = torch.zeros(2, dtype=torch.float32, device=dev)
-        if self.lazy:
-            m._item_grad, m._row_touched = None, None
-        else:
+        if m._grad_sumsq is None or m._grad_sumsq.device != dev:
+            m._grad_sumsq = torch.zeros(2, dtype=torch.float32, device=dev)
+        # shared by every engine of the model (a captured graph keeps raw pointers: never re-allocate what exists)
+        if not self.lazy and (m._item_grad is None or m._item_grad.device != dev or m._item_grad.shape[0] != R):
             m._item_grad = torch.zeros(R, D, dtype=torch.float32, device=dev)
             m._row_touched = torch.zeros(R, dtype=torch.int32, device=dev)
 
@@ -326,7 +327,7 @@ class ShardedTrainStep(TrainStep):
     def _fwd_bwd(self):
         m, lib, st = self.model, self.lib, self.model._shard
         P, G = m._params_struct(), m._grads_struct()
-        ws, sws = self.ws, st.sws
+        ws, sws = self.ws, self._sws
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):     # ids only: runs beside the forward pass
@@ -348,7 +349,9 @@ class ShardedTrainStep(TrainStep):
         m, lib, st, s = self.model, self.lib, self.model._shard, _lib.stream_ptr()
         if self.world > 1:     # norm of the all-reduced dense gradients
             _lib.check(lib.fbn_sumsq(_lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(self.sumsq_scratch), _lib.ptr(m._grad_sumsq), s))
-        _lib.check(lib.fbn_shard_merge(C.byref(self.plan), _lib.ptr(st.sws), st.sws.numel(), _lib.ptr(m._item_grad), _lib.ptr(m._row_touched),
+        dense = None if self.lazy else m._item_grad
+        touched = None if self.lazy else m._row_touched
+        _lib.check(lib.fbn_shard_merge(C.byref(self.plan), _lib.ptr(self._sws), self._sws.numel(), _lib.ptr(dense), _lib.ptr(touched),
                                        _lib.ptr(self._sq_local), s), "fbn_shard_merge")
 
     def _update(self):
@@ -360,7 +363,7 @@ class ShardedTrainStep(TrainStep):
             clip = _lib.ptr(o._clip)
         w = m.item_emb.weight.data
         if self.lazy:
-            _lib.check(lib.fbn_shard_adam_rows(C.byref(self.plan), _lib.ptr(st.sws), st.sws.numel(), _lib.ptr(w), _lib.ptr(o._m_item),
+            _lib.check(lib.fbn_shard_adam_rows(C.byref(self.plan), _lib.ptr(self._sws), self._sws.numel(), _lib.ptr(w), _lib.ptr(o._m_item),
                                                _lib.ptr(o._v_item), clip, None, _lib.ptr(self.hyper_dev), s), "fbn_shard_adam_rows")
         else:
             _lib.check(lib.fbn_adam_table(_lib.ptr(w), _lib.ptr(o._m_item), _lib.ptr(o._v_item), _lib.ptr(m._item_grad),

@@ -119,10 +119,11 @@ class ShardState:
         self.peers = PeerMap(rank, world)
         self.table_ptrs: Optional[List[int]] = None
         self._table_key = None
-        self.plan: Optional[_lib.ShardPlan] = None
+        self.plan: Optional[_lib.ShardPlan] = None      # the most recently created exchange (what stats() reports on)
         self.xchg: Optional[torch.Tensor] = None
         self.sws: Optional[torch.Tensor] = None
         self.cap = 0
+        self._exchanges = {}      # (cap, merge_cap) -> (plan, xchg, sws): one per engine size, never freed while peers map them
 
     def ensure_table(self, weight: torch.Tensor):
         """(Re-)exchange the slice pointers when the parameter storage moved (collective on first use / after .to())."""
@@ -146,19 +147,20 @@ class ShardState:
         if merge_cap is None:
             merge_cap = self.world * cap
         merge_cap = max(1, min(int(merge_cap), self.world * cap))
-        if self.plan is not None and self.cap == cap and self.plan.merge_cap == merge_cap:
-            return self.plan
+        hit = self._exchanges.get((cap, merge_cap))
+        if hit is None:
+            xchg = torch.zeros(lib.fbn_shard_xchg_bytes(cap), dtype=torch.uint8, device=device)
+            sws = torch.zeros(lib.fbn_shard_ws_bytes(cap, merge_cap, self.world, self.shard_rows), dtype=torch.uint8, device=device)
+            ptrs = self.peers.share(xchg)
+            plan = _lib.ShardPlan()
+            plan.n_shards, plan.rank = self.world, self.rank
+            plan.item_rows, plan.shard_rows, plan.cap, plan.merge_cap = self.item_rows, self.shard_rows, cap, merge_cap
+            for r, p in enumerate(ptrs):
+                plan.xchg[r] = p
+            hit = self._exchanges[(cap, merge_cap)] = (plan, xchg, sws)
+        self.plan, self.xchg, self.sws = hit
         self.cap = cap
-        self.xchg = torch.zeros(lib.fbn_shard_xchg_bytes(cap), dtype=torch.uint8, device=device)
-        self.sws = torch.zeros(lib.fbn_shard_ws_bytes(cap, merge_cap, self.world, self.shard_rows), dtype=torch.uint8, device=device)
-        ptrs = self.peers.share(self.xchg)
-        plan = _lib.ShardPlan()
-        plan.n_shards, plan.rank = self.world, self.rank
-        plan.item_rows, plan.shard_rows, plan.cap, plan.merge_cap = self.item_rows, self.shard_rows, cap, merge_cap
-        for r, p in enumerate(ptrs):
-            plan.xchg[r] = p
-        self.plan = plan
-        return plan
+        return self.plan
 
     def stats(self) -> dict:
         """{U, owner_start, T, Um, overflow} of the last step (synchronises; tests / diagnostics)."""

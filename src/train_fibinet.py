@@ -22,7 +22,8 @@ from utils import compute_auc, set_seed  # noqa: E402
 
 from ctr_recommendation_b200 import FusedAdam  # noqa: E402
 from ctr_recommendation_b200 import dist as fdist  # noqa: E402
-from ctr_recommendation_b200.engine import Scorer, TrainStep  # noqa: E402
+from ctr_recommendation_b200 import sharded  # noqa: E402
+from ctr_recommendation_b200.engine import Scorer, ShardedTrainStep, TrainStep  # noqa: E402
 
 
 def load_config():
@@ -54,7 +55,11 @@ def main():
     valid_loader = MMCTRDataLoader(None, dataset_cfg["valid_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=False,
                                    num_workers=workers, max_len=max_len)
 
-    model = build_model({"precision": model_cfg.get("precision", "tf32x3")}, model_cfg).to(device)
+    fm = {"precision": model_cfg.get("precision", "tf32x3")}
+    row_sharded = str(model_cfg.get("table_sharding", "")).lower() == "row"   # B200 extra: item table partitioned by id % world
+    if row_sharded:
+        fm["table_sharding"] = "row"
+    model = build_model(fm, model_cfg).to(device)
     if world > 1:
         fdist.broadcast_parameters(model)
     lr = float(model_cfg.get("learning_rate", 1e-3))
@@ -72,7 +77,8 @@ def main():
     def train_engine(rows, L, dtype):
         key = ("t", rows, L, dtype)
         if key not in engines:
-            engines[key] = TrainStep(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0)
+            cls = ShardedTrainStep if row_sharded else TrainStep
+            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0)
         return engines[key]
 
     def score_engine(rows, L, dtype):
@@ -116,8 +122,11 @@ def main():
             log(f"Epoch {epoch + 1} | Train Loss: {avg_loss:.4f} | Valid AUC: {auc:.4f}")
             if auc > best_auc:
                 best_auc = auc
+                sd = model.state_dict()
+                if row_sharded:      # the checkpoint keeps the reference's format: the full (91718,128) table (collective)
+                    sd["item_emb.weight"] = sharded.gather_full_table(model)
                 if rank == 0:
-                    torch.save(model.state_dict(), best_path)
+                    torch.save(sd, best_path)
                     log(f"[ckpt] new best -> {best_path}")
     log(f"Done. Best AUC: {best_auc:.4f}")
 

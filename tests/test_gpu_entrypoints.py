@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_train_and_predict_scripts(tmp_path):
+@pytest.mark.parametrize("table_sharding", [None, "row"])
+def test_train_and_predict_scripts(tmp_path, table_sharding):
     from oracle import synth
     data = tmp_path / "data" / "MicroLens_1M_x1"
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_dataset.py"), str(data), "--train", "3000", "--valid", "700",
@@ -21,6 +22,8 @@ def test_train_and_predict_scripts(tmp_path):
     cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "fibinet_config.yaml")))
     run = cfg[cfg["base_expid"]]
     run.update(epochs=2, batch_size=1024)
+    if table_sharding:
+        run["table_sharding"] = table_sharding      # one rank here: the same kernels, the exchange degenerates to a local copy
     (tmp_path / "config").mkdir()
     yaml.safe_dump(cfg, open(tmp_path / "config" / "fibinet_config.yaml", "w"))
     cwd = tmp_path / "src"
