@@ -349,31 +349,22 @@ def kernel_rooflines(args, model, dev_batch, peaks, lib):
     g_bytes = B * (184 + 2 * 512 + 512 + 512 + 2560 + 2560 + 512 + 48) + nvalid * 512
     out["gather_senet_fwd"] = {"ms": ms, "bytes": g_bytes, "GBps": g_bytes / ms / 1e6, "frac": g_bytes / ms / 1e6 / peaks["hbm"]}
     model.train()
-    # (3) the three MLP-1 GEMMs (forward, data gradient, weight gradient): the GEMM kernel alone, operands packed once,
-    #     L2 flushed before every timed launch (fbn_time_gemm records CUDA events on the launching stream)
-    prec = _lib.PRECISIONS[args.precision]
-    live = 0
-    for blk in list(range(1, 6)) + list(range(11, 21)):
-        live |= 1 << blk                      # 15 live 128-column blocks of the 21 (user field and its pairs are zero)
-    full = (1 << 64) - 1
-    X = torch.randn(B, 2688, device="cuda")
-    Wt = torch.randn(512, 2688, device="cuda")
-    dH = torch.randn(B, 512, device="cuda")
-    nscr = max(lib.fbn_gemm_scratch_bytes(B, 512, 2688, prec), lib.fbn_gemm_scratch_bytes(512, 2688, B, prec),
-               lib.fbn_gemm_scratch_bytes(B, 2688, 512, prec), 16)
-    scr = torch.empty(nscr, dtype=torch.uint8, device="cuda")
+    # (3) the three MLP-1 GEMMs (forward, data gradient, weight gradient) exactly as the step launches them -- same operands,
+    #     strides, structural-zero masks and split-K -- on the workspace the training steps above left behind; L2 flushed before
+    #     every timed launch, CUDA events on the launching stream (fbn_time_stage)
+    live_cols = 15 * 128                      # 15 live 128-column blocks of the 21 (user field and its pairs are zero)
     msf = C.c_float(0.0)
 
-    def tgemm(name, A, Bm, M, N, K, a_t, b_t, kmask, useful_flops):
-        Cc = torch.empty(M, N, device="cuda")
-        _lib.check(lib.fbn_time_gemm(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(Cc), M, N, K, a_t, b_t, kmask, prec, _lib.ptr(scr), nscr,
-                                     _lib.ptr(flush), flush.numel() * 4, 8, C.byref(msf), st), "fbn_time_gemm")
+    def tstage(name, stage, useful_flops):
+        _lib.check(lib.fbn_time_stage(C.byref(P), C.byref(bs), _lib.ptr(ws), ws.numel(), stage.encode(), _lib.ptr(flush), flush.numel() * 4,
+                                      8, C.byref(msf), st), "fbn_time_stage")
         ms = float(msf.value)
         out[name] = {"ms": ms, "flops": useful_flops, "TFLOPs": useful_flops / ms / 1e9,
                      "frac_of_bf16_peak": useful_flops / ms / 1e9 / peaks["tf"]}
-    tgemm("mlp1_fwd_gemm", X, Wt, B, 512, 2688, 0, 1, live, 2.0 * B * 1920 * 512)
-    tgemm("mlp1_dgrad_gemm", dH, Wt, B, 2688, 512, 0, 0, full, 2.0 * B * 2688 * 512)
-    tgemm("mlp1_wgrad_gemm", dH, X, 512, 2688, B, 1, 0, full, 2.0 * B * 2688 * 512)
+    gemm_flops = 2.0 * B * live_cols * 512
+    tstage("mlp1_fwd_gemm", "mlp1", gemm_flops)
+    tstage("mlp1_dgrad_gemm", "mlp1_dgrad", gemm_flops)
+    tstage("mlp1_wgrad_gemm", "mlp1_wgrad", gemm_flops)       # includes the fixed-order split-K reduction
     out["mlp1_gemm"] = out["mlp1_fwd_gemm"]
     passes = {"tf32x3": 3, "bf16": 1, "fp32": 1}[args.precision]
     traffic = None

@@ -670,6 +670,8 @@ extern "C" int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void*
   tl_reg.describe(p->bil_w, (long long)nW * D, D, w.pk_bil);
   const PackDst pkC = tl_reg.dst(w.C, B, K1, w.pk_C);
   const PackDst pkX = tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm);
+  tl_reg.describe(w.A1, B, H1, w.pk_A1);
+  tl_reg.describe(w.dH1, B, H1, w.pk_dH1);      // valid after an fbn_backward on this workspace (mlp1_dgrad / mlp1_wgrad)
   const std::string s(stage);
   cudaEvent_t e0, e1;
   FBN_CHECK_CUDA(cudaEventCreate(&e0));
@@ -686,6 +688,12 @@ extern "C" int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void*
       g1.A = w.C; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = K1; g1.lda = K1; g1.ldb = K1; g1.ldc = H1;
       g1.b_t = 1; g1.kmask = active_mask();
       RC(tl_reg.run(g1, w));
+    } else if (s == "mlp1_dgrad") {      // dC = dH1 * w1, live column blocks only (as in fbn_backward)
+      GemmArgs d;
+      d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = active_mask();
+      RC(tl_reg.run(d, w));
+    } else if (s == "mlp1_wgrad") {      // dw1 = dH1^T * C, split-K + fixed-order reduce (as in fbn_backward; result goes to scratch)
+      RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, active_mask(), p->precision, w, w.partial_side, st, w.partial));
     } else {
       FBN_REQUIRE(false, FBN_ERR_ARG, "fbn_time_stage: unknown stage '%s'", stage);
     }
