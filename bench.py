@@ -54,6 +54,10 @@ def parse():
                          "owner-side gradient merge (engine.ShardedTrainStep)")
     ap.add_argument("--item-rows", type=int, default=0, help="rows of the item table (default: the reference's 91718)")
     ap.add_argument("--lazy", action="store_true", help="row sharding: lazy row Adam (touched rows only) instead of dense-exact Adam")
+    ap.add_argument("--resident-mm", action="store_true",
+                    help="keep the frozen (91718,128) item_emb_d128 matrix on the GPU and gather it by item_id inside the fused kernel "
+                         "(SURVEY 8f-1): batches then carry ids only (188 instead of 700 bytes / sample over PCIe)")
+    ap.add_argument("--int32-ids", action="store_true", help="loader delivers int32 ids / history instead of float64 / int64 (100 B / sample)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
@@ -123,6 +127,11 @@ def make_pool(args, rank, n):
         b, y = synth.make_batch(seed=2025 + 1000 * rank + i, batch=args.batch, max_len=L_HIST, id_dist=args.id_dist,
                                 index_dtype=np.float64, mm_table=table, edge_cases=False)
         b.pop("user_id")
+        if args.resident_mm:
+            b.pop("item_emb_d128")
+        if args.int32_ids:
+            for k in ("item_id", "likes_level", "views_level", "item_seq"):
+                b[k] = b[k].astype(np.int32)
         if big:    # scaled synthetic table: ids uniform over [1, V); the padding pattern of the history is kept
             V = args.item_rows
             b["item_id"] = torch.randint(1, V, (args.batch,), generator=g).numpy().astype(np.float64)
@@ -157,6 +166,9 @@ def run_ours(args):
     model = build_model(fm, {"embedding_dim": 128}).to(dev).train()
     if world > 1:
         fdist.broadcast_parameters(model)
+    if args.resident_mm:
+        from oracle import synth as _synth
+        model.attach_mm_table(torch.from_numpy(_synth.make_item_mm_table(seed=11)))
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
     total_steps = max(10, 2 * (args.steps + args.warmup) * 2 + 10)
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=total_steps, pct_start=0.3, div_factor=25.0,
@@ -175,8 +187,11 @@ def run_ours(args):
         engine = ShardedTrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0, lazy=args.lazy,
                                   merge_cap=4 * args.batch * (1 + L_HIST))
     else:
-        engine = None if args.eager else (Scorer(model, args.batch, L_HIST, idx_dtype=torch.float64) if infer else
-                                          TrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0))
+        idt = torch.int32 if args.int32_ids else torch.float64
+        sdt = torch.int32 if args.int32_ids else torch.int64
+        engine = None if args.eager else (
+            Scorer(model, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, use_mm_table=args.resident_mm) if infer else
+            TrainStep(model, opt, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0, use_mm_table=args.resident_mm))
 
     def step(batch, labels):
         if infer:                    # scoring: forward only, predictions read back by the caller
@@ -236,8 +251,11 @@ def run_ours(args):
             nb, ny = pool[(k + 1) % len(pool)]
             engine.prefetch(nb, ny)
             return loss.item()
-        if engine is not None:
-            loss = step(hb, hy)     # Scorer copies the pinned host batch into its static device buffers
+        if engine is not None:      # Scorer: the copy of batch k+1 (copy stream) overlaps the scoring of batch k, as a prefetching
+            if not engine._prefetched:   # loader would; the predictions are read back every batch like Prediction.py:113
+                engine.prefetch(hb)
+            loss = engine()
+            engine.prefetch(pool[(k + 1) % len(pool)][0])
         else:
             for name, t in hb.items():
                 stage[0][name].copy_(t, non_blocking=True)

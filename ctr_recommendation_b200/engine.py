@@ -400,6 +400,25 @@ class Scorer:
         self._bs = TrainStep._batch_struct(self)
         self._graph, self._use_graph = None, graph
         self.kernels_per_step = 0
+        self.dev = dev
+        # input prefetch (same scheme as TrainStep.prefetch): the next batch crosses PCIe on a copy stream while this one is scored
+        self._copy = torch.cuda.Stream(device=dev)
+        self._stage = None
+        self._h2d_done = torch.cuda.Event()
+        self._stage_free = torch.cuda.Event()
+        self._prefetched = False
+
+    def prefetch(self, batch: dict):
+        """Start the host->device copy of the NEXT batch on the copy stream; the following call without arguments scores it."""
+        if self._stage is None:
+            t = self.inp.t
+            self._stage = _StaticBatch(self.B, self.L, t["item_id"].dtype, t["item_seq"].dtype if "item_seq" in t else torch.int64,
+                                       self.dev, with_mm="item_emb_d128" in t, with_labels=False)
+        self._copy.wait_event(self._stage_free)
+        with torch.cuda.stream(self._copy):
+            self._stage.load(batch)
+            self._h2d_done.record(self._copy)
+        self._prefetched = True
 
     def _fwd(self):
         m = self.model
@@ -407,10 +426,19 @@ class Scorer:
         _lib.check(self.lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(self.ws), self.ws.numel(), 0, 0.0, None, None, 0, 0, None,
                                         _lib.ptr(self.prob), _lib.stream_ptr()), "fbn_forward")
 
-    def __call__(self, batch: dict) -> torch.Tensor:
+    def __call__(self, batch: dict | None = None) -> torch.Tensor:
         if self.model.training:
             raise RuntimeError("Scorer needs model.eval()")
-        self.inp.load(batch)
+        if batch is None:
+            if not self._prefetched:
+                raise RuntimeError("Scorer() without a batch needs a preceding prefetch()")
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._h2d_done)
+            self.inp.load(self._stage.t)              # device-to-device
+            self._stage_free.record(cur)
+            self._prefetched = False
+        else:
+            self.inp.load(batch)
         if not self._use_graph:
             self._fwd()
             return self.prob

@@ -423,3 +423,21 @@ def test_scorer_matches_module_eval(gpu):
             ref = model(dev).clone()
         got = sc(dev)
         assert torch.equal(ref, got)
+
+
+def test_scorer_prefetch_matches_direct(gpu):
+    """Scorer.prefetch (next batch copied on the copy stream while the current one is scored) returns the same predictions."""
+    from ctr_recommendation_b200.engine import Scorer
+    model = gpu["make_model"]()
+    B = 777
+    sc, ref = Scorer(model, B, 20, idx_dtype=torch.int64), Scorer(model, B, 20, idx_dtype=torch.int64, graph=False)
+    hosts = []
+    for s in range(3):
+        batch, _ = synth.make_batch(seed=50 + s, batch=B, index_dtype=np.int64)
+        hosts.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items() if k != "user_id"})
+    sc.prefetch(hosts[0])
+    for s in range(3):
+        out = sc().clone()
+        if s + 1 < 3:
+            sc.prefetch(hosts[s + 1])
+        assert torch.equal(out, ref({k: v.cuda() for k, v in hosts[s].items()}))
