@@ -60,8 +60,8 @@ def main():
         key = (rows, 0 if seq is None else seq.shape[1], batch["item_id"].dtype)
         if key not in scorers:
             scorers[key] = Scorer(model, key[0], key[1], idx_dtype=key[2])
-        preds.append(scorers[key](batch).cpu().numpy())
-    predictions = np.concatenate(preds)
+        preds.append(scorers[key](batch).clone())      # stays on the device: no per-batch host sync (reference: .cpu() per batch)
+    predictions = torch.cat(preds).cpu().numpy()
 
     sub = pd.DataFrame({"ID": range(len(predictions)), "Task2": predictions})
     sub.to_csv("prediction_fibinet.csv", index=False)
