@@ -79,6 +79,10 @@ def main():
         if k == "item_emb.weight" or "running" in k or "num_batches" in k:
             continue
         d = (sd1[k].double() - sd2[k].double()).abs().max().item() / max(sd1[k].abs().max().item(), 1e-30)
+        if world > 2 and k in ("mlp.0.bias", "mlp.4.bias"):
+            # a Linear bias in front of BatchNorm has an identically zero gradient in exact arithmetic: what Adam normalises is
+            # rounding noise, so beyond the bit-identical 2-rank case these two move by rounding-determined +-lr steps
+            continue
         worst = max(worst, d)
         assert d <= (0.0 if world == 2 else 1e-5), (k, d)
     st = shd._shard.stats()
