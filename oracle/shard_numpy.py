@@ -64,3 +64,45 @@ def lazy_adam_rows(p, m, v, grad, touched, lr, beta1, beta2, eps, weight_decay, 
     pp = pp - dt(step_size) * (mm / denom)
     p[rows], m[rows], v[rows] = pp, mm, vv
     return p, m, v
+
+
+def table_grad_ordered(item_id, item_seq, dXitem, dXhist, item_rows: int, hot: int = 256) -> np.ndarray:
+    """The same gradient as table_grad_dense but in fp32 with the summation ORDER the CUDA path specifies (segsum.cuh), so that
+    the result can be compared bit for bit: a row's occurrences are taken in source order (the B target ids first, then the
+    history ids in (sample, position) order); up to `hot` occurrences are added sequentially; longer lists are cut into
+    `hot`-sized chunks relative to the row's own start, every chunk is summed sequentially from zero, and the chunk sums are then
+    added sequentially in chunk order."""
+    item_id = np.clip(np.asarray(item_id).astype(np.int64), 0, item_rows - 1)
+    B = item_id.shape[0]
+    keys = [item_id]
+    src = [np.arange(B)]
+    if item_seq is not None:
+        seq = np.clip(np.asarray(item_seq).astype(np.int64), 0, item_rows - 1)
+        keys.append(seq.reshape(-1))
+        src.append(B + np.arange(seq.size))
+        L = seq.shape[1]
+    keys, src = np.concatenate(keys), np.concatenate(src)
+    order = np.argsort(keys, kind="stable")
+    keys, src = keys[order], src[order]
+    g = np.zeros((item_rows, dXitem.shape[1]), dtype=np.float32)
+    start = 0
+    n = keys.shape[0]
+
+    def seq_sum(rows):      # sequential fp32 accumulation starting from 0 (cumsum is strictly left to right)
+        return np.cumsum(rows, axis=0, dtype=np.float32)[-1]
+    while start < n:
+        end = start
+        while end < n and keys[end] == keys[start]:
+            end += 1
+        row = keys[start]
+        if row != 0:
+            s = src[start:end]
+            vals = np.where((s < B)[:, None], dXitem[np.minimum(s, B - 1)],
+                            dXhist[(np.maximum(s - B, 0) // L) if item_seq is not None else 0]).astype(np.float32)
+            if len(s) <= hot:
+                g[row] = seq_sum(vals)
+            else:
+                chunks = np.stack([seq_sum(vals[c:c + hot]) for c in range(0, len(s), hot)])
+                g[row] = seq_sum(chunks)
+        start = end
+    return g

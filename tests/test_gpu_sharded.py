@@ -261,3 +261,42 @@ def test_sharded_scorer_matches_replicated(env):
         batch, _ = synth.make_batch(seed=60 + s, batch=B, id_dist="zipf", index_dtype=np.int64)
         dev = env["to_dev"]({k: v for k, v in batch.items() if k != "user_id"})
         assert torch.equal(sa(dev), sb(dev))
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_shard_exchange_matches_specified_summation_order_bitwise(env, world):
+    """The CUDA path documents its summation order (source order; > 256 occurrences: 256-chunks relative to the row's start, chunk
+    sums in chunk order; ranks in rank order).  oracle.table_grad_ordered restates exactly that order in fp32, so the comparison
+    is bit for bit -- on a Zipf batch whose head rows take the chunked path."""
+    V, B, L = 3000, 1500, 20
+    res = _virtual_exchange(env, world, V, B, L, seed=77, id_dist="zipf", lazy=False)
+    total = None
+    for ids, seq, dXi, dXh in res["inputs"]:
+        g = sorc.table_grad_ordered(ids, seq, dXi, dXh, V)
+        total = g if total is None else (total + g).astype(np.float32)       # contributions are added in rank order
+    occ = np.zeros(V, dtype=np.int64)
+    for ids, seq, _, _ in res["inputs"]:
+        occ = np.maximum(occ, np.bincount(np.r_[ids, seq.reshape(-1)], minlength=V))
+    assert occ[1:].max() > 256, "the batch must contain a hot row"
+    for o in range(world):
+        want = sorc.slice_of(total, o, world)
+        touched = res["out"][o]["touched"].cpu().numpy().astype(bool)
+        got = res["out"][o]["g"].cpu().numpy()
+        assert np.array_equal(got[touched], want[touched]), f"owner {o}: summation order differs from the specification"
+
+
+def test_replicated_table_gradient_matches_specified_order_bitwise(env):
+    """Same statement for the replicated table (embbwd.cu shares segsum.cuh): item_emb.grad of a Zipf batch == the oracle's
+    ordered fp32 sums of the dX rows the kernels themselves produced."""
+    model = env["make_model"](train=True)
+    B = 2048
+    batch, labels = synth.make_batch(seed=88, batch=B, id_dist="zipf", index_dtype=np.float64)
+    y = model(env["to_dev"](batch))
+    torch.nn.BCELoss()(y, torch.from_numpy(labels).cuda()).backward()
+    dXi = model.workspace_view("dXitem", (B, D)).cpu().numpy()
+    dXh = model.workspace_view("dXhist", (B, D)).cpu().numpy()
+    want = sorc.table_grad_ordered(batch["item_id"], batch["item_seq"], dXi, dXh, model.item_emb.weight.shape[0])
+    got = model.item_emb.weight.grad.cpu().numpy()
+    occ = np.bincount(np.r_[batch["item_id"].astype(np.int64), batch["item_seq"].reshape(-1)], minlength=want.shape[0])
+    assert occ[1:].max() > 256
+    assert np.array_equal(got, want)
