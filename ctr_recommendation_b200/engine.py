@@ -376,6 +376,15 @@ class ShardedTrainStep(TrainStep):
         import torch.distributed as dist
         dist.all_reduce(self.model._gflat, op=dist.ReduceOp.SUM)
 
+    def check(self) -> dict:
+        """Synchronising health check: raises if the owner-side merge lists overflowed ``merge_cap`` in the last step (partial
+        gradient rows would have been dropped); returns the exchange statistics.  Call it every few hundred steps."""
+        st = self.model._shard.stats(self.plan, self._sws)
+        if st["overflow"]:
+            raise RuntimeError(f"row-sharded table: {st['T']} partial rows addressed to rank {self.plan.rank} exceed merge_cap="
+                               f"{self.plan.merge_cap}; build ShardedTrainStep with a larger merge_cap")
+        return st
+
     def _allreduce_sumsq(self):
         import torch.distributed as dist
         dist.all_reduce(self._sq_local, op=dist.ReduceOp.SUM)

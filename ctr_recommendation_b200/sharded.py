@@ -162,11 +162,13 @@ class ShardState:
         self.cap = cap
         return self.plan
 
-    def stats(self) -> dict:
-        """{U, owner_start, T, Um, overflow} of the last step (synchronises; tests / diagnostics)."""
+    def stats(self, plan=None, sws=None) -> dict:
+        """{U, owner_start, T, Um, overflow} of the last step of an exchange (default: the most recently created one).
+        Synchronises the stream; tests / diagnostics / the periodic overflow check of ShardedTrainStep.check()."""
+        plan = self.plan if plan is None else plan
+        sws = self.sws if sws is None else sws
         out = (C.c_int32 * 24)()
-        _lib.check(_lib.load().fbn_shard_stats(C.byref(self.plan), _lib.ptr(self.sws), self.sws.numel(), out, _lib.stream_ptr()),
-                   "fbn_shard_stats")
+        _lib.check(_lib.load().fbn_shard_stats(C.byref(plan), _lib.ptr(sws), sws.numel(), out, _lib.stream_ptr()), "fbn_shard_stats")
         return {"U": out[0], "owner_start": [out[1 + o] for o in range(self.world + 1)], "T": out[20], "Um": out[21],
                 "overflow": out[22]}
 
