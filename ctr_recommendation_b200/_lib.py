@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(HERE, "libfibinet_b200.so")
 IDX_I32, IDX_I64, IDX_F64, IDX_F32 = 0, 1, 2, 3
 PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
 BILINEAR_ALL, BILINEAR_EACH, BILINEAR_INTERACTION = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
+PREC_TF32X2 = 3
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}          # what the model path accepts
+GEMM_PRECISIONS = dict(PRECISIONS, tf32x2=PREC_TF32X2)                               # fbn_gemm only (K-major x K-major)
 BILINEAR_TYPES = {"all": BILINEAR_ALL, "field_all": BILINEAR_ALL, "each": BILINEAR_EACH, "field_each": BILINEAR_EACH,
                   "interaction": BILINEAR_INTERACTION, "field_interaction": BILINEAR_INTERACTION}
 

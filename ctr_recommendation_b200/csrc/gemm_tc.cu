@@ -4,6 +4,11 @@
 //                     x_h = x & 0xffffe000 (exactly representable in tf32) and x_l = x - x_h, fp32 accumulation
 //                     in TMEM (single-pass TF32 misses the 1e-5 logit tolerance, 3x passes it).
 //   FBN_PREC_BF16   : one kind::f16 (bf16) pass, fp32 accumulation in TMEM.
+//   FBN_PREC_TF32X2 : Ah*Bh as kind::tf32 plus Al*Bh + Ah*Bl as kind::f16 bf16 MMAs into the same accumulator.  The correction
+//                     terms are 2^-11 of the product, so bf16 operands (2^-9) keep the result at ~1.4e-6 while the tensor work
+//                     drops from 3 to 1 + 1/2 + 1/2 = 2 pass equivalents.  Operand part 1 holds, per 32-element k-block, one
+//                     128-byte row [hi as bf16 x32 | lo as bf16 x32]: the same 128B-swizzled K-major tile as the fp32 lo part,
+//                     the bf16 MMAs address the two halves by the ordinary in-row descriptor advance.  K-major operands only.
 //
 // Structure (one 128x128 output tile per CTA, 192 threads):
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d (128B swizzle) into a 3..6 stage smem ring
@@ -108,6 +113,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+constexpr bool is32(int mode) { return mode == FBN_PREC_TF32X3 || mode == FBN_PREC_TF32X2; }   // 4-byte operand parts
+
 template <int MODE>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   if (MODE == FBN_PREC_TF32X3) {
@@ -166,19 +173,48 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[128], float* s
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 struct TcCfg {
-  static constexpr int ESZ = MODE == FBN_PREC_TF32X3 ? 4 : 2;
+  static constexpr int ESZ = is32(MODE) ? 4 : 2;
   static constexpr int BK = 128 / ESZ;                                   // k-block: 32 (tf32) / 64 (bf16) elements
   static constexpr int UK = 32 / ESZ;                                    // K per tcgen05.mma: 8 / 16
   static constexpr int EPB = 128 / ESZ;                                  // elements per 128-byte swizzle row
-  static constexpr int NPART = MODE == FBN_PREC_TF32X3 ? 2 : 1;          // hi + lo
+  static constexpr int NPART = is32(MODE) ? 2 : 1;                       // hi + lo (tf32x3) / hi + [hi|lo as bf16] (tf32x2)
   static constexpr int TILE_BYTES = TC_BM * 128;                         // 128 x BK (K-major) == BK x 128 (MN-major)
   static constexpr int BOX_MN_BYTES = BK * 128;                          // one MN-major box: BK rows x 128 bytes
   static constexpr int STAGE_BYTES = 2 * NPART * TILE_BYTES;
-  static constexpr int STAGES = MODE == FBN_PREC_TF32X3 ? 3 : 6;
+  static constexpr int STAGES = is32(MODE) ? 3 : 6;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int NBAR = 2 * STAGES + 4;
-  static constexpr int FMT = MODE == FBN_PREC_TF32X3 ? 2 : 1;
+  static constexpr int FMT = is32(MODE) ? 2 : 1;
+  // k-blocks per TMEM chunk.  tf32x2 issues 8 MMAs per k-block instead of 12: 6 k-blocks keep the 48 accumulations per chunk (same
+  // truncation error) and give the epilogue warps as long to fold a chunk as before (MLP-1 forward GEMM, B = 65536: 460 us with 4,
+  // 441 us with 6; tf32x3: 517 us).  The gain stays well below the 1/3 fewer MMAs because operand delivery, not the tensor pipe, then
+  // sets the pace: 64 KB of smem fill per CTA and k-block in 1.2 us is ~7.7 TB/s of L2 -> smem traffic over the 148 SMs.
+  static constexpr int CHUNK = MODE == FBN_PREC_TF32X2 ? 6 : TC_CHUNK;
 };
+
+// the MMAs of one UK-wide k-step (k = 0 .. BK/UK-1) of a staged k-block.  a_p0/b_p0 = part 0 (hi), a_p1/b_p1 = part 1.
+template <int MODE>
+__device__ __forceinline__ void issue_kstep(uint32_t tacc, uint64_t a_p0, uint64_t b_p0, uint64_t a_p1, uint64_t b_p1, uint64_t adv_a,
+                                            uint64_t adv_b, int k, uint32_t idesc, uint32_t idesc_bf16, uint32_t acc) {
+  if (MODE == FBN_PREC_TF32X3) {
+    umma<FBN_PREC_TF32X3>(tacc, a_p1 + k * adv_a, b_p0 + k * adv_b, idesc, acc);      // small terms first
+    umma<FBN_PREC_TF32X3>(tacc, a_p0 + k * adv_a, b_p1 + k * adv_b, idesc, 1u);
+    umma<FBN_PREC_TF32X3>(tacc, a_p0 + k * adv_a, b_p0 + k * adv_b, idesc, 1u);
+  } else if (MODE == FBN_PREC_TF32X2) {
+    // K-major only: a k-step covers 8 tf32 = 32 bytes of the hi row.  The bf16 corrections run at 16 elements per MMA, i.e. once per
+    // two tf32 k-steps: part-1 row = [hi_bf16 x32 (bytes 0..63) | lo_bf16 x32 (bytes 64..127)], 16 bf16 = 32 bytes = 2 x (16-byte units).
+    if ((k & 1) == 0) {
+      const uint64_t h = (uint64_t)(k >> 1) * 2, l = 4 + (uint64_t)(k >> 1) * 2;
+      umma<FBN_PREC_BF16>(tacc, a_p1 + l, b_p1 + h, idesc_bf16, acc);                   // Al * Bh
+      umma<FBN_PREC_BF16>(tacc, a_p1 + h, b_p1 + l, idesc_bf16, 1u);                    // Ah * Bl
+      umma<FBN_PREC_TF32X3>(tacc, a_p0 + k * adv_a, b_p0 + k * adv_b, idesc, 1u);       // Ah * Bh (tf32)
+    } else {
+      umma<FBN_PREC_TF32X3>(tacc, a_p0 + k * adv_a, b_p0 + k * adv_b, idesc, acc);
+    }
+  } else {
+    umma<MODE>(tacc, a_p0 + k * adv_a, b_p0 + k * adv_b, idesc, acc);
+  }
+}
 
 struct TcMaps { CUtensorMap a[2], b[2]; };   // [0] = hi (or the only part), [1] = lo
 
@@ -273,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
       constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
       constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
-      constexpr bool base32 = MODE == FBN_PREC_TF32X3;   // 4-byte elements, MN-major: 32B-atom swizzle
+      constexpr bool base32 = is32(MODE);   // 4-byte elements, MN-major: 32B-atom swizzle
       constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
       constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
       int it = 0;
@@ -281,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         if (!active(kb)) continue;
         const int s = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1;
-        const int chunk = it / TC_CHUNK, buf = chunk & 1, pos = it % TC_CHUNK;
+        const int chunk = it / Cfg::CHUNK, buf = chunk & 1, pos = it % Cfg::CHUNK;
         if (pos == 0) {  // the epilogue must have drained this accumulator (two chunks ago)
           mbar_wait(tempty + buf, ((chunk >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -295,18 +331,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
           const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
-          if (Cfg::NPART == 2) {
-            const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
-            const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
-            umma<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);      // small terms first
-            umma<MODE>(tacc, a_hi + k * adv_a, b_lo + k * adv_b, idesc, 1u);
-            umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
-          } else {
-            umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
-          }
+          const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);           // part 1 (unused for bf16)
+          const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+          issue_kstep<MODE>(tacc, a_hi, b_hi, a_lo, b_lo, adv_a, adv_b, k, idesc, make_idesc(1, TC_BM, TC_BN, 0, 0), acc);
         }
         tc_commit(empty + s);                                  // frees the smem stage once the MMAs have read it
-        if (pos == TC_CHUNK - 1 || it == nact - 1) tc_commit(tfull + buf);   // chunk complete
+        if (pos == Cfg::CHUNK - 1 || it == nact - 1) tc_commit(tfull + buf);   // chunk complete
         ++it;
       }
     }
@@ -317,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     float acc[TC_BN];
 #pragma unroll
     for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
-    const int nchunks = (nact + TC_CHUNK - 1) / TC_CHUNK;
+    const int nchunks = (nact + Cfg::CHUNK - 1) / Cfg::CHUNK;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
       mbar_wait(tfull + buf, (c >> 1) & 1);
@@ -357,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 struct TcpCfg {
-  static constexpr int STAGES = MODE == FBN_PREC_TF32X3 ? 2 : 4;
+  static constexpr int STAGES = is32(MODE) ? 2 : 4;
   static constexpr int STAGE_BYTES = TcCfg<MODE>::STAGE_BYTES;
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int NBAR = 2 * STAGES + 4;
@@ -474,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
       constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
       constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
       constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
-      constexpr bool base32 = MODE == FBN_PREC_TF32X3;
+      constexpr bool base32 = is32(MODE);
       constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
       constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
       int it = 0, chunk = 0;       // global ring positions (continue across tiles)
@@ -486,7 +516,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
           if (!active(kb)) continue;
           const int s = it % PC::STAGES;
           const uint32_t ph = (it / PC::STAGES) & 1;
-          const int buf = chunk & 1, pos = done % TC_CHUNK;
+          const int buf = chunk & 1, pos = done % Cfg::CHUNK;
           if (pos == 0) {
             mbar_wait(tempty + buf, ((chunk >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -500,20 +530,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
 #pragma unroll
           for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
             const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
-            if (Cfg::NPART == 2) {
-              const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
-              const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
-              umma<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);
-              umma<MODE>(tacc, a_hi + k * adv_a, b_lo + k * adv_b, idesc, 1u);
-              umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
-            } else {
-              umma<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
-            }
+            const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
+            const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+            issue_kstep<MODE>(tacc, a_hi, b_hi, a_lo, b_lo, adv_a, adv_b, k, idesc, make_idesc(1, TC_BM, TC_BN, 0, 0), acc);
           }
           tc_commit(empty + s);
           ++done;
           ++it;
-          if (pos == TC_CHUNK - 1 || done == ti.nact) {
+          if (pos == Cfg::CHUNK - 1 || done == ti.nact) {
             tc_commit(tfull + buf);
             ++chunk;
           }
@@ -530,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
       float acc[TC_BN];
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
-      const int nchunks = (ti.nact + TC_CHUNK - 1) / TC_CHUNK;
+      const int nchunks = (ti.nact + Cfg::CHUNK - 1) / Cfg::CHUNK;
       for (int c = 0; c < nchunks; ++c, ++chunk) {
         const int buf = chunk & 1;
         mbar_wait(tfull + buf, (chunk >> 1) & 1);
@@ -702,7 +726,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
       constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
       constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
       constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
-      constexpr bool base32 = MODE == FBN_PREC_TF32X3;
+      constexpr bool base32 = is32(MODE);
       constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
       constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
       int it = 0;
@@ -710,7 +734,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
         if (!active(kb)) continue;
         const int s = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1;
-        const int chunk = it / TC_CHUNK, buf = chunk & 1, pos = it % TC_CHUNK;
+        const int chunk = it / Cfg::CHUNK, buf = chunk & 1, pos = it % Cfg::CHUNK;
         if (pos == 0) {
           mbar_wait(tempty + buf, ((chunk >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -724,7 +748,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 #pragma unroll
         for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
           const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
-          if (Cfg::NPART == 2) {
+          if (MODE == FBN_PREC_TF32X2) {         // see issue_kstep: tf32 hi*hi every k-step, the bf16 corrections every second one
+            const uint64_t a_p1 = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
+            const uint64_t b_p1 = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+            constexpr uint32_t idesc_bf16 = make_idesc(1, 256, TC2_BN, 0, 0);
+            if ((k & 1) == 0) {
+              const uint64_t h = (uint64_t)(k >> 1) * 2, l = 4 + (uint64_t)(k >> 1) * 2;
+              umma_pair<FBN_PREC_BF16>(tacc, a_p1 + l, b_p1 + h, idesc_bf16, acc);
+              umma_pair<FBN_PREC_BF16>(tacc, a_p1 + h, b_p1 + l, idesc_bf16, 1u);
+              umma_pair<FBN_PREC_TF32X3>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
+            } else {
+              umma_pair<FBN_PREC_TF32X3>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
+            }
+          } else if (Cfg::NPART == 2) {
             const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
             const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
             umma_pair<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);
@@ -735,7 +771,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
           }
         }
         tc_commit_pair(empty + s);
-        if (pos == TC_CHUNK - 1 || it == nact - 1) tc_commit_pair(tfull + buf);
+        if (pos == Cfg::CHUNK - 1 || it == nact - 1) tc_commit_pair(tfull + buf);
         ++it;
       }
     }
@@ -745,7 +781,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
     float acc[128];
 #pragma unroll
     for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-    const int nchunks = (nact + TC_CHUNK - 1) / TC_CHUNK;
+    const int nchunks = (nact + Cfg::CHUNK - 1) / Cfg::CHUNK;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
       mbar_wait(tfull + buf, (c >> 1) & 1);
@@ -803,6 +839,20 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long ld, lo
       const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
       st4(d + r * Kp + c, h);
       st4(d + lo_off + r * Kp + c, v - h);
+    } else if (MODE == FBN_PREC_TF32X2) {
+      // part 0: hi (tf32 in an fp32 word); part 1: per 32-element k-block one 128-byte row [hi as bf16 x32 | lo as bf16 x32]
+      float* d = static_cast<float*>(dst);
+      const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      st4(d + r * Kp + c, h);
+      const float4 l = v - h;
+      char* blk = reinterpret_cast<char*>(d + lo_off + r * Kp + (c & ~31LL)) + (c & 31) * 2;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(h.x, h.y), h1 = __floats2bfloat162_rn(h.z, h.w);
+      __nv_bfloat162 l0 = __floats2bfloat162_rn(l.x, l.y), l1 = __floats2bfloat162_rn(l.z, l.w);
+      uint2 oh, ol;
+      oh.x = *reinterpret_cast<uint32_t*>(&h0); oh.y = *reinterpret_cast<uint32_t*>(&h1);
+      ol.x = *reinterpret_cast<uint32_t*>(&l0); ol.y = *reinterpret_cast<uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(blk) = oh;
+      *reinterpret_cast<uint2*>(blk + 64) = ol;
     } else {
       __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
       __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
@@ -838,14 +888,14 @@ static EncodeTiledFn get_encode() {
 static int make_map(CUtensorMap* m, int mode, const void* base, long long rows, long long cols, long long pitch, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   FBN_REQUIRE(enc != nullptr, FBN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const int esz = mode == FBN_PREC_TF32X3 ? 4 : 2;
+  const int esz = is32(mode) ? 4 : 2;
   const cuuint32_t epb = 128 / esz;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(pitch * esz)};
   cuuint32_t box[2] = {epb, mn_major ? epb : 128u};   // MN-major: BK == epb rows of K
   cuuint32_t estr[2] = {1, 1};
   FBN_REQUIRE(aligned16(base) && (pitch * esz) % 16 == 0, FBN_ERR_ALIGN, "tcgen05 operand is not 16-byte aligned");
-  CUresult r = enc(m, mode == FBN_PREC_TF32X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = enc(m, is32(mode) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    (mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -857,8 +907,8 @@ static int make_map(CUtensorMap* m, int mode, const void* base, long long rows, 
 static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 size_t packed_bytes(long long rows, long long cols, int precision) {
-  const long long pitch = round_up(cols, 8);
-  return (size_t)(rows * pitch * (precision == FBN_PREC_TF32X3 ? 8 : 2)) + 1024;
+  const long long pitch = round_up(cols, precision == FBN_PREC_TF32X2 ? 32 : 8);
+  return (size_t)(rows * pitch * (is32(precision) ? 8 : 2)) + 1024;
 }
 
 Packed packed_describe(void* region, long long rows, long long cols) {
@@ -873,15 +923,22 @@ Packed packed_describe(void* region, long long rows, long long cols) {
 // converts src (rows x cols fp32, ld) into operand format at dst (1024-byte aligned inside the caller's region)
 int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
                  Packed* out, cudaStream_t st) {
-  FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16, FBN_ERR_ARG, "pack_operand: bad precision");
+  FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16 || precision == FBN_PREC_TF32X2, FBN_ERR_ARG,
+              "pack_operand: bad precision");
   FBN_REQUIRE(aligned16(src) && ld % 4 == 0, FBN_ERR_ALIGN, "pack_operand: source must be 16-byte aligned with ld %% 4 == 0");
   *out = packed_describe(dst, rows, cols);
+  if (precision == FBN_PREC_TF32X2) {          // whole 32-element k-blocks per row (the interleaved bf16 part needs them)
+    out->pitch = round_up(cols, 32);
+    out->lo_off = rows * out->pitch;
+  }
   const long long pitch = out->pitch, lo_off = out->lo_off;
   void* base = out->data;
   const long long n = rows * (pitch / 4);
   int blocks = (int)std::min<long long>(cdiv(n, 256), 16LL * num_sms());
   if (precision == FBN_PREC_TF32X3)
     pack_rows_kernel<FBN_PREC_TF32X3><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, rows, cols, pitch, base, lo_off, colmask);
+  else if (precision == FBN_PREC_TF32X2)
+    pack_rows_kernel<FBN_PREC_TF32X2><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, rows, cols, pitch, base, lo_off, colmask);
   else
     pack_rows_kernel<FBN_PREC_BF16><<<std::max(blocks, 1), 256, 0, st>>>(src, ld, rows, cols, pitch, base, lo_off, colmask);
   FBN_CHECK_LAUNCH();
@@ -894,6 +951,8 @@ size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precisio
 }
 
 bool gemm_tc_supported(const GemmArgs& g, int precision) {
+  if (precision == FBN_PREC_TF32X2)   // K-major x K-major only, no pre-packed operands of another format
+    return g.a_t == 0 && g.b_t != 0 && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch == 1;
   return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16) && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch >= 1;
 }
 
@@ -1054,9 +1113,46 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
   return FBN_OK;
 }
 
+// FBN_PREC_TF32X2: C[M,N] = A[M,K] * B[N,K]^T, both operands K-major, packed here (hi | interleaved bf16 hi/lo), single-CTA tiles
+static int gemm_tc_x2(const GemmArgs& g, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  constexpr int MODE = FBN_PREC_TF32X2;
+  const size_t na = g.pkA.data ? 0 : packed_bytes(g.M, g.K, MODE), nb = g.pkB.data ? 0 : packed_bytes(g.N, g.K, MODE);
+  FBN_REQUIRE(na + nb == 0 || (scratch != nullptr && scratch_bytes >= na + nb), FBN_ERR_ARG,
+              "tcgen05 GEMM (tf32x2): operand scratch too small (%zu < %zu)", scratch_bytes, na + nb);
+  Packed pa = g.pkA, pb = g.pkB;      // pre-packed operands must be in the tf32x2 format (pack_operand with this precision)
+  uint8_t* sp = static_cast<uint8_t*>(scratch);
+  int rc = FBN_OK;
+  if (!pa.data) rc = pack_operand(g.A, g.lda, g.M, g.K, MODE, sp, ~0ull, &pa, st);
+  if (rc) return rc;
+  if (!pb.data) rc = pack_operand(g.B, g.ldb, g.N, g.K, MODE, sp + na, ~0ull, &pb, st);
+  if (rc) return rc;
+  TcMaps maps;
+  // part 0 clips at K (TMA zero fill); part 1 is addressed in whole 32-slot blocks, its padding was zeroed by the pack kernel
+  rc = make_map(&maps.a[0], MODE, pa.data, g.M, g.K, pa.pitch, false);
+  if (rc) return rc;
+  rc = make_map(&maps.a[1], MODE, static_cast<float*>(pa.data) + pa.lo_off, g.M, pa.pitch, pa.pitch, false);
+  if (rc) return rc;
+  rc = make_map(&maps.b[0], MODE, pb.data, g.N, g.K, pb.pitch, false);
+  if (rc) return rc;
+  rc = make_map(&maps.b[1], MODE, static_cast<float*>(pb.data) + pb.lo_off, g.N, pb.pitch, pb.pitch, false);
+  if (rc) return rc;
+  TcArgs t;
+  t.C = g.C; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
+  t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
+  const long long pair_ctas = 2 * cdiv(g.M, 256) * cdiv(g.N, TC2_BN) * g.splits;
+  if (g_tc_pair && g_tc_persistent <= 0 && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {      // same rule as the other precisions
+    dim3 grid2((unsigned)(2 * cdiv(g.M, 256)), (unsigned)cdiv(g.N, TC2_BN), (unsigned)g.splits);
+    return launch_tc2<MODE, false, false>(maps, t, grid2, st);
+  }
+  dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)g.splits);
+  return launch_tc<MODE, false, false>(maps, t, grid, st, false);
+}
+
 int gemm_tc(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-  FBN_REQUIRE(gemm_tc_supported(g, precision), FBN_ERR_SHAPE, "tcgen05 GEMM: unsupported shape (N %lld must be a multiple of 128)", g.N);
+  FBN_REQUIRE(gemm_tc_supported(g, precision), FBN_ERR_SHAPE,
+              "tcgen05 GEMM: unsupported shape / layout (N %lld must be a multiple of 128; tf32x2 takes a_t = 0, b_t = 1 only)", g.N);
   if (g.M <= 0) return FBN_OK;
+  if (precision == FBN_PREC_TF32X2) return gemm_tc_x2(g, scratch, scratch_bytes, st);
   if (precision == FBN_PREC_TF32X3) return gemm_tc_mode<FBN_PREC_TF32X3>(g, scratch, scratch_bytes, st);
   return gemm_tc_mode<FBN_PREC_BF16>(g, scratch, scratch_bytes, st);
 }

@@ -99,7 +99,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, bias=None, a_t=False, b_t=False, prec
     K = a.shape[0] if a_t else a.shape[1]
     N = b.shape[0] if b_t else b.shape[1]
     c = torch.empty(M, N, dtype=torch.float32, device=a.device)
-    prec = _lib.PRECISIONS[precision]
+    prec = _lib.GEMM_PRECISIONS[precision]
     nbytes = lib.fbn_gemm_scratch_bytes(M, N, K, prec)
     scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=a.device)
     _lib.check(lib.fbn_gemm(_lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(c), M, N, K, a.shape[1], b.shape[1], N, int(a_t),

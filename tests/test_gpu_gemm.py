@@ -99,3 +99,33 @@ def test_model_step_identical_under_kernel_variants(knobs, precision):
             ref = outs[0][1][k]
             err = (g[k] - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
             assert err <= (1e-5 if precision == "tf32x3" else 5e-2), (k, err)
+
+
+@pytest.mark.parametrize("persistent", [-1, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 512, 2688), (4096, 256, 512), (40000, 128, 128), (1000, 384, 1000), (256, 512, 4096),
+                                   (20000, 512, 1056)])        # last: large enough for the CTA-pair kernel
+def test_tf32x2_gemm(knobs, persistent, M, N, K):
+    """FBN_PREC_TF32X2 (hi*hi as one tf32 MMA + the two correction terms as bf16 MMAs = 2 tensor-pass equivalents instead of 3)
+    against an fp64 matmul: K-major x K-major operands, fp32-grade within 4e-6 (numpy simulation of the scheme: 1.3-1.5e-6)."""
+    from ctr_recommendation_b200.functional import gemm
+    knobs.fbn_set_option(b"tc_persistent", persistent)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = torch.relu(torch.randn(M, K, device="cuda", generator=g))            # ReLU-like activations
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05                 # nn.Linear weight (N, K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = (A.double() @ W.double().t() + bias.double()).float()
+    out = gemm(A, W, bias, a_t=False, b_t=True, precision="tf32x2")
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 4e-6, err
+    x3 = gemm(A, W, bias, a_t=False, b_t=True, precision="tf32x3")
+    assert (x3 - ref).abs().max().item() / ref.abs().max().item() <= 3e-6
+
+
+def test_tf32x2_rejects_other_layouts(knobs):
+    from ctr_recommendation_b200.functional import gemm
+    from ctr_recommendation_b200._lib import FibinetCudaError
+    A = torch.randn(256, 128, device="cuda")
+    B = torch.randn(128, 128, device="cuda")
+    with pytest.raises(FibinetCudaError):
+        gemm(A, B, None, a_t=False, b_t=False, precision="tf32x2")          # B stored (K,N) would be MN-major
