@@ -248,6 +248,12 @@ class MM_FiBiNET(nn.Module):
     def attach_mm_table(self, table: torch.Tensor):
         """Keep the frozen (item_rows,128) item_emb_d128 matrix resident on the GPU; batches that do
         not carry ``item_emb_d128`` are then gathered from it inside the fused kernel."""
+        rows = self._shard.item_rows if self._shard is not None else self.item_emb.weight.shape[0]
+        table = torch.as_tensor(table)
+        if table.dim() != 2 or table.shape[1] != D:
+            raise ValueError(f"item_emb_d128 table must be (rows, {D})")
+        if table.shape[0] < rows:       # the kernel indexes it with the clamped item id: pad so that every id is in range
+            table = torch.cat([table, torch.zeros(rows - table.shape[0], D, dtype=table.dtype)], 0)
         self._mm_table = table.to(self.item_emb.weight.device, torch.float32).contiguous()
 
     def _params_struct(self) -> _lib.Params:

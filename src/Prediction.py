@@ -24,7 +24,8 @@ class InferenceCollator(BatchCollator):
     """Label-less collation; unknown item ids get an all-zero item_emb_d128 instead of raising."""
 
     def __init__(self, max_len, column_index, item_info_path):
-        super().__init__(None, max_len, column_index, item_info_path, strict=False)
+        # with_mm=False: item_emb_d128 stays on the GPU (resident matrix gathered by item_id inside the fused kernel)
+        super().__init__(None, max_len, column_index, item_info_path, strict=False, with_mm=False)
 
 
 def main():
@@ -51,15 +52,17 @@ def main():
 
     test_dataset = ParquetDataset(dataset_cfg["test_data"])
     collator = InferenceCollator(int(model_cfg.get("max_len", 20)), test_dataset.column_index, dataset_cfg["item_info"])
-    loader = DataLoader(test_dataset, batch_size=8192, shuffle=False, num_workers=int(os.environ.get("FBN_NUM_WORKERS", "4")),
-                        collate_fn=collator)
+    model.attach_mm_table(torch.from_numpy(collator.item_embedding_matrix))
+    # the batched fetch (ParquetDataset.__getitems__) makes the single-process loader faster than 4 workers + IPC
+    loader = DataLoader(test_dataset, batch_size=8192, shuffle=False, num_workers=int(os.environ.get("FBN_NUM_WORKERS", "0")),
+                        collate_fn=collator, pin_memory=True)
     scorers, preds = {}, []
     for batch in loader:
         rows = batch["item_id"].shape[0]
         seq = batch.get("item_seq")
         key = (rows, 0 if seq is None else seq.shape[1], batch["item_id"].dtype)
         if key not in scorers:
-            scorers[key] = Scorer(model, key[0], key[1], idx_dtype=key[2])
+            scorers[key] = Scorer(model, key[0], key[1], idx_dtype=key[2], use_mm_table=True)
         preds.append(scorers[key](batch).clone())      # stays on the device: no per-batch host sync (reference: .cpu() per batch)
     predictions = torch.cat(preds).cpu().numpy()
 

@@ -49,17 +49,20 @@ def main():
 
     batch_size = int(model_cfg.get("batch_size", 4096))
     max_len = int(model_cfg.get("max_len", 20))
-    workers = int(os.environ.get("FBN_NUM_WORKERS", "4"))
+    # single-process loader by default: with the batched fetch (ParquetDataset.__getitems__) it outruns 4 workers + IPC.
+    # with_mm=False: batches carry ids only, the frozen item_emb_d128 matrix lives on the GPU
+    workers = int(os.environ.get("FBN_NUM_WORKERS", "0"))
     train_loader = MMCTRDataLoader(None, dataset_cfg["train_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=True,
-                                   num_workers=workers, max_len=max_len)
+                                   num_workers=workers, max_len=max_len, with_mm=False, pin_memory=True)
     valid_loader = MMCTRDataLoader(None, dataset_cfg["valid_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=False,
-                                   num_workers=workers, max_len=max_len)
+                                   num_workers=workers, max_len=max_len, with_mm=False, pin_memory=True)
 
     fm = {"precision": model_cfg.get("precision", "tf32x3")}
     row_sharded = str(model_cfg.get("table_sharding", "")).lower() == "row"   # B200 extra: item table partitioned by id % world
     if row_sharded:
         fm["table_sharding"] = "row"
     model = build_model(fm, model_cfg).to(device)
+    model.attach_mm_table(torch.from_numpy(train_loader.collator.item_embedding_matrix))
     if world > 1:
         fdist.broadcast_parameters(model)
     lr = float(model_cfg.get("learning_rate", 1e-3))
@@ -78,13 +81,13 @@ def main():
         key = ("t", rows, L, dtype)
         if key not in engines:
             cls = ShardedTrainStep if row_sharded else TrainStep
-            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0)
+            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True)
         return engines[key]
 
     def score_engine(rows, L, dtype):
         key = ("s", rows, L, dtype)
         if key not in engines:
-            engines[key] = Scorer(model, rows, L, idx_dtype=dtype)
+            engines[key] = Scorer(model, rows, L, idx_dtype=dtype, use_mm_table=True)
         return engines[key]
 
     best_auc = 0.0

@@ -177,3 +177,35 @@ def test_lazy_adam_oracle_matches_dense_adam_on_touched_rows():
     p, m, v = sorc.lazy_adam_rows(p0, z, z, g, touched, 3e-3, 0.9, 0.999, 1e-8, 1e-5, step=1)
     assert np.array_equal(p[touched], P["w"][touched]) and np.array_equal(m[touched], opt.state["w"]["m"][touched])
     assert np.array_equal(p[~touched], p0[~touched]) and np.all(m[~touched] == 0) and np.all(v[~touched] == 0)
+
+
+def test_loader_batched_fetch_and_resident_mm_mode(tmp_path):
+    """ParquetDataset.__getitems__ (one fancy-index copy, or a view for sequential batches) == stacking the rows one by one;
+    with_mm=False drops the per-batch item_emb_d128 block (the GPU gathers it from the resident matrix) but keeps the strict check."""
+    import subprocess
+    import importlib.util
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_dataset.py"), str(tmp_path), "--train", "200", "--valid", "10",
+                    "--test", "50", "--items", "2000"], check=True, capture_output=True)
+    spec = importlib.util.spec_from_file_location("our_dl2", os.path.join(ROOT, "src", "dataloader.py"))
+    dl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dl)
+    ds = dl.ParquetDataset(str(tmp_path / "train.parquet"))
+    for idx in ([3, 4, 5, 6], [7], [9, 2, 150, 2, 31]):
+        assert np.array_equal(ds.__getitems__(idx), np.stack([ds[i] for i in idx]))
+    full = dl.BatchCollator(None, 20, ds.column_index, str(tmp_path / "item_info.parquet"))
+    lean = dl.BatchCollator(None, 20, ds.column_index, str(tmp_path / "item_info.parquet"), with_mm=False)
+    rows = [ds[i] for i in (5, 1, 77)]
+    (bf, yf), (bl, yl) = full(rows), lean(ds.__getitems__([5, 1, 77]))
+    assert "item_emb_d128" in bf and "item_emb_d128" not in bl and torch.equal(yf, yl)
+    for k in bl:
+        assert torch.equal(bf[k], bl[k]), k
+    assert np.array_equal(full.item_embedding_matrix[bf["item_id"].long().numpy()], bf["item_emb_d128"].numpy())
+    bad = ds.__getitems__([0, 1]).copy()
+    bad[1, ds.column_index["item_id"]] = 999999
+    with pytest.raises(KeyError):
+        lean(bad)
+    torch.manual_seed(0)
+    a = dl.MMCTRDataLoader(None, str(tmp_path / "train.parquet"), str(tmp_path / "item_info.parquet"), batch_size=64, shuffle=True,
+                           num_workers=0, max_len=20, with_mm=False)
+    seen = torch.cat([b["user_id"] for b, _ in a])
+    assert seen.numel() == 200 and sorted(seen.tolist()) == sorted(ds.darray[:, ds.column_index["user_id"]].tolist())
