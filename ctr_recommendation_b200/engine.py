@@ -79,6 +79,7 @@ class TrainStep:
         self.dprob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.initial_step_counter = 0      # set before the first step to resume the dropout stream of an earlier run (checkpoint resume)
         self.hyper_dev = torch.zeros(12, dtype=torch.float32, device=dev)
         self.hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
         self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(max(self._table_grad_numel(), model._flat.numel())), 16),
@@ -186,7 +187,7 @@ class TrainStep:
         torch.cuda.synchronize()
         for b, k in zip((m.mlp[1].running_mean, m.mlp[1].running_var, m.mlp[5].running_mean, m.mlp[5].running_var), keep):
             b.copy_(k)                         # the warm-up forward must not count as a training step
-        self.step_counter.zero_()
+        self.step_counter.fill_(int(self.initial_step_counter))
         # group the stages into graphs: a new graph starts after every collective
         groups, cur_fns = [], []
         for fn, coll in self._stages():
@@ -253,6 +254,8 @@ class TrainStep:
         else:
             self.inp.load(batch, labels)
         self._write_hyper()
+        if self._steps == 0 and not self._use_graph:
+            self.step_counter.fill_(int(self.initial_step_counter))
         if self._use_graph and self._graphs is None:
             self._capture()
         if self._use_graph:

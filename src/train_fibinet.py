@@ -82,6 +82,7 @@ def main():
         if key not in engines:
             cls = ShardedTrainStep if row_sharded else TrainStep
             engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True)
+            engines[key].initial_step_counter = resume_counters.get(str(key), 0)      # continue the dropout stream on resume
         return engines[key]
 
     def score_engine(rows, L, dtype):
@@ -93,8 +94,22 @@ def main():
     best_auc = 0.0
     os.makedirs("../checkpoints", exist_ok=True)
     best_path = "../checkpoints/FiBiNET_best.pth"
+    # Resume (the reference only ever saves the best weights and cannot continue a run): after every epoch rank 0
+    # writes the full training state -- weights, Adam moments + step, scheduler, dropout-stream counters, loader RNG -- and
+    # FBN_RESUME=1 continues from it bit for bit.  Not offered for a row-sharded table (its moments live on the owning ranks).
+    last_path = "../checkpoints/FiBiNET_last.pth"
+    start_epoch, resume_counters = 0, {}
+    if os.environ.get("FBN_RESUME") == "1" and os.path.exists(last_path) and not row_sharded:
+        state = torch.load(last_path, map_location="cpu", weights_only=False)
+        model.load_state_dict(state["model"])
+        optimizer.load_state_dict(state["optimizer"])
+        scheduler.load_state_dict(state["scheduler"])
+        start_epoch, best_auc, resume_counters = state["epoch"], state["best_auc"], state["dropout_counters"]
+        torch.set_rng_state(state["torch_rng"])
+        log(f"[resume] {last_path}: continuing at epoch {start_epoch + 1}")
+    stop_after = int(os.environ.get("FBN_STOP_AFTER_EPOCH", "0"))
     log("[train] start")
-    for epoch in range(epochs):
+    for epoch in range(start_epoch, epochs):
         model.train()
         total_loss = torch.zeros(1, device=device)
         steps = 0
@@ -131,6 +146,16 @@ def main():
                 if rank == 0:
                     torch.save(sd, best_path)
                     log(f"[ckpt] new best -> {best_path}")
+        if rank == 0 and not row_sharded:
+            torch.cuda.synchronize()
+            torch.save({"model": model.state_dict(),
+                        "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()},
+                        "scheduler": scheduler.state_dict(), "epoch": epoch + 1, "best_auc": best_auc,
+                        "dropout_counters": {str(k): int(e.step_counter.item()) for k, e in engines.items() if k[0] == "t"},
+                        "torch_rng": torch.get_rng_state()}, last_path)
+        if stop_after and epoch + 1 >= stop_after:
+            log(f"[train] stopping after epoch {epoch + 1} (FBN_STOP_AFTER_EPOCH)")
+            return
     log(f"Done. Best AUC: {best_auc:.4f}")
 
 

@@ -58,3 +58,42 @@ def test_train_and_predict_scripts(tmp_path, table_sharding):
     with torch.no_grad():
         y = model({k: v.cuda() for k, v in batch.items()}).cpu().numpy()
     assert np.allclose(y, sub["Task2"].to_numpy()[:256], atol=1e-6)
+
+
+def _run_train(cwd, env_extra):
+    env = dict(os.environ, FBN_NUM_WORKERS="0", PYTHONPATH=ROOT, **env_extra)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "src", "train_fibinet.py")], cwd=cwd, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_resume_continues_bit_for_bit(tmp_path):
+    """SURVEY 8f-3: FiBiNET_last.pth carries weights, Adam moments + step, scheduler, dropout-stream counters and the loader RNG;
+    1 epoch + FBN_RESUME=1 for the remaining 2 ends in exactly the state of an uninterrupted 3-epoch run (dropout is ON)."""
+    states = {}
+    for tag in ("straight", "resumed"):
+        root = tmp_path / tag
+        data = root / "data" / "MicroLens_1M_x1"
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_dataset.py"), str(data), "--train", "1500", "--valid", "300",
+                        "--test", "10"], check=True, capture_output=True)
+        cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "fibinet_config.yaml")))
+        cfg[cfg["base_expid"]].update(epochs=3, batch_size=512)
+        (root / "config").mkdir()
+        yaml.safe_dump(cfg, open(root / "config" / "fibinet_config.yaml", "w"))
+        cwd = root / "src"
+        cwd.mkdir()
+        if tag == "straight":
+            _run_train(cwd, {})
+        else:
+            out = _run_train(cwd, {"FBN_STOP_AFTER_EPOCH": "1"})
+            assert "stopping after epoch 1" in out
+            out = _run_train(cwd, {"FBN_RESUME": "1"})
+            assert "continuing at epoch 2" in out
+        states[tag] = torch.load(root / "checkpoints" / "FiBiNET_last.pth", map_location="cpu", weights_only=False)
+    a, b = states["straight"], states["resumed"]
+    assert a["epoch"] == b["epoch"] == 3 and a["dropout_counters"] == b["dropout_counters"] and a["optimizer"]["step"] == b["optimizer"]["step"]
+    for k in a["model"]:
+        assert torch.equal(a["model"][k], b["model"][k]), k
+    for k in ("m_flat", "v_flat", "m_item", "v_item"):
+        assert torch.equal(a["optimizer"][k], b["optimizer"][k]), k
