@@ -26,6 +26,42 @@ from ctr_recommendation_b200 import sharded  # noqa: E402
 from ctr_recommendation_b200.engine import Scorer, ShardedTrainStep, TrainStep  # noqa: E402
 
 
+class DeviceBatches:
+    """The training split resident on the GPU, in the loader's own dtypes (float64 scalars, int64 history cropped to max_len,
+    float32 labels: 188 bytes / row, 0.7 GB for MicroLens_1M_x1's 3.6 M rows).  A batch is a slice / index_select on the device,
+    so an epoch involves no host work at all -- the reference-style loader delivers 0.3-2 M samples/s, the step consumes 7-15 M.
+    Opt-in (FBN_DEVICE_DATASET=1); same batches as the loader when shuffling is off."""
+
+    def __init__(self, loader, device, shuffle):
+        ds, coll = loader.dataset, loader.collator
+        mat, ci = ds.darray, ds.column_index
+        coll.check_known(mat[:, ci["item_id"]])                       # the loader's strict check, once for the whole split
+
+        def dev(a, dtype=None):
+            a = np.ascontiguousarray(a if dtype is None else a.astype(dtype))
+            return torch.from_numpy(a).to(device)
+        self.cols = {k: dev(mat[:, ci[k]]) for k in ("item_id", "likes_level", "views_level")}
+        if "item_seq" in ci:
+            idx = ci["item_seq"]
+            lo, hi = idx[0], idx[0] + len(idx)
+            self.cols["item_seq"] = dev(mat[:, max(lo, hi - coll.max_len):hi], np.int64)
+        self.labels = dev(mat[:, ci["label"]], np.float32)
+        self.n, self.batch, self.shuffle, self.device = mat.shape[0], loader.batch_size, shuffle, device
+
+    def __len__(self):
+        return -(-self.n // self.batch)
+
+    def __iter__(self):
+        order = torch.randperm(self.n).to(self.device) if self.shuffle else None      # CPU generator: covered by the resume state
+        for i in range(0, self.n, self.batch):
+            if order is None:
+                sl = slice(i, min(self.n, i + self.batch))
+                yield {k: v[sl] for k, v in self.cols.items()}, self.labels[sl]
+            else:
+                idx = order[i:i + self.batch]
+                yield {k: v.index_select(0, idx) for k, v in self.cols.items()}, self.labels.index_select(0, idx)
+
+
 def load_config():
     path = "../config/fibinet_config.yaml"
     if not os.path.exists(path):
@@ -52,7 +88,8 @@ def main():
     # single-process loader by default: with the batched fetch (ParquetDataset.__getitems__) it outruns 4 workers + IPC.
     # with_mm=False: batches carry ids only, the frozen item_emb_d128 matrix lives on the GPU
     workers = int(os.environ.get("FBN_NUM_WORKERS", "0"))
-    train_loader = MMCTRDataLoader(None, dataset_cfg["train_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=True,
+    shuffle = os.environ.get("FBN_SHUFFLE", "1") != "0"
+    train_loader = MMCTRDataLoader(None, dataset_cfg["train_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=shuffle,
                                    num_workers=workers, max_len=max_len, with_mm=False, pin_memory=True)
     valid_loader = MMCTRDataLoader(None, dataset_cfg["valid_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=False,
                                    num_workers=workers, max_len=max_len, with_mm=False, pin_memory=True)
@@ -108,12 +145,16 @@ def main():
         torch.set_rng_state(state["torch_rng"])
         log(f"[resume] {last_path}: continuing at epoch {start_epoch + 1}")
     stop_after = int(os.environ.get("FBN_STOP_AFTER_EPOCH", "0"))
+    train_batches = train_loader
+    if os.environ.get("FBN_DEVICE_DATASET") == "1":
+        train_batches = DeviceBatches(train_loader, device, shuffle)
+        log(f"[data] training split resident on the GPU: {train_batches.n} rows")
     log("[train] start")
     for epoch in range(start_epoch, epochs):
         model.train()
         total_loss = torch.zeros(1, device=device)
         steps = 0
-        for batch_dict, labels in train_loader:
+        for batch_dict, labels in train_batches:
             shard, ylab, _ = fdist.shard_batch(batch_dict, labels, rank, world)     # DataParallel-style split on dim 0
             rows = ylab.shape[0]
             seq = shard.get("item_seq")

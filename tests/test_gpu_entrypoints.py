@@ -97,3 +97,27 @@ def test_resume_continues_bit_for_bit(tmp_path):
         assert torch.equal(a["model"][k], b["model"][k]), k
     for k in ("m_flat", "v_flat", "m_item", "v_item"):
         assert torch.equal(a["optimizer"][k], b["optimizer"][k]), k
+
+
+def test_device_resident_dataset_matches_loader(tmp_path):
+    """FBN_DEVICE_DATASET=1 (training split resident on the GPU, batches cut on the device) trains to exactly the same state as
+    the DataLoader path when both see the rows in file order."""
+    states = {}
+    for tag, extra in (("loader", {"FBN_SHUFFLE": "0"}), ("device", {"FBN_SHUFFLE": "0", "FBN_DEVICE_DATASET": "1"})):
+        root = tmp_path / tag
+        data = root / "data" / "MicroLens_1M_x1"
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_dataset.py"), str(data), "--train", "1500", "--valid", "300",
+                        "--test", "10"], check=True, capture_output=True)
+        cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "fibinet_config.yaml")))
+        cfg[cfg["base_expid"]].update(epochs=2, batch_size=512)
+        (root / "config").mkdir()
+        yaml.safe_dump(cfg, open(root / "config" / "fibinet_config.yaml", "w"))
+        cwd = root / "src"
+        cwd.mkdir()
+        out = _run_train(cwd, extra)
+        assert ("resident on the GPU" in out) == (tag == "device")
+        states[tag] = torch.load(root / "checkpoints" / "FiBiNET_last.pth", map_location="cpu", weights_only=False)
+    a, b = states["loader"], states["device"]
+    for k in a["model"]:
+        assert torch.equal(a["model"][k], b["model"][k]), k
+    assert torch.equal(a["optimizer"]["m_item"], b["optimizer"]["m_item"])
