@@ -43,12 +43,25 @@ def _stamp() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if the sources changed) and link the library.  Safe under torchrun: the whole build is serialised by an
+    exclusive file lock (ranks that find the library missing wait for the first one instead of compiling into the same
+    object files), and the link goes to a temporary name that is renamed over the final .so."""
+    import fcntl
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     stamp_file = os.path.join(OBJ, "stamp")
     stamp = _stamp()
     if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return OUT
     nvcc = _nvcc()
-    os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src):
@@ -63,10 +76,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart", "-lcuda"]
+    tmp = OUT + f".tmp{os.getpid()}"
+    cmd = [nvcc, *ARCH, "-shared", "-o", tmp, *objs, "-lcudart", "-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, OUT)
     with open(stamp_file, "w") as fh:
         fh.write(stamp)
     return OUT

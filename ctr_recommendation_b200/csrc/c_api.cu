@@ -70,6 +70,7 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   w.B = B; w.L = L;
   w.ids = (int32_t*)take(Bp * 4 * 4);
   w.seq = (int32_t*)take(Bp * Lp * 4);
+  w.idflag = (int32_t*)take(4 * 4);
   w.X5 = (float*)take(Bp * NA * D * f);
   w.sgate = (float*)take(Bp * 8 * f);
   w.xhat = (float*)take(Bp * D * f);
@@ -260,7 +261,7 @@ extern "C" size_t fbn_workspace_offset(int64_t batch, int64_t seq_len, int64_t i
   char* base = reinterpret_cast<char*>(uintptr_t(4096));
   carve_workspace(w, base, batch, seq_len, item_rows);
   struct { const char* n; void* p; } tab[] = {
-      {"ids", w.ids}, {"seq", w.seq}, {"X5", w.X5}, {"sgate", w.sgate}, {"xhat", w.xhat}, {"rstd", w.rstd}, {"cnt", w.cnt},
+      {"ids", w.ids}, {"seq", w.seq}, {"idflag", w.idflag}, {"X5", w.X5}, {"sgate", w.sgate}, {"xhat", w.xhat}, {"rstd", w.rstd}, {"cnt", w.cnt},
       {"C", w.C}, {"T", w.T}, {"H1", w.Hd1}, {"A1", w.A1}, {"H2", w.Hd2}, {"A2", w.A2}, {"logit", w.logit}, {"prob", w.prob},
       {"bn", w.bn}, {"dlogit", w.dlogit}, {"dH2", w.dH2}, {"dH1", w.dH1}, {"dC", w.dC}, {"dT", w.dT}, {"dV", w.dV},
       {"dXitem", w.dXitem}, {"dXhist", w.dXhist}, {"dln", w.dln}, {"dy", w.dy}, {"row_off", w.row_off}, {"row_cnt", w.row_cnt},
@@ -345,7 +346,7 @@ static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace&
   e.seq = b->seq_len > 0 ? b->item_seq : nullptr;
   e.item_mm = b->item_mm; e.mm_table = b->mm_table; e.idx_dtype = b->idx_dtype; e.seq_dtype = b->seq_dtype;
   e.B = B; e.L = (int)b->seq_len; e.item_rows = p->item_rows; e.cate_rows = (int)p->cate_rows; e.save = save;
-  e.ids = w.ids; e.seq32 = w.seq; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.xmm = w.xmm; e.rstd = w.rstd; e.cnt = w.cnt;
+  e.ids = w.ids; e.seq32 = w.seq; e.idflag = w.idflag; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.xmm = w.xmm; e.rstd = w.rstd; e.cnt = w.cnt;
   e.C = w.C;
   e.pkC = pkC; e.pkX = pkX;
   e.nshard = p->n_shards;

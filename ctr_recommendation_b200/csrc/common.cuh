@@ -149,6 +149,7 @@ struct Workspace {
   // canonical indices
   int32_t* ids;      // (B,4): item_id, likes, views, n_valid
   int32_t* seq;      // (B,L)
+  int32_t* idflag;   // (4) sticky out-of-range flags written by the gather kernel
   // forward activations kept for backward
   float* X5;         // (B,5,128) fields 1..5 before SENET
   float* sgate;      // (B,8) sigmoid gates s_0..s_5

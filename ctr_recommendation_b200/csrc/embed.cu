@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
         iid = __shfl_sync(0xffffffffu, iid, 0);
         lk = __shfl_sync(0xffffffffu, lk, 1);
         vw = __shfl_sync(0xffffffffu, vw, 2);
-        // out-of-range ids would be an IndexError in torch; clamp so the kernel cannot fault
+        // out-of-range ids are an IndexError in torch (nn.Embedding, ref :155-159): flag them for the host, which raises, and
+        // clamp so the kernel itself cannot fault
+        if (lane == 0 && (iid < 0 || iid >= a.item_rows)) a.idflag[0] = 1;
+        if (lane == 1 && (lk < 0 || lk >= a.cate_rows || vw < 0 || vw >= a.cate_rows)) a.idflag[1] = 1;
         iid = min(max(iid, 0LL), a.item_rows - 1);
         lk = min(max(lk, 0LL), (long long)a.cate_rows - 1);
         vw = min(max(vw, 0LL), (long long)a.cate_rows - 1);
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
             int myid = 0;
             if (l0 + lane < a.L) {
               long long v = load_index(a.seq, a.seq_dtype, b * a.L + l0 + lane);
+              if (v < 0 || v >= a.item_rows) a.idflag[2] = 1;
               myid = (int)min(max(v, 0LL), a.item_rows - 1);
               if (a.save) a.seq32[b * a.L + l0 + lane] = myid;
             }

@@ -17,6 +17,7 @@ struct EmbedFwdArgs {
   long long B; int L; long long item_rows; int cate_rows;
   int save;            // write the tensors backward needs
   int32_t* ids; int32_t* seq32;
+  int32_t* idflag;     // [0] item_id, [1] likes/views, [2] item_seq out of range (sticky; torch raises IndexError for these)
   float* X5; float* sgate; float* xhat; float* xmm; float* rstd; float* cnt; float* C;
   PackDst pkC;         // packed copy of the field blocks of C
   PackDst pkX;         // packed copy of the item_emb_d128 rows (B,128)

@@ -56,8 +56,11 @@ class _StaticBatch:
 
 
 class TrainStep:
+    HYPER_SLOTS = 16
+
     def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
-                 seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True):
+                 seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True,
+                 global_batch: int | None = None):
         if not isinstance(model, MM_FiBiNET) or not isinstance(optimizer, FusedAdam):
             raise TypeError("TrainStep needs a ctr_recommendation_b200 MM_FiBiNET and its FusedAdam")
         self.model, self.opt, self.max_norm = model, optimizer, max_norm
@@ -78,10 +81,15 @@ class TrainStep:
         self.prob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.dprob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.initial_step_counter = 0      # set before the first step to resume the dropout stream of an earlier run (checkpoint resume)
+        # dropout stream position: ONE counter per model, shared by every engine that drives it (a tail-batch engine must not
+        # replay the masks the main engine used at the same local step); model.set_dropout_counter(n) resumes a stream
+        self.step_counter = model._dropout_counter(dev)
         self.hyper_dev = torch.zeros(12, dtype=torch.float32, device=dev)
-        self.hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+        # the host never waits for the device between steps, so the pinned source of the hyper-parameter copy of step t must
+        # not be rewritten while that copy is still queued: a ring of pinned slots, each guarded by the event of its last copy
+        self._hyper_ring = [torch.zeros(12, dtype=torch.float32).pin_memory() for _ in range(self.HYPER_SLOTS)]
+        self._hyper_ev = [None] * self.HYPER_SLOTS
+        self._hyper_pos = 0
         self.sumsq_scratch = torch.zeros(max(self.lib.fbn_sumsq_partial_floats(max(self._table_grad_numel(), model._flat.numel())), 16),
                                          dtype=torch.float32, device=dev)
         self._side = torch.cuda.Stream(device=dev)
@@ -92,7 +100,9 @@ class TrainStep:
         self._h2d_done = torch.cuda.Event()
         self._stage_free = torch.cuda.Event()
         self._prefetched = False
-        self.loss_weight = 1.0 / self.world
+        # DataParallel semantics (reference src/train_fibinet.py:69-70,115): the loss is the mean over the GLOBAL batch, so this
+        # rank's local mean is weighted by B_r / B (scatter chunking gives the last ranks fewer rows on a tail batch)
+        self.loss_weight = (batch_size / float(global_batch)) if global_batch else 1.0 / self.world
         self._bs = self._batch_struct()
         self._graphs = None
         self._use_graph = graph
@@ -176,6 +186,10 @@ class TrainStep:
                                       clip, None, _lib.ptr(self.hyper_dev), st), "fbn_adam_dense")
         self.step_counter += 1
 
+    def check_ids(self):
+        """IndexError if any batch since the last call carried an id outside its table (synchronises; see MM_FiBiNET.check_ids)."""
+        self.model.check_ids(self.ws, self.B, self.L)
+
     def _capture(self):
         m = self.model
         keep = [b.clone() for b in (m.mlp[1].running_mean, m.mlp[1].running_var, m.mlp[5].running_mean, m.mlp[5].running_var)]
@@ -187,7 +201,6 @@ class TrainStep:
         torch.cuda.synchronize()
         for b, k in zip((m.mlp[1].running_mean, m.mlp[1].running_var, m.mlp[5].running_mean, m.mlp[5].running_var), keep):
             b.copy_(k)                         # the warm-up forward must not count as a training step
-        self.step_counter.fill_(int(self.initial_step_counter))
         # group the stages into graphs: a new graph starts after every collective
         groups, cur_fns = [], []
         for fn, coll in self._stages():
@@ -213,7 +226,11 @@ class TrainStep:
         self.opt._step += 1
         t = self.opt._step
         lr, b1, b2 = float(g["lr"]), float(g["betas"][0]), float(g["betas"][1])
-        h = self.hyper_host
+        slot = self._hyper_pos % self.HYPER_SLOTS
+        self._hyper_pos += 1
+        if self._hyper_ev[slot] is not None:
+            self._hyper_ev[slot].synchronize()      # the copy that last read this slot has executed
+        h = self._hyper_ring[slot]
         h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, float(g["eps"]), float(g["weight_decay"])
         h[5] = lr / (1.0 - b1 ** t)
         h[6] = math.sqrt(1.0 - b2 ** t)
@@ -221,6 +238,9 @@ class TrainStep:
         h[8], h[9] = 1.0 - b1, 1.0 - b2          # evaluated in double like torch, rounded to fp32 by the store
         h[10] = (1.0 - lr * float(g["weight_decay"])) if self.opt.decoupled else 0.0     # AdamW decay multiplier
         self.hyper_dev.copy_(h, non_blocking=True)
+        ev = self._hyper_ev[slot] or torch.cuda.Event()
+        ev.record()
+        self._hyper_ev[slot] = ev
 
     # ------------------------------------------------------------------
     def prefetch(self, batch: dict, labels: torch.Tensor):
@@ -254,8 +274,6 @@ class TrainStep:
         else:
             self.inp.load(batch, labels)
         self._write_hyper()
-        if self._steps == 0 and not self._use_graph:
-            self.step_counter.fill_(int(self.initial_step_counter))
         if self._use_graph and self._graphs is None:
             self._capture()
         if self._use_graph:
@@ -279,6 +297,22 @@ class TrainStep:
         dist.all_reduce(m._gflat, op=dist.ReduceOp.SUM)
         dist.all_reduce(m._item_grad, op=dist.ReduceOp.SUM)
 
+    def step_empty(self) -> torch.Tensor:
+        """This rank received no rows of the global batch (torch's scatter chunking leaves the last ranks empty when
+        n < world * ceil(n / world), e.g. n = 17 on 8 ranks): contribute zero gradients, join the collectives and apply the
+        same update as every other rank.  Eager launches (a tail batch happens once per epoch)."""
+        m = self.model
+        if self.world == 1:
+            raise RuntimeError("step_empty() only makes sense with more than one rank")
+        m._gflat.zero_()
+        m._item_grad.zero_()
+        self._write_hyper()
+        self._allreduce()
+        self._update()
+        self._steps += 1
+        self.loss.zero_()
+        return self.loss
+
 
 class ShardedTrainStep(TrainStep):
     """TrainStep for a row-sharded item table (``feature_map={"table_sharding": "row", ...}``, sharded.py).
@@ -293,12 +327,12 @@ class ShardedTrainStep(TrainStep):
 
     def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
                  seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True,
-                 lazy: bool = False, merge_cap: int | None = None):
+                 lazy: bool = False, merge_cap: int | None = None, global_batch: int | None = None):
         if model._shard is None:
             raise TypeError("ShardedTrainStep needs a model built with table_sharding='row'")
         self.lazy = bool(lazy)
         self._merge_cap = merge_cap
-        super().__init__(model, optimizer, batch_size, seq_len, idx_dtype, seq_dtype, max_norm, use_mm_table, graph)
+        super().__init__(model, optimizer, batch_size, seq_len, idx_dtype, seq_dtype, max_norm, use_mm_table, graph, global_batch)
         st = model._shard
         if st.world != self.world:
             raise ValueError(f"the table is sharded over {st.world} ranks but the process group has {self.world}")
@@ -431,6 +465,10 @@ class Scorer:
             self._stage.load(batch)
             self._h2d_done.record(self._copy)
         self._prefetched = True
+
+    def check_ids(self):
+        """IndexError if any batch scored since the last call carried an id outside its table (synchronises)."""
+        self.model.check_ids(self.ws, self.B, self.L)
 
     def _fwd(self):
         m = self.model

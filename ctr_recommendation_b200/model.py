@@ -197,10 +197,31 @@ class MM_FiBiNET(nn.Module):
         self._cur = None
         self._fwd_token = 0
         self._mm_table: Optional[torch.Tensor] = None   # optional resident item_emb_d128 table
+        self.check_ids_every_forward = True             # eager module path: IndexError for out-of-range ids, like torch (one sync)
         self._fused_optimizer = None                    # set by FusedAdam
-        self._seed, self._offset = 0x5EED, 0
+        # Philox key of the dropout masks: from torch's seed (set_seed(cfg seed) in the scripts) mixed with the rank, so that
+        # runs with different seeds draw different masks and every rank draws its own (like DataParallel's replicas)
+        self._seed, self._offset = self._derive_seed(), 0
+        self._drop_ctr: Optional[torch.Tensor] = None   # device step counter shared by all TrainStep engines of this model
         self._test_masks = None
         self._dense_table_grad = False                  # data parallel: every table-gradient row is written
+
+    @staticmethod
+    def _derive_seed() -> int:
+        import torch.distributed as dist
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+        z = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + (rank + 1) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z ^= z >> 31
+        return z & 0x7FFFFFFFFFFFFFFF
+
+    def _dropout_counter(self, device) -> torch.Tensor:
+        if self._drop_ctr is None or self._drop_ctr.device != torch.device(device):
+            self._drop_ctr = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._drop_ctr
+
+    def set_dropout_counter(self, n: int):
+        """Continue the dropout stream of an earlier run at optimizer step ``n`` (checkpoint resume)."""
+        self._dropout_counter(self.item_emb.weight.device).fill_(int(n))
 
     # ------------------------------------------------------------------ parameter plumbing
     def _dense_params(self):
@@ -310,6 +331,23 @@ class MM_FiBiNET(nn.Module):
         itemsize = torch.empty((), dtype=dtype).element_size()
         return ws[off:off + n * itemsize].view(dtype).view(*shape)
 
+    def check_ids(self, ws: Optional[torch.Tensor] = None, B: Optional[int] = None, L: Optional[int] = None):
+        """Raise IndexError if the gather kernel met an id outside its table since the last check (torch's nn.Embedding raises
+        for these, reference src/model_fibinet.py:155-167; the kernel clamps so that it cannot fault and sets a sticky device
+        flag).  Synchronises the stream: the eager module path calls it after every forward (``check_ids_every_forward``),
+        TrainStep / Scorer users call ``engine.check_ids()`` whenever they read results back."""
+        if ws is None:
+            ws, B, L = self._cur["ws"], self._cur["B"], self._cur["L"]
+        off = _lib.load().fbn_workspace_offset(B, L, self._ws_rows(), b"idflag")
+        flag = ws[off:off + 16].view(torch.int32)
+        f = flag.tolist()
+        if any(f[:3]):
+            flag.zero_()
+            bad = [n for n, v in zip(("item_id", "likes_level / views_level", "item_seq"), f) if v]
+            rows = self._shard.item_rows if self._shard is not None else self.item_emb.weight.shape[0]
+            raise IndexError(f"index out of range in self: {', '.join(bad)} (item table has {rows} rows, "
+                             f"cate table {self.cate_emb.weight.shape[0]})")
+
     # ------------------------------------------------------------------ batch marshalling
     def _batch_struct(self, batch_dict: Dict[str, torch.Tensor]):
         item_id = batch_dict["item_id"]
@@ -385,6 +423,8 @@ class MM_FiBiNET(nn.Module):
                 self.mlp[5].num_batches_tracked += 1
         self._fwd_token += 1
         self._cur = dict(B=B, L=L, ws=ws, bs=bs, keep=keep, train=train, p_drop=p_drop, masks=(m1, m2))
+        if self.check_ids_every_forward and not torch.cuda.is_current_stream_capturing():
+            self.check_ids()
         return prob
 
     def _run_backward(self, dprob: torch.Tensor):

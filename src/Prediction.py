@@ -65,6 +65,8 @@ def main():
             scorers[key] = Scorer(model, key[0], key[1], idx_dtype=key[2], use_mm_table=True)
         preds.append(scorers[key](batch).clone())      # stays on the device: no per-batch host sync (reference: .cpu() per batch)
     predictions = torch.cat(preds).cpu().numpy()
+    for sc in scorers.values():
+        sc.check_ids()                                  # IndexError for ids outside the tables, as nn.Embedding would raise
 
     sub = pd.DataFrame({"ID": range(len(predictions)), "Task2": predictions})
     sub.to_csv("prediction_fibinet.csv", index=False)

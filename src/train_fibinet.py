@@ -114,12 +114,12 @@ def main():
                                                     pct_start=0.3, div_factor=25.0, final_div_factor=1000.0)
     engines = {}
 
-    def train_engine(rows, L, dtype):
-        key = ("t", rows, L, dtype)
+    def train_engine(rows, L, dtype, n_global):
+        # n_global is part of the key: this rank's loss weight is rows / n_global (DataParallel: mean over the global batch)
+        key = ("t", rows, L, dtype, n_global)
         if key not in engines:
             cls = ShardedTrainStep if row_sharded else TrainStep
-            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True)
-            engines[key].initial_step_counter = resume_counters.get(str(key), 0)      # continue the dropout stream on resume
+            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True, global_batch=n_global)
         return engines[key]
 
     def score_engine(rows, L, dtype):
@@ -135,13 +135,14 @@ def main():
     # writes the full training state -- weights, Adam moments + step, scheduler, dropout-stream counters, loader RNG -- and
     # FBN_RESUME=1 continues from it bit for bit.  Not offered for a row-sharded table (its moments live on the owning ranks).
     last_path = "../checkpoints/FiBiNET_last.pth"
-    start_epoch, resume_counters = 0, {}
+    start_epoch = 0
     if os.environ.get("FBN_RESUME") == "1" and os.path.exists(last_path) and not row_sharded:
-        state = torch.load(last_path, map_location="cpu", weights_only=False)
+        state = torch.load(last_path, map_location="cpu", weights_only=True)     # tensors + plain Python values only
         model.load_state_dict(state["model"])
         optimizer.load_state_dict(state["optimizer"])
         scheduler.load_state_dict(state["scheduler"])
-        start_epoch, best_auc, resume_counters = state["epoch"], state["best_auc"], state["dropout_counters"]
+        start_epoch, best_auc = int(state["epoch"]), float(state["best_auc"])
+        model.set_dropout_counter(int(state["dropout_counter"]))                 # continue the dropout stream
         torch.set_rng_state(state["torch_rng"])
         log(f"[resume] {last_path}: continuing at epoch {start_epoch + 1}")
     stop_after = int(os.environ.get("FBN_STOP_AFTER_EPOCH", "0"))
@@ -156,24 +157,32 @@ def main():
         steps = 0
         for batch_dict, labels in train_batches:
             shard, ylab, _ = fdist.shard_batch(batch_dict, labels, rank, world)     # DataParallel-style split on dim 0
-            rows = ylab.shape[0]
+            rows, n_global = ylab.shape[0], labels.shape[0]
             seq = shard.get("item_seq")
-            step = train_engine(rows, 0 if seq is None else seq.shape[1], shard["item_id"].dtype)
-            loss = step(shard, ylab)                       # fwd + BCE + bwd + clip(10) + Adam, one graph replay
+            if rows == 0:      # scatter chunking left this rank without rows (tiny tail batch): zero gradients, same collectives
+                loss = next(e for k, e in engines.items() if k[0] == "t").step_empty()
+            else:
+                step = train_engine(rows, 0 if seq is None else seq.shape[1], shard["item_id"].dtype, n_global)
+                loss = step(shard, ylab)                   # fwd + BCE + bwd + clip(10) + Adam, one graph replay
             scheduler.step()
             total_loss += loss                             # stays on the device: no per-step host sync
             steps += 1
             if steps % 200 == 0:
                 log(f"Epoch {epoch + 1} | Step {steps} | Loss: {loss.item():.4f} | LR: {scheduler.get_last_lr()[0]:.6f}")
         avg_loss = (total_loss.item() / steps) if steps else 0.0
+        for k, e in engines.items():
+            e.check_ids()                                  # IndexError for ids outside the tables, as nn.Embedding would raise
 
         model.eval()
         y_trues, y_preds = [], []
         for batch_dict, labels in valid_loader:
             shard, ylab, _ = fdist.shard_batch(batch_dict, labels, rank, world)
             seq = shard.get("item_seq")
-            sc = score_engine(ylab.shape[0], 0 if seq is None else seq.shape[1], shard["item_id"].dtype)
-            pred = fdist.gather_predictions(sc(shard).clone())
+            if ylab.shape[0] == 0:
+                local = torch.empty(0, dtype=torch.float32, device=device)
+            else:
+                local = score_engine(ylab.shape[0], 0 if seq is None else seq.shape[1], shard["item_id"].dtype)(shard).clone()
+            pred = fdist.gather_predictions(local)
             y_trues.append(labels.numpy())
             y_preds.append(pred.cpu().numpy())
         if y_trues:
@@ -189,11 +198,17 @@ def main():
                     log(f"[ckpt] new best -> {best_path}")
         if rank == 0 and not row_sharded:
             torch.cuda.synchronize()
+            # tensors and plain values only (loads with weights_only=True); written beside the old file and renamed over it, so a
+            # crash during the save never leaves a truncated resume file
+            sched_state = {k: v for k, v in scheduler.state_dict().items() if isinstance(v, (int, float, bool, str, list, tuple, dict))
+                           and k != "_scale_fn_ref"}
+            tmp = last_path + ".tmp"
             torch.save({"model": model.state_dict(),
                         "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()},
-                        "scheduler": scheduler.state_dict(), "epoch": epoch + 1, "best_auc": best_auc,
-                        "dropout_counters": {str(k): int(e.step_counter.item()) for k, e in engines.items() if k[0] == "t"},
-                        "torch_rng": torch.get_rng_state()}, last_path)
+                        "scheduler": sched_state, "epoch": epoch + 1, "best_auc": float(best_auc),
+                        "dropout_counter": int(model._dropout_counter(device).item()),
+                        "torch_rng": torch.get_rng_state()}, tmp)
+            os.replace(tmp, last_path)
         if stop_after and epoch + 1 >= stop_after:
             log(f"[train] stopping after epoch {epoch + 1} (FBN_STOP_AFTER_EPOCH)")
             return

@@ -1,0 +1,128 @@
+"""GPU tests of the loop-body engines' host logic: hyper-parameter hand-off without host syncs, the shared dropout
+stream, out-of-range ids (IndexError like nn.Embedding, reference src/model_fibinet.py:155-167), loss weighting."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from gpu_common import make_model, to_dev
+    import ctr_recommendation_b200  # noqa: F401
+    return dict(make_model=make_model, to_dev=to_dev)
+
+
+def _pinned(b):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items() if k != "user_id"}
+
+
+def test_many_unsynchronised_steps_graph_equals_eager(gpu):
+    """The host runs far ahead of the device (no .item(), no synchronize between steps) while OneCycleLR rewrites lr and
+    beta1 every step: each queued step must still see ITS hyper-parameters (ring of pinned slots), i.e. the CUDA-graph
+    engine ends bit-identical to the same launches issued eagerly, and different from a run with frozen hyper-parameters."""
+    from ctr_recommendation_b200 import FusedAdam
+    from ctr_recommendation_b200.engine import TrainStep
+    B, steps = 2048, 72                       # > 4 * HYPER_SLOTS queued copies
+    pool = [synth.make_batch(seed=900 + s, batch=B, index_dtype=np.float64, edge_cases=False) for s in range(3)]
+    dev = [({k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in b.items() if k != "user_id"}, torch.from_numpy(y).cuda())
+           for b, y in pool]
+    finals = []
+    for graph in (True, False):
+        model = gpu["make_model"](train=True, precision="tf32x3")
+        opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=steps + 8, pct_start=0.3)
+        eng = TrainStep(model, opt, B, 20, idx_dtype=torch.float64, graph=graph)
+        assert TrainStep.HYPER_SLOTS * 4 <= steps
+        for s in range(steps):
+            eng(*dev[s % 3])
+            sched.step()
+        torch.cuda.synchronize()
+        finals.append({k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()})
+        m, v = opt.moments()["mlp.4.weight"]
+        finals[-1]["_m"] = m.cpu().numpy().copy()
+    for k in finals[0]:
+        assert np.array_equal(finals[0][k], finals[1][k]), k
+
+
+def test_engines_of_one_model_share_the_dropout_stream(gpu):
+    from ctr_recommendation_b200 import FusedAdam
+    from ctr_recommendation_b200.engine import TrainStep
+    model = gpu["make_model"](train=True, precision="fp32")
+    opt = FusedAdam(model, lr=1e-3)
+    a = TrainStep(model, opt, 256, 20, idx_dtype=torch.float64)
+    b = TrainStep(model, opt, 96, 20, idx_dtype=torch.float64)
+    assert a.step_counter.data_ptr() == b.step_counter.data_ptr()
+    ba, ya = synth.make_batch(seed=1, batch=256, index_dtype=np.float64)
+    bb, yb = synth.make_batch(seed=2, batch=96, index_dtype=np.float64)
+    for _ in range(3):
+        a(_pinned(ba), torch.from_numpy(ya).pin_memory())
+    b(_pinned(bb), torch.from_numpy(yb).pin_memory())
+    assert int(a.step_counter.item()) == 4
+    model.set_dropout_counter(11)
+    assert int(b.step_counter.item()) == 11
+
+
+def test_dropout_seed_follows_torch_seed(gpu):
+    from ctr_recommendation_b200 import build_model
+    torch.manual_seed(123)
+    s1 = build_model(None, {"embedding_dim": 128})._seed
+    torch.manual_seed(123)
+    s2 = build_model(None, {"embedding_dim": 128})._seed
+    torch.manual_seed(124)
+    s3 = build_model(None, {"embedding_dim": 128})._seed
+    assert s1 == s2 and s1 != s3
+
+
+@pytest.mark.parametrize("column,value", [("item_id", 91718.0), ("item_id", -1.0), ("likes_level", 11.0), ("views_level", -2.0),
+                                          ("item_seq", 91718)])
+def test_out_of_range_ids_raise_index_error(gpu, column, value):
+    model = gpu["make_model"]()
+    batch, _ = synth.make_batch(seed=5, batch=64, index_dtype=np.float64)
+    with torch.no_grad():
+        model(gpu["to_dev"](batch))                       # a clean batch passes
+    if column == "item_seq":
+        batch["item_seq"][17, -1] = value
+    else:
+        batch[column][17] = value
+    with pytest.raises(IndexError, match="index out of range"):
+        with torch.no_grad():
+            model(gpu["to_dev"](batch))
+    batch2, _ = synth.make_batch(seed=5, batch=64, index_dtype=np.float64)
+    with torch.no_grad():
+        model(gpu["to_dev"](batch2))                      # the flag was cleared by the raise
+
+
+def test_engine_check_ids(gpu):
+    from ctr_recommendation_b200.engine import Scorer
+    model = gpu["make_model"]()
+    sc = Scorer(model, 128, 20, idx_dtype=torch.int64)
+    batch, _ = synth.make_batch(seed=6, batch=128, index_dtype=np.int64)
+    sc(gpu["to_dev"](batch))
+    sc.check_ids()
+    batch["item_id"][3] = 10 ** 9
+    sc(gpu["to_dev"](batch))
+    with pytest.raises(IndexError):
+        sc.check_ids()
+    sc.check_ids()                                        # sticky flag cleared
+
+
+def test_global_batch_loss_weight(gpu):
+    """DataParallel semantics: a rank's gradient contribution is (rows / global rows) x its local-mean gradient."""
+    from ctr_recommendation_b200 import FusedAdam
+    from ctr_recommendation_b200.engine import TrainStep
+    b, y = synth.make_batch(seed=3, batch=200, index_dtype=np.float64)
+    grads = []
+    for n in (None, 500):
+        model = gpu["make_model"](train=True, precision="fp32")
+        model.dropout_p = 0.0
+        opt = FusedAdam(model, lr=1e-3)
+        eng = TrainStep(model, opt, 200, 20, idx_dtype=torch.float64, graph=False, global_batch=n)
+        eng(_pinned(b), torch.from_numpy(y).pin_memory())
+        torch.cuda.synchronize()
+        grads.append(model._gflat.clone())
+    ratio = (grads[1].double().norm() / grads[0].double().norm()).item()
+    assert abs(ratio - 200 / 500) <= 1e-5

@@ -30,19 +30,30 @@ def main():
     rank, local, world = fdist.init_from_env()
     torch.cuda.set_device(local)
     precision = "tf32x3"
-    B, steps = 1024, 3
+    # global batch sizes: even split, uneven tail (rank shards of different size: loss weights B_r / B), and a tail so small that
+    # torch's scatter chunking leaves the last rank WITHOUT rows (it joins the collectives with zero gradients)
+    sizes = [1024, 1023, world - 1] if world > 1 else [1024, 1023]
+    steps = len(sizes)
     model = make(precision)
     fdist.broadcast_parameters(model)
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=20)
-    per = B // world
-    eng = TrainStep(model, opt, per, 20, idx_dtype=torch.float64)
-    batches = [synth.make_batch(seed=700 + s, batch=B, id_dist="zipf", index_dtype=np.float64) for s in range(steps)]
+    engines = {}
+
+    def engine(rows, n):
+        if (rows, n) not in engines:
+            engines[(rows, n)] = TrainStep(model, opt, rows, 20, idx_dtype=torch.float64, global_batch=n)
+        return engines[(rows, n)]
+    batches = [synth.make_batch(seed=700 + s, batch=B, id_dist="zipf", index_dtype=np.float64, edge_cases=B >= 8)
+               for s, B in enumerate(sizes)]
     grads_dp = []
     for b, y in batches:
         tb = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in b.items() if k != "user_id"}
         shard, ys, w = fdist.shard_batch(tb, torch.from_numpy(y), rank, world)
-        eng({k: v.pin_memory() for k, v in shard.items()}, ys.pin_memory())
+        if ys.shape[0] == 0:
+            next(iter(engines.values())).step_empty()
+        else:
+            engine(ys.shape[0], y.shape[0])({k: v.pin_memory() for k, v in shard.items()}, ys.pin_memory())
         sched.step()
         if len(grads_dp) == 0:      # the all-reduced gradients of the first step (identical weights on both sides)
             torch.cuda.synchronize()
@@ -68,6 +79,8 @@ def main():
             gsum, isum = None, None
             for r in range(world):
                 shard, ys, w = fdist.shard_batch(tb, ty, r, world)
+                if ys.shape[0] == 0:
+                    continue
                 sopt.zero_grad()
                 out = single(shard)
                 (torch.nn.BCELoss()(out, ys) * w).backward()
@@ -100,7 +113,7 @@ def main():
             rel = d.mean().item()
             worst = max(worst, rel)
             assert rel <= 0.05 * 5e-4, (k, rel)
-        print(f"dp_check OK: {world} ranks, replicas identical, first-step all-reduced gradients within {grad_worst:.2e} (rel) of the "
+        print(f"dp_check OK: {world} ranks, global batches {sizes} (uneven + empty-shard tails), replicas identical, first-step all-reduced gradients within {grad_worst:.2e} (rel) of the "
               f"single-process DataParallel emulation, worst mean |weight diff| after {steps} steps {worst:.2e}")
     dist.barrier()
     dist.destroy_process_group()

@@ -1,0 +1,110 @@
+"""CPU study: how accurate is a split-operand tensor-core GEMM scheme *inside the model*?
+
+Every matmul of the numpy oracle (forward and backward) is replaced by an emulation of one scheme
+
+    tf32x3 : Ah*Bh + Ah*Bl + Al*Bh, hi = x & 0xffffe000 (tf32), lo = x - hi (truncated to tf32 by the tensor core)
+    tf32x2 : Ah*Bh (tf32) + bf16(Ah)*bf16(Bl) + bf16(Al)*bf16(Bh)
+    bf16x3 : h = bf16_rn(x), l = bf16_rn(x - h) ; hh + hl + lh   (three kind::f16 passes at the bf16 rate)
+    bf16   : one bf16 pass
+
+with exact (fp64) accumulation of the products, rounded to fp32 once -- i.e. the operand-representation error only,
+which is what separates the schemes (accumulation order noise is the same ~1e-7 for all of them).  The result is compared
+with the fp64 oracle on probabilities, logits and all 21 gradients (max|a-b| / max|b| per tensor).
+
+    python tools/split_precision_sim.py [B]
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import fibinet_numpy as O  # noqa: E402
+from oracle import synth  # noqa: E402
+
+
+def bf16_rn(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def tf32_trunc(x):
+    return (np.ascontiguousarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+SCHEME = "fp32"
+
+
+def split_mm(a, b):
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    d = np.float64
+    if SCHEME == "fp32":
+        return (a.astype(d) @ b.astype(d)).astype(np.float32)
+    if SCHEME == "bf16":
+        return (bf16_rn(a).astype(d) @ bf16_rn(b).astype(d)).astype(np.float32)
+    if SCHEME == "bf16x3":
+        ah, bh = bf16_rn(a), bf16_rn(b)
+        al, bl = bf16_rn(a - ah), bf16_rn(b - bh)
+        return (ah.astype(d) @ bh.astype(d) + ah.astype(d) @ bl.astype(d) + al.astype(d) @ bh.astype(d)).astype(np.float32)
+    ah, bh = tf32_trunc(a), tf32_trunc(b)
+    al, bl = a - ah, b - bh
+    if SCHEME == "tf32x3":
+        al, bl = tf32_trunc(al), tf32_trunc(bl)
+        return (ah.astype(d) @ bh.astype(d) + ah.astype(d) @ bl.astype(d) + al.astype(d) @ bh.astype(d)).astype(np.float32)
+    if SCHEME == "tf32x2":
+        return (ah.astype(d) @ bh.astype(d) + bf16_rn(ah).astype(d) @ bf16_rn(bl).astype(d)
+                + bf16_rn(al).astype(d) @ bf16_rn(bh).astype(d)).astype(np.float32)
+    raise ValueError(SCHEME)
+
+
+class Q(np.ndarray):
+    """ndarray whose @ is the emulated tensor-core product; propagates through ufuncs / views."""
+    __array_priority__ = 100
+
+    def __matmul__(self, other):
+        return split_mm(self, other).view(Q)
+
+    def __rmatmul__(self, other):
+        return split_mm(other, self).view(Q)
+
+
+def run(P, batch, labels, masks, scheme):
+    global SCHEME
+    SCHEME = scheme
+    Pq = {k: (np.array(v).view(Q) if v.dtype.kind == "f" else np.array(v)) for k, v in P.items()}
+    bq = dict(batch)
+    bq["item_emb_d128"] = np.array(batch["item_emb_d128"]).view(Q)
+    prob, cache = O.forward(Pq, bq, train=True, masks=masks, dtype=np.float32, update_running=False)
+    _, dprob = O.bce_loss(np.asarray(prob), labels)
+    G = O.backward(Pq, cache, dprob.view(Q))
+    return np.asarray(prob), np.asarray(cache["logit"]), {k: np.asarray(v) for k, v in G.items()}, cache
+
+
+def rel(a, b):
+    b = np.asarray(b, np.float64)
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    P = synth.make_weights(7)
+    batch, labels = synth.make_batch(101, B, id_dist="zipf")
+    masks = synth.make_dropout_masks(5, B)
+    P64 = {k: v.copy() for k, v in P.items()}
+    p64, c64 = O.forward(P64, batch, train=True, masks=masks, dtype=np.float64, update_running=False)
+    _, dp64 = O.bce_loss(p64, labels, np.float64)
+    G64 = O.backward(P64, c64, dp64)
+    for scheme in ("fp32", "tf32x3", "tf32x2", "bf16x3", "bf16"):
+        p, logit, G, c = run(P, batch, labels, masks, scheme)
+        flips1 = int(((c["Y1"] > 0) != (c64["Y1"] > 0)).sum())
+        flips2 = int(((c["Y2"] > 0) != (c64["Y2"] > 0)).sum())
+        errs = {k: rel(G[k], G64[k]) for k in G}
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+        print(f"{scheme:7s} prob {rel(p, p64):.2e} logit {rel(logit, c64['logit']):.2e} relu flips {flips1}+{flips2}  "
+              f"grad max {max(errs.values()):.2e}  worst: " + ", ".join(f"{k} {v:.1e}" for k, v in worst), flush=True)
+
+
+if __name__ == "__main__":
+    main()
