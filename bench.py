@@ -2,7 +2,7 @@
 """bench.py -- FiBiNET train-step throughput on synthetic MicroLens_1M_x1-shaped batches.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref, else the port), rank 0 only
 
 One "step" = zero_grad -> forward -> BCELoss -> backward -> clip_grad_norm_(10) -> Adam(wd 1e-5) ->
 OneCycleLR (reference src/train_fibinet.py:113-122) over one batch.  Prints ONE JSON line (rank 0).
@@ -42,8 +42,9 @@ def parse():
                     help="per-GPU batch (BASELINE config 2 sweeps 1K-64K; 65536 is its largest point)")
     ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"])
     ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"])
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows per CPU-baseline step (0 = the per-GPU batch itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config1", action="store_true", help="skip the second block at the reference's batch_size 4096")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through")
     ap.add_argument("--bilinear", default="all", choices=["all", "each", "interaction"],
                     help="bilinear_type (BASELINE config 2 sweep); the reference hard-codes 'all'")
@@ -170,7 +171,7 @@ def run_ours(args):
         from oracle import synth as _synth
         model.attach_mm_table(torch.from_numpy(_synth.make_item_mm_table(seed=11)))
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
-    total_steps = max(10, 2 * (args.steps + args.warmup) * 2 + 10)
+    total_steps = max(10, 12 * (args.steps + args.warmup) * 2 + 64)
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=total_steps, pct_start=0.3, div_factor=25.0,
                                                 final_div_factor=1000.0)
     loss_fn = torch.nn.BCELoss()
@@ -277,11 +278,6 @@ def run_ours(args):
         ms_e2e = timed(e2e, args.steps)
 
     global_batch = args.batch * world
-    bil = "bilinear all" if args.bilinear == "all" else f"bilinear {args.bilinear} [not the reference's hard-coded 'all']"
-    workload = (f"FiBiNET {'train step' if not infer else 'eval forward'} (config/fibinet_config.yaml model: D=128, 6 fields, {bil}, "
-                f"MLP 2688-512-256-1), per-GPU batch {args.batch}, history L={L_HIST}, item ids {args.id_dist}, " +
-                (f"item table of {model._shard.item_rows} rows row-sharded over {world} ranks (remote gather over NVLink, owner-side "
-                 f"gradient merge, {'lazy row' if args.lazy else 'dense-exact'} Adam)" if sharded else "replicated tables"))
     value = global_batch * args.steps / (ms / 1e3)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
     peaks = load_peaks()
@@ -294,22 +290,49 @@ def run_ours(args):
         "metric": METRIC if not infer else "inference samples/sec FiBiNET MicroLens-shape (Prediction.py path)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
-        "config": {"workload": workload,
-                   "global_batch": global_batch, "per_gpu_batch": args.batch,
-                   "parallelism": f"dp{world}" + ("+row-sharded item table" if sharded else ""),
-                   "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
-                   "l2": "working set per step (table p/m/v/grad 188 MB + activations) exceeds the 126 MB L2; inputs cycle over "
-                         f"{args.pool} distinct batches"},
+        "config": workload_config(args, world, infer, sharded, model._shard.item_rows if sharded else None),
+        "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 if not infer else 4 * args.batch},
         "gpu_launches": int(getattr(engine, "kernels_per_step", 0) * args.steps) if engine is not None else int(launches),
         "clocks": clk.summary(),
         "clocks_e2e": clk2.summary(),
     }
+    if world == 1 and not infer and not sharded and engine is not None and args.batch != 4096 and not args.no_config1:
+        # second block: the same step at the reference's own batch_size (config/fibinet_config.yaml: 4096 = BASELINE config 1)
+        a1 = argparse.Namespace(**vars(args))
+        a1.batch = 4096
+        pool1 = make_pool(a1, rank, args.pool)
+        dev1 = [({k: v.to(dev) for k, v in b.items()}, y.to(dev)) for b, y in pool1]
+        eng1 = TrainStep(model, opt, 4096, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0, use_mm_table=args.resident_mm)
+        n1 = max(4 * args.steps, 40)
+
+        def res1(k):
+            eng1(*dev1[k % len(dev1)])
+            sched.step()
+
+        def e2e1(k):
+            if not eng1._prefetched:
+                eng1.prefetch(*pool1[k % len(pool1)])
+            loss = eng1()
+            sched.step()
+            eng1.prefetch(*pool1[(k + 1) % len(pool1)])
+            return loss.item()
+        for k in range(max(args.warmup, 3)):
+            res1(k)
+        ms1 = timed(res1, n1)
+        for k in range(3):
+            e2e1(k)
+        ms1e = timed(e2e1, n1)
+        out["config1"] = {"config": workload_config(a1, world), "value": 4096 * n1 / (ms1 / 1e3), "unit": UNIT, "steps": n1,
+                          "ms_per_step": ms1 / n1, "gpu_launches_per_step": int(eng1.kernels_per_step),
+                          "e2e": {"value": 4096 * n1 / (ms1e / 1e3), "unit": UNIT, "ms_per_step": ms1e / n1,
+                                  "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pool1[0][0].values()) + 4096 * 4,
+                                  "d2h_bytes_per_step": 4}}
     if rank == 0:
         out.update(kernels)
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args, steps=3, warmup=1)
+            out["cpu_baseline"] = cpu_baseline(args, steps=4, warmup=1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -385,31 +408,104 @@ def kernel_rooflines(args, model, dev_batch, peaks, lib):
     tstage("mlp1_wgrad_gemm", "mlp1_wgrad", gemm_flops)       # includes the fixed-order split-K reduction
     out["mlp1_gemm"] = out["mlp1_fwd_gemm"]
     passes = {"tf32x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+    # the kernel with the largest share of the step (ncu launch list, profiles/): the MLP-1 data-gradient GEMM
+    dom = max(("mlp1_dgrad_gemm", "mlp1_fwd_gemm", "mlp1_wgrad_gemm"), key=lambda k: out[k]["ms"])
+    g = out[dom]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            traffic = json.load(fh).get(f"mlp1_fwd_gemm/{args.precision}/b{B}")
-    g = out["mlp1_fwd_gemm"]
-    roof = {"bound": "tensor", "kernel": "gemm_tc (MLP-1 forward, B x 512 x 1920 live K)", "achieved": g["TFLOPs"], "peak": peaks["tf"],
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if traffic is None and os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(f"{dom}/{args.precision}/b{B}")
+    shapes = {"mlp1_fwd_gemm": "forward, H1[B,512] = C[B,1920 live of 2688] x W1^T", "mlp1_dgrad_gemm": "data gradient, dC[B,1920 live] = dH1[B,512] x W1",
+              "mlp1_wgrad_gemm": "weight gradient, dW1[512,1920 live] = dH1^T x C, split-K + fixed-order reduce"}
+    # gather: SURVEY 8(d) counts 5,304 + 512 * n_valid bytes per sample; the wider count adds what the kernel also writes for
+    # backward (X5 / xhat / ids / gates: 3,120 B per sample)
+    g8d = B * 5304 + nvalid * 512
+    gk = out["gather_senet_fwd"]
+    gk["bytes_8d"] = g8d
+    gk["GBps_8d"] = g8d / gk["ms"] / 1e6
+    gk["frac_8d"] = gk["GBps_8d"] / peaks["hbm"]
+    roof = {"bound": "tensor", "kernel": f"gemm_tc2 (MLP-1 {shapes[dom]})", "achieved": g["TFLOPs"], "peak": peaks["tf"],
             "unit": "TFLOP/s", "frac": g["frac_of_bf16_peak"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 dense (burst)",
-            "note": f"algorithmic FLOPs 2*B*1920*512; precision {args.precision} issues {passes}x these on the tensor pipe "
-                    "(kind::tf32 dense peak is half the bf16 figure used as denominator)",
-            "hbm_kernels": {k: {"achieved_GBps": out[k]["GBps"], "frac": out[k]["frac"]} for k in ("adam_table", "gather_senet_fwd")}}
+            "note": f"dominant kernel of the step; algorithmic FLOPs 2*B*1920*512 (structural-zero blocks not counted); precision "
+                    f"{args.precision} issues {passes}x these on the tensor pipe and kind::tf32 runs at half the bf16 rate used as "
+                    "denominator, so 1/6 = 0.167 is this scheme's ceiling (tools/split_precision_sim.py: cheaper operand splits miss the "
+                    "1e-5 gradient tolerance)",
+            "all_mlp1_gemms": {k: {"ms": out[k]["ms"], "TFLOPs": out[k]["TFLOPs"], "frac": out[k]["frac_of_bf16_peak"]}
+                               for k in ("mlp1_fwd_gemm", "mlp1_dgrad_gemm", "mlp1_wgrad_gemm")},
+            "hbm_kernels": {"adam_table": {"achieved_GBps": out["adam_table"]["GBps"], "frac": out["adam_table"]["frac"]},
+                            "gather_senet_fwd": {"achieved_GBps_8d_bytes": gk["GBps_8d"], "frac_8d_bytes": gk["frac_8d"],
+                                                 "achieved_GBps_incl_saved": gk["GBps"], "frac_incl_saved": gk["frac"]}}}
     return {"roofline": roof, "kernels": out}
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_config(args, world, infer=False, sharded=False, item_rows=None):
+    """The `config` object of the JSON line: names the workload only, so the reference arm carries the identical object."""
+    bil = "bilinear all" if args.bilinear == "all" else f"bilinear {args.bilinear} [not the reference's hard-coded 'all']"
+    where = {65536: "largest point of BASELINE config 2's 1K-64K batch sweep",
+             4096: "the reference's batch_size in config/fibinet_config.yaml, BASELINE config 1"}.get(
+                 args.batch, "a point of BASELINE config 2's 1K-64K batch sweep")
+    workload = (f"FiBiNET {'train step' if not infer else 'eval forward'} (config/fibinet_config.yaml model: D=128, 6 fields, {bil}, "
+                f"MLP 2688-512-256-1), per-GPU batch {args.batch} ({where}), history L={L_HIST}, "
+                f"item ids {args.id_dist}, " +
+                (f"item table of {item_rows} rows row-sharded over {world} ranks (remote gather over NVLink, owner-side "
+                 f"gradient merge, {'lazy row' if args.lazy else 'dense-exact'} Adam)" if sharded else "replicated tables"))
+    return {"workload": workload, "global_batch": args.batch * world, "per_gpu_batch": args.batch,
+            "parallelism": f"dp{world}" + ("+row-sharded item table" if sharded else ""),
+            "l2": "working set per step (table p/m/v/grad 188 MB + activations) exceeds the 126 MB L2; inputs cycle over "
+                  f"{args.pool} distinct batches"}
+
+
+class ReferenceStep:
+    """The reference's own train step on the host CPU.  kind = "reference": the UNMODIFIED src/model_fibinet.py vendored into
+    oracle/_ref/ by oracle/make_ref.py (run by build() in the dev container), driven by the loop body of
+    src/train_fibinet.py:113-122 (zero_grad, forward, BCELoss, backward, clip_grad_norm_(10), Adam.step, OneCycleLR.step,
+    loss.item()).  kind = "port" (oracle/_ref absent): oracle/fibinet_torch_port.py, the same ATen op stream."""
+
+    def __init__(self, lr=1e-3, weight_decay=1e-5, total_steps=1000):
+        import importlib.util
+        from oracle import make_ref, synth
+        W = synth.make_weights(seed=7)
+        rd = make_ref.ref_dir()
+        if rd is not None:
+            spec = importlib.util.spec_from_file_location("_reference_model_fibinet", os.path.join(rd, "model_fibinet.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            self.kind = "reference"
+            self.model = mod.build_model(None, {"embedding_dim": 128})
+            self.model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in W.items()}, strict=True)
+            self.model.train()
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)          # ref :78
+            self.loss_fn = torch.nn.BCELoss()                                                              # ref :79
+            self.sched = torch.optim.lr_scheduler.OneCycleLR(self.opt, max_lr=lr * 10, total_steps=total_steps, pct_start=0.3,
+                                                             div_factor=25.0, final_div_factor=1000.0)      # ref :84-92
+        else:
+            from oracle import fibinet_torch_port as port
+            self.kind = "port"
+            self.tr = port.Trainer(port.tensors_from_numpy(W), lr=lr, weight_decay=weight_decay)
+
+    def step(self, batch, labels):
+        if self.kind == "port":
+            return self.tr.step(batch, labels)
+        self.opt.zero_grad()                                                            # ref :113
+        y = self.model(dict(batch))
+        loss = self.loss_fn(y, labels)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=10.0)          # ref :119
+        self.opt.step()
+        self.sched.step()
+        return loss.item()                                                              # ref :124
+
+
 def cpu_baseline(args, steps, warmup):
-    """The reference's CPU train step (oracle/fibinet_torch_port.py: same ATen op stream), all host cores,
-    on a bounded sample of the workload."""
-    from oracle import fibinet_torch_port as port
+    """The reference's CPU train step on all host cores, on a bounded number of steps of the SAME per-GPU batch."""
     from oracle import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = min(args.cpu_sample, args.batch)
-    W = synth.make_weights(seed=7)
-    tr = port.Trainer(port.tensors_from_numpy(W), lr=1e-3, weight_decay=1e-5)
+    B = args.batch if args.cpu_sample <= 0 else min(args.cpu_sample, args.batch)
+    ref = ReferenceStep(total_steps=steps + warmup + 8)
     table = synth.make_item_mm_table(seed=11)
     batches = []
     for i in range(2):
@@ -417,28 +513,28 @@ def cpu_baseline(args, steps, warmup):
         b.pop("user_id")
         batches.append(({k: torch.from_numpy(v) for k, v in b.items()}, torch.from_numpy(y)))
     for k in range(warmup):
-        tr.step(*batches[k % 2])
+        ref.step(*batches[k % 2])
     t0 = time.perf_counter()
     for k in range(steps):
-        tr.step(*batches[k % 2])
+        ref.step(*batches[k % 2])
     dt = time.perf_counter() - t0
-    return {"value": B * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} train steps of {B} rows (of the {args.batch}-row workload batch), torch {torch.__version__} CPU fp32, "
+    what = ("the unmodified reference src/model_fibinet.py (oracle/_ref) + the loop body of src/train_fibinet.py:113-122"
+            if ref.kind == "reference" else "oracle/fibinet_torch_port.py (oracle/_ref absent)")
+    return {"value": B * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
+            "sample": f"{steps} train steps of {B} rows (the per-GPU batch is {args.batch}), {what}, torch {torch.__version__} CPU fp32, "
                       f"{cores} host cores", "ms_per_step": dt / steps * 1e3}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU path on the same config / metric, rank 0 only (the other ranks exit 0)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warmup = max(1, min(args.warmup, 2))
-    cb = cpu_baseline(args, steps=steps, warmup=warmup)
-    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-           "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    cb = cpu_baseline(args, steps=args.steps, warmup=args.warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"FiBiNET train step, reference op stream on host CPU, {min(args.cpu_sample, args.batch)}-row sample of the "
-                                  f"per-GPU batch {args.batch} workload", "parallelism": "cpu"},
+           "config": workload_config(args, args.gpus),
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
