@@ -98,7 +98,7 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   w.dy = (float*)take(Bp * D * f);
   w.sestat = (float*)take(Bp * 24 * f);
   size_t pf = 0;
-  pf = std::max<size_t>(pf, (size_t)8 * H1 * K1);   // up to 8-way split-K of the MLP-1 weight gradient
+  pf = std::max<size_t>(pf, (size_t)12 * H1 * K1);  // up to 12-way split-K of the MLP-1 weight gradient
   pf = std::max<size_t>(pf, (size_t)pick_splits(2 * 4, Bp) * H2 * H1);
   pf = std::max<size_t>(pf, (size_t)10 * 32 * D * D);
   pf = std::max<size_t>(pf, (size_t)2 * 148 * 4 * MAX_CATE * D);
@@ -426,16 +426,18 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
 // split-K factor for a weight gradient on the tcgen05 path: with CTA-pair tiles the CTA count is 2 * clusters * splits;
 // choose the split that wastes the least of the last wave of 148 SMs
 static int pick_splits_pair(long long M, long long N, long long K, unsigned long long nmask, size_t max_floats) {
-  long long clusters = 0;
-  for (long long n0 = 0; n0 < N; n0 += 256)
-    if (nmask == ~0ull || ((nmask >> (n0 / 128)) & 3ull)) clusters += cdiv(M, 256);
+  // tiles of the persistent CTA-pair kernel: 256 rows x 2 LIVE 128-column blocks, walked by num_sms / 2 clusters
+  long long nlive = 0;
+  for (long long n0 = 0; n0 < N; n0 += 128)
+    if (nmask == ~0ull || ((nmask >> (n0 / 128)) & 1ull)) ++nlive;
+  const long long clusters = cdiv(M, 256) * cdiv(nlive, 2);
   const long long kblocks = std::max<long long>(1, cdiv(K, 32));
+  const long long slots = std::max(1, num_sms() / 2);
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= 32; ++s) {
     if ((size_t)s * M * N > max_floats || cdiv(kblocks, s) < 4) break;
-    const long long ctas = 2 * clusters * s;
-    const double cost = (double)cdiv(ctas, 148) / s + 0.002 * s;   // waves per unit of K work (+ a little for the reduce)
+    const double cost = (double)cdiv(clusters * s, slots) / s + 0.002 * s;   // waves per unit of K work (+ a little for the reduce)
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
@@ -796,12 +798,13 @@ extern "C" int fbn_time_gemm(const float* A, const float* Bm, float* C, int64_t 
   return FBN_OK;
 }
 
-namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); }
+namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); }
 
 // runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles
 extern "C" int fbn_set_option(const char* name, int value) {
   FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
+  if (strcmp(name, "tc_pair_persistent") == 0) { fbn::set_tc_pair_persistent(value); return FBN_OK; }
   if (strcmp(name, "side_streams") == 0) { g_use_side = value; return FBN_OK; }
   if (strcmp(name, "tc_persistent") == 0) { fbn::set_tc_persistent(value); return FBN_OK; }
   if (strcmp(name, "stage_events") == 0) { set_stage_events(value); return FBN_OK; }

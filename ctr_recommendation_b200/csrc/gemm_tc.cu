@@ -814,6 +814,265 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent CTA-pair kernel: 74 clusters of 2 CTAs (one CTA per SM) walk the tile list
+//   t = cluster, cluster + #clusters, ...  over  (M tile of 256) x (split) x (N tile of 2 live 128-column blocks), N fastest,
+// so that (i) barriers / TMEM / tensor maps are set up once per SM instead of once per tile, (ii) the TMA producer and the MMA
+// issuer run ahead into tile i+1 while the epilogue warps fold and store tile i (with K = 512 the non-overlapped prologue +
+// epilogue of the one-tile-per-cluster kernel cost ~1/3 of the tile: 65 % tensor activity in the MLP-1 data gradient),
+// (iii) clusters that run at the same time work on the same A rows (the two N tiles of an M block are adjacent in the order, so
+// the second one finds A in L2: the one-tile kernel re-read the whole packed A from DRAM once per N tile), and (iv) the N tiles
+// are built from the LIVE 128-column blocks only: each CTA of a pair stages its own 128-column half of the B tile, so any two
+// live blocks can share a tile -- the 15 live blocks of the MLP input (of 21) fill 8 tiles instead of the 9 (3 of them half dead)
+// that a regular 256-column grid needs.
+// The epilogue stages through a DEDICATED 4 KB per warp (32 rows x 32 floats, XOR-swizzled) because the pipeline stages
+// are already being refilled for the next tile.
+// ------------------------------------------------------------------------------------------------
+struct Tc2pArgs {
+  TcArgs g;
+  long long ntiles;
+  int nNt;                  // N tiles = ceil(nlive / 2)
+  int nlive;                // live 128-column blocks
+  unsigned char nb[64];     // their block indices
+};
+
+constexpr int EPI2_WARP_FLOATS = 32 * 32;
+
+__device__ __forceinline__ void epilogue_store_sw(const float (&acc)[128], float* stage, int lane, long long row0, long long M,
+                                                  float* cbase, long long ldc, const float* bias, int accumulate) {
+  const int rr = lane >> 3, cc = lane & 7;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4)
+      *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+          make_float4(acc[q4 * 32 + c4 * 4], acc[q4 * 32 + c4 * 4 + 1], acc[q4 * 32 + c4 * 4 + 2], acc[q4 * 32 + c4 * 4 + 3]);
+    __syncwarp();
+    const float4 bv = bias ? ld4(bias + q4 * 32 + cc * 4) : f4(0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + rr;
+      if (row0 + r < M) {
+        float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((cc ^ (r & 7)) << 2)) + bv;
+        float* cp = cbase + (long long)r * ldc + q4 * 32 + cc * 4;
+        if (accumulate) o += *reinterpret_cast<const float4*>(cp);
+        st4(cp, o);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+struct Tile2 { int m0, sp, nbA, nbB, kb0, kb1, nact; bool hasB; };
+
+template <int MODE>
+__device__ __forceinline__ Tile2 tile2_info(const Tc2pArgs& p, long long t, int kblocks, int per) {
+  using Cfg = TcCfg<MODE>;
+  Tile2 ti;
+  const int x = (int)(t % p.nNt);
+  const long long r = t / p.nNt;
+  ti.sp = (int)(r % p.g.splits);
+  ti.m0 = (int)(r / p.g.splits) * 256;
+  ti.nbA = p.nb[2 * x];
+  ti.hasB = 2 * x + 1 < p.nlive;
+  ti.nbB = ti.hasB ? p.nb[2 * x + 1] : p.nb[2 * x];      // dead second half: stage the first block again, never stored
+  ti.kb0 = ti.sp * per; ti.kb1 = min(kblocks, ti.kb0 + per);
+  int nact = 0;
+  for (int kb = ti.kb0; kb < ti.kb1; ++kb)
+    nact += (p.g.kmask == ~0ull || ((p.g.kmask >> ((kb * Cfg::BK) / 128)) & 1ull)) ? 1 : 0;
+  ti.nact = nact;
+  return ti;
+}
+
+template <int MODE>
+struct Tc2pCfg {
+  static constexpr int STAGES = TcCfg<MODE>::STAGES;
+  static constexpr int STAGE_BYTES = TcCfg<MODE>::STAGE_BYTES;
+  static constexpr int EPI_BYTES = 8 * EPI2_WARP_FLOATS * 4;        // 32 KB
+  static constexpr int NBAR = 2 * STAGES + 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
+
+template <int MODE, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+    gemm_tc2p_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ Tc2pArgs p) {
+  using Cfg = TcCfg<MODE>;
+  using PC = Tc2pCfg<MODE>;
+  const TcArgs& g = p.g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi = smem + PC::STAGES * PC::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + PC::EPI_BYTES);
+  uint64_t* full = bars;                            // leader: TMA bytes of BOTH CTAs
+  uint64_t* empty = bars + PC::STAGES;              // per CTA: stage free (multicast commit)
+  uint64_t* tfull = bars + 2 * PC::STAGES;          // per CTA [2]: accumulator chunk complete (multicast commit)
+  uint64_t* tempty = bars + 2 * PC::STAGES + 2;     // leader [2]: both CTAs' epilogues drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + PC::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int kblocks = (int)((g.K + Cfg::BK - 1) / Cfg::BK);
+  const int per = (kblocks + g.splits - 1) / g.splits;
+  auto active = [&](int kb) { return g.kmask == ~0ull || ((g.kmask >> ((kb * Cfg::BK) / 128)) & 1ull); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PC::STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 2 * 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < Cfg::NPART; ++q) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.a[q])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.b[q])) : "memory");
+      }
+      int it = 0;
+      for (long long t = cid; t < p.ntiles; t += ncl) {
+        const Tile2 ti = tile2_info<MODE>(p, t, kblocks, per);
+        const int m0 = ti.m0 + (int)rank * 128;                       // this CTA's 128 rows of the 256-row tile
+        const int nb = (rank == 0 ? ti.nbA : ti.nbB) * 128;           // and its 128-column half of the B tile
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+          if (!active(kb)) continue;
+          const int s = it % PC::STAGES;
+          const uint32_t ph = (it / PC::STAGES) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          const uint32_t lbar = mapa_u32(smem_u32(full + s), 0);
+          if (rank == 0) mbar_expect_tx(full + s, 2 * PC::STAGE_BYTES);
+          uint8_t* st = smem + s * PC::STAGE_BYTES;
+          const int kc = kb * Cfg::BK;
+#pragma unroll
+          for (int q = 0; q < Cfg::NPART; ++q) {
+            uint8_t* sa = st + q * Cfg::TILE_BYTES;
+            uint8_t* sb = st + (Cfg::NPART + q) * Cfg::TILE_BYTES;
+            if (!A_MN) {
+              tma_load_2d_pair(sa, &tm.a[q], lbar, kc, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < TC_BM / Cfg::EPB; ++j) tma_load_2d_pair(sa + j * Cfg::BOX_MN_BYTES, &tm.a[q], lbar, m0 + j * Cfg::EPB, kc);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(sb, &tm.b[q], lbar, kc, nb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 128 / Cfg::EPB; ++j) tma_load_2d_pair(sb + j * Cfg::BOX_MN_BYTES, &tm.b[q], lbar, nb + j * Cfg::EPB, kc);
+            }
+          }
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Cfg::FMT, 256, TC2_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint64_t adv_a = A_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint64_t adv_b = B_MN ? (uint64_t)(Cfg::UK * 128) >> 4 : (uint64_t)(Cfg::UK * Cfg::ESZ) >> 4;
+      constexpr uint32_t lbo_a = A_MN ? Cfg::BOX_MN_BYTES : 16, lbo_b = B_MN ? Cfg::BOX_MN_BYTES : 16;
+      constexpr bool base32 = is32(MODE);
+      constexpr uint32_t sbo_a = (A_MN && base32) ? 512 : 1024, sbo_b = (B_MN && base32) ? 512 : 1024;
+      constexpr uint32_t lay_a = (A_MN && base32) ? 1 : 2, lay_b = (B_MN && base32) ? 1 : 2;
+      int it = 0, chunk = 0;
+      for (long long t = cid; t < p.ntiles; t += ncl) {
+        const Tile2 ti = tile2_info<MODE>(p, t, kblocks, per);
+        if (ti.nact == 0) continue;
+        int done = 0;
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+          if (!active(kb)) continue;
+          const int s = it % PC::STAGES;
+          const uint32_t ph = (it / PC::STAGES) & 1;
+          const int buf = chunk & 1, pos = done % Cfg::CHUNK;
+          if (pos == 0) {
+            mbar_wait(tempty + buf, ((chunk >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(buf * TC2_BN);
+          const uint32_t sa = smem_u32(smem + s * PC::STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa, lbo_a, sbo_a, lay_a);
+          const uint64_t b_hi = make_desc(sa + Cfg::NPART * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+            const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+            if (Cfg::NPART == 2) {
+              const uint64_t a_lo = make_desc(sa + Cfg::TILE_BYTES, lbo_a, sbo_a, lay_a);
+              const uint64_t b_lo = make_desc(sa + 3 * Cfg::TILE_BYTES, lbo_b, sbo_b, lay_b);
+              umma_pair<MODE>(tacc, a_lo + k * adv_a, b_hi + k * adv_b, idesc, acc);      // small terms first
+              umma_pair<MODE>(tacc, a_hi + k * adv_a, b_lo + k * adv_b, idesc, 1u);
+              umma_pair<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, 1u);
+            } else {
+              umma_pair<MODE>(tacc, a_hi + k * adv_a, b_hi + k * adv_b, idesc, acc);
+            }
+          }
+          tc_commit_pair(empty + s);
+          ++done;
+          ++it;
+          if (pos == Cfg::CHUNK - 1 || done == ti.nact) {
+            tc_commit_pair(tfull + buf);
+            ++chunk;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(epi) + (warp - 2) * EPI2_WARP_FLOATS;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(tempty), 0);
+    int chunk = 0;
+    for (long long t = cid; t < p.ntiles; t += ncl) {
+      const Tile2 ti = tile2_info<MODE>(p, t, kblocks, per);
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      const int nchunks = (ti.nact + Cfg::CHUNK - 1) / Cfg::CHUNK;
+      for (int c = 0; c < nchunks; ++c, ++chunk) {
+        const int buf = chunk & 1;
+        mbar_wait(tfull + buf, (chunk >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC2_BN + half * 128 + c0), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(tempty_leader0 + (uint32_t)(buf * 8));
+      }
+      if (half == 0 || ti.hasB) {
+        const int ncol0 = (half == 0 ? ti.nbA : ti.nbB) * 128;
+        if (ncol0 < g.N) {
+          const long long row0 = (long long)ti.m0 + (long long)rank * 128 + q * 32;
+          float* cbase = g.C + (long long)ti.sp * g.strideSplit + row0 * g.ldc + ncol0;
+          epilogue_store_sw(acc, stage, lane, row0, g.M, cbase, g.ldc, g.bias ? g.bias + ncol0 : nullptr, g.accumulate);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pack kernel: fp32 (rows x cols, ld) -> same layout in operand format, pitch Kp elements
 //   tf32x3: hi at dst, lo at dst + lo_off floats ; bf16: dst (rows x pitch) bf16
 //   colmask: 128-column blocks to convert (structurally-zero blocks of the MLP input are never read)
@@ -1008,8 +1267,32 @@ static int launch_tc2(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream
   return FBN_OK;
 }
 
+template <int MODE, bool A_MN, bool B_MN>
+static int launch_tc2p(const TcMaps& maps, const TcArgs& t, cudaStream_t st) {
+  using PC = Tc2pCfg<MODE>;
+  static bool attr = false;
+  if (!attr) {
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2p_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM));
+    attr = true;
+  }
+  Tc2pArgs p;
+  p.g = t;
+  p.nlive = 0;
+  for (int i = 0; i < (int)(t.N / 128); ++i)
+    if (t.nmask == ~0ull || ((t.nmask >> i) & 1ull)) p.nb[p.nlive++] = (unsigned char)i;
+  if (p.nlive == 0) return FBN_OK;
+  p.nNt = (p.nlive + 1) / 2;
+  p.ntiles = cdiv(t.M, 256) * t.splits * p.nNt;
+  const int clusters = (int)std::min<long long>(p.ntiles, std::max(1, num_sms() / 2));
+  gemm_tc2p_kernel<MODE, A_MN, B_MN><<<2 * clusters, TC2_THREADS, PC::SMEM, st>>>(maps, p);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
 static int g_tc_pair = 1;   // 0: always use the 1-CTA kernel (fbn_set_option("tc_pair", 0))
 void set_tc_pair(int on) { g_tc_pair = on; }
+static int g_tc_pair_persistent = 1;   // 0: one 256 x 256 tile per cluster (fbn_set_option("tc_pair_persistent", 0)), for A/B runs
+void set_tc_pair_persistent(int on) { g_tc_pair_persistent = on; }
 
 template <int MODE>
 static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -1095,6 +1378,14 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     const long long single_tiles = cdiv(g.M, TC_BM) * (g.N / TC_BN);
     const bool persist = MODE == FBN_PREC_BF16 && g.splits == 1 && g.K <= 512 && single_tiles >= 2LL * num_sms();
     if (g_tc_pair && !use_persistent(persist) && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {
+      if (g_tc_pair_persistent && g.N / 128 <= 64) {
+        if (a_mn && b_mn) rc = launch_tc2p<MODE, true, true>(maps, t, st);
+        else if (a_mn) rc = launch_tc2p<MODE, true, false>(maps, t, st);
+        else if (b_mn) rc = launch_tc2p<MODE, false, true>(maps, t, st);
+        else rc = launch_tc2p<MODE, false, false>(maps, t, st);
+        if (rc) return rc;
+        continue;
+      }
       dim3 grid2((unsigned)(2 * cdiv(g.M, 256)), (unsigned)cdiv(g.N, TC2_BN), (unsigned)g.splits);
       if (a_mn && b_mn) rc = launch_tc2<MODE, true, true>(maps, t, grid2, st);
       else if (a_mn) rc = launch_tc2<MODE, true, false>(maps, t, grid2, st);

@@ -50,18 +50,23 @@ def knobs():
     yield lib
     lib.fbn_set_option(b"tc_pair", 1)
     lib.fbn_set_option(b"tc_persistent", 0)
+    lib.fbn_set_option(b"tc_pair_persistent", 1)
 
 
-@pytest.mark.parametrize("pair,persistent", [(1, 0), (0, -1), (0, 1), (1, 1)])
+@pytest.mark.parametrize("pair,persistent,pair_persistent", [(1, 0, 1), (1, 0, 0), (0, -1, 1), (0, 1, 1), (1, 1, 1)])
 @pytest.mark.parametrize("precision,tol", [("tf32x3", 3e-6), ("bf16", 6e-3)])
 @pytest.mark.parametrize("a_t,b_t,M,N,K", [(False, True, 40000, 256, 512), (False, False, 40000, 512, 256), (False, False, 39000, 128, 128),
-                                           (True, False, 512, 384, 5000), (False, True, 300, 512, 2688)])
-def test_tcgen05_kernel_variants(knobs, pair, persistent, precision, tol, a_t, b_t, M, N, K):
-    """Every tcgen05 kernel variant the dispatcher can pick -- CTA pairs, one tile per CTA, the persistent tile loop (forced on /
-    off / chosen by the heuristic at these sizes) -- against an fp64 matmul."""
+                                           (True, False, 512, 384, 5000), (False, True, 300, 512, 2688),
+                                           (False, False, 20001, 2688, 512),      # 21 column blocks: the last pair tile is half dead
+                                           (True, False, 512, 2688, 20000)])
+def test_tcgen05_kernel_variants(knobs, pair, persistent, pair_persistent, precision, tol, a_t, b_t, M, N, K):
+    """Every tcgen05 kernel variant the dispatcher can pick -- CTA pairs (persistent tile loop over 74 clusters, or one tile per
+    cluster), one tile per CTA, the single-CTA persistent tile loop (forced on / off / chosen by the heuristic at these sizes)
+    -- against an fp64 matmul."""
     from ctr_recommendation_b200.functional import gemm
     knobs.fbn_set_option(b"tc_pair", pair)
     knobs.fbn_set_option(b"tc_persistent", persistent)
+    knobs.fbn_set_option(b"tc_pair_persistent", pair_persistent)
     g = torch.Generator(device="cuda").manual_seed(3)
     A = torch.randn(M, K, device="cuda", generator=g)
     Bm = torch.randn(K, N, device="cuda", generator=g)
@@ -84,9 +89,10 @@ def test_model_step_identical_under_kernel_variants(knobs, precision):
     B = 40000
     batch, labels = synth.make_batch(seed=31, batch=B, id_dist="uniform", index_dtype=np.float64, edge_cases=False)
     outs = []
-    for pair, persistent in ((1, 0), (1, -1), (0, 1)):
+    for pair, persistent, pp in ((1, 0, 1), (1, 0, 0), (1, -1, 1), (0, 1, 1)):
         knobs.fbn_set_option(b"tc_pair", pair)
         knobs.fbn_set_option(b"tc_persistent", persistent)
+        knobs.fbn_set_option(b"tc_pair_persistent", pp)
         model = make_model(train=True, precision=precision)
         model.dropout_p = 0.0
         y = model(to_dev(batch))
