@@ -55,6 +55,10 @@ class AdamHyper(C.Structure):
                 ("one_minus_beta1", _f), ("one_minus_beta2", _f), ("decoupled", _i32)]
 
 
+class AdagradHyper(C.Structure):
+    _fields_ = [("lr", _f), ("lr_decay", _f), ("eps", _f), ("weight_decay", _f), ("step", _i32)]
+
+
 _SIGNATURES = {
     "fbn_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "fbn_workspace_offset": (_sz, [_i64, _i64, _i64, C.c_char_p]),
@@ -67,6 +71,8 @@ _SIGNATURES = {
     "fbn_clip_coef": (C.c_int, [_vp, C.c_int, _f, _vp, _vp]),
     "fbn_adam_table": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(AdamHyper), _vp, _vp]),
     "fbn_adam_dense": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(AdamHyper), _vp, _vp]),
+    "fbn_adagrad_table": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(AdagradHyper), _vp, _vp]),
+    "fbn_adagrad_dense": (C.c_int, [_vp, _vp, _vp, _i64, _vp, C.POINTER(AdagradHyper), _vp, _vp]),
     "fbn_onecycle_hyper": (C.c_int, [_vp, C.c_int, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _vp]),
     "fbn_sumsq": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "fbn_sumsq_partial_floats": (_sz, [_i64]),

@@ -124,6 +124,60 @@ __global__ void __launch_bounds__(256) adam_dense_kernel(float* __restrict__ p, 
   }
 }
 
+// ---- Adagrad (north_star (2): "scatter-add of sparse row gradients fused into the Adam/Adagrad row update") -----------------
+// torch.optim.Adagrad, single-tensor path (torch/optim/adagrad.py): grad += wd * p ; clr = lr / (1 + (step - 1) * lr_decay) ;
+// state_sum += grad * grad ; p -= clr * grad / (sqrt(state_sum) + eps).  The reference itself builds Adam (src/train_fibinet.py:78):
+// extension, pinned to torch.optim.Adagrad on CPU (tests/test_oracle_optim.py).  hyper_dev = {clr, -, -, eps, wd, ...}.
+struct AdagradHyper { float clr, eps, wd; };
+
+__device__ __forceinline__ AdagradHyper resolve_adagrad(const AdagradHyper& h, const float* dev) {
+  if (!dev) return h;
+  AdagradHyper r;
+  r.clr = dev[0]; r.eps = dev[3]; r.wd = dev[4];
+  return r;
+}
+
+__device__ __forceinline__ void adagrad1(float& p, float& ssum, float g, const AdagradHyper& h) {
+  g = fmaf(h.wd, p, g);                        // grad.add(param, alpha=weight_decay)  (wd == 0: g unchanged)
+  ssum = fmaf(g, g, ssum);                     // state_sum.addcmul_(grad, grad, value=1)
+  const float std_ = sqrtf(ssum) + h.eps;      // state_sum.sqrt().add_(eps)
+  p = p - h.clr * (g / std_);                  // param.addcdiv_(grad, std, value=-clr)
+}
+
+// Row update over the table: a touched row takes its segment-summed gradient (x clip coefficient); an untouched row has
+// g = wd * p -- with wd == 0 that is the identity (0 / (sqrt(sum) + eps) = 0), so the row is not even read: the update then
+// moves 4 streams x 512 B per TOUCHED row only (the sparse row update), otherwise it is dense-exact like the Adam kernel.
+__global__ void __launch_bounds__(256) adagrad_table_kernel(float* __restrict__ p, float* __restrict__ ssum, const float* __restrict__ grad,
+                                                            const int32_t* __restrict__ touched, long long rows,
+                                                            const float* __restrict__ clip, AdagradHyper hv, const float* __restrict__ hdev) {
+  const AdagradHyper h = resolve_adagrad(hv, hdev);
+  const float coef = clip ? clip[1] : 1.0f;
+  const long long total4 = rows * (D / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i >> 5;
+    const bool hit = touched == nullptr || touched[r] > 0;
+    if (!hit && h.wd == 0.f) continue;
+    const float4 g = hit ? ld4s(grad + i * 4) * coef : f4(0.f);
+    float4 pp = ld4s(p + i * 4), ss = ld4s(ssum + i * 4);
+    adagrad1(pp.x, ss.x, g.x, h); adagrad1(pp.y, ss.y, g.y, h); adagrad1(pp.z, ss.z, g.z, h); adagrad1(pp.w, ss.w, g.w, h);
+    st4(p + i * 4, pp); st4(ssum + i * 4, ss);
+  }
+}
+
+__global__ void __launch_bounds__(256) adagrad_dense_kernel(float* __restrict__ p, float* __restrict__ ssum, const float* __restrict__ grad,
+                                                            long long n, const float* __restrict__ clip, AdagradHyper hv,
+                                                            const float* __restrict__ hdev) {
+  const AdagradHyper h = resolve_adagrad(hv, hdev);
+  const float coef = clip ? clip[1] : 1.0f;
+  const long long total4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g = ld4s(grad + i * 4) * coef;
+    float4 pp = ld4s(p + i * 4), ss = ld4s(ssum + i * 4);
+    adagrad1(pp.x, ss.x, g.x, h); adagrad1(pp.y, ss.y, g.y, h); adagrad1(pp.z, ss.z, g.z, h); adagrad1(pp.w, ss.w, g.w, h);
+    st4(p + i * 4, pp); st4(ssum + i * 4, ss);
+  }
+}
+
 // 1 - beta as torch computes it: in double, from the decimal literal the user wrote.  An fp32 beta is the rounding of such a
 // literal; the shortest decimal that rounds to it (<= 9 digits) recovers the double, e.g. 0.999f -> 0.999 -> 1e-3.
 float one_minus(float beta) {
@@ -138,12 +192,15 @@ float one_minus(float beta) {
 static AdamHyper make_hyper(const fbn_adam_t& a) {
   AdamHyper h;
   h.lr = a.lr; h.beta1 = a.beta1; h.beta2 = a.beta2; h.eps = a.eps; h.wd = a.weight_decay;
-  const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
-  const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
-  h.step_size = (float)((double)a.lr / bc1);
-  h.bc2_sqrt = (float)sqrt(bc2);
   h.omb1 = a.one_minus_beta1 > 0.f ? a.one_minus_beta1 : one_minus(a.beta1);
   h.omb2 = a.one_minus_beta2 > 0.f ? a.one_minus_beta2 : one_minus(a.beta2);
+  // bias corrections 1 - beta^t: the fp32 rounding of beta (0.999f = 0.99900001) would put a 1.3e-5 relative error into
+  // 1 - beta2^t at t = 1 (cancellation), i.e. 6e-6 into every step; 1 - (1 - beta), with 1 - beta as torch evaluates it, does not
+  const double b1 = 1.0 - (double)h.omb1, b2 = 1.0 - (double)h.omb2;
+  const double bc1 = 1.0 - pow(b1, (double)a.step);
+  const double bc2 = 1.0 - pow(b2, (double)a.step);
+  h.step_size = (float)((double)a.lr / bc1);
+  h.bc2_sqrt = (float)sqrt(bc2);
   h.decay_mul = a.decoupled ? (float)(1.0 - (double)a.lr * (double)a.weight_decay) : 0.f;
   return h;
 }
@@ -234,4 +291,37 @@ extern "C" int fbn_sumsq(const float* x, int64_t n, float* partial, float* out, 
   FBN_REQUIRE(x && out && partial, FBN_ERR_ARG, "fbn_sumsq: null pointer");
   FBN_REQUIRE(aligned16(x), FBN_ERR_ALIGN, "fbn_sumsq: unaligned pointer");
   return sumsq(x, n, partial, out, (cudaStream_t)stream);
+}
+
+static AdagradHyper make_adagrad(const fbn_adagrad_t& a) {
+  AdagradHyper h;
+  h.clr = (float)((double)a.lr / (1.0 + (double)(a.step - 1) * (double)a.lr_decay));
+  h.eps = a.eps; h.wd = a.weight_decay;
+  return h;
+}
+
+extern "C" int fbn_adagrad_table(float* p, float* state_sum, const float* grad, const int32_t* row_touched, int64_t rows,
+                                 const float* clip, const fbn_adagrad_t* h, const float* hyper_dev, fbn_stream_t stream) {
+  FBN_REQUIRE(p && state_sum && grad && (h || hyper_dev), FBN_ERR_ARG, "fbn_adagrad_table: null pointer");
+  FBN_REQUIRE(aligned16(p) && aligned16(state_sum) && aligned16(grad), FBN_ERR_ALIGN, "fbn_adagrad_table: unaligned pointer");
+  AdagradHyper hv{};
+  if (h) hv = make_adagrad(*h);
+  const long long total4 = rows * (D / 4);
+  int blocks = (int)std::min<long long>(cdiv(total4, 256), 16LL * num_sms());
+  adagrad_table_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(p, state_sum, grad, row_touched, rows, clip, hv, hyper_dev);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+extern "C" int fbn_adagrad_dense(float* p, float* state_sum, const float* grad, int64_t n, const float* clip, const fbn_adagrad_t* h,
+                                 const float* hyper_dev, fbn_stream_t stream) {
+  FBN_REQUIRE(p && state_sum && grad && (h || hyper_dev), FBN_ERR_ARG, "fbn_adagrad_dense: null pointer");
+  FBN_REQUIRE(n % 4 == 0, FBN_ERR_SHAPE, "fbn_adagrad_dense: n must be a multiple of 4 (pad the flat buffer)");
+  FBN_REQUIRE(aligned16(p) && aligned16(state_sum) && aligned16(grad), FBN_ERR_ALIGN, "fbn_adagrad_dense: unaligned pointer");
+  AdagradHyper hv{};
+  if (h) hv = make_adagrad(*h);
+  int blocks = (int)std::min<long long>(cdiv(n / 4, 256), 16LL * num_sms());
+  adagrad_dense_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(p, state_sum, grad, n, clip, hv, hyper_dev);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
 }

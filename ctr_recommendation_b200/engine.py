@@ -24,7 +24,7 @@ import torch
 from . import _lib
 from . import dist as fdist
 from .model import MM_FiBiNET, D, _IDX_DTYPES
-from .optim import FusedAdam
+from .optim import FusedAdagrad, FusedAdam
 
 
 class _StaticBatch:
@@ -61,8 +61,8 @@ class TrainStep:
     def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
                  seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True,
                  global_batch: int | None = None):
-        if not isinstance(model, MM_FiBiNET) or not isinstance(optimizer, FusedAdam):
-            raise TypeError("TrainStep needs a ctr_recommendation_b200 MM_FiBiNET and its FusedAdam")
+        if not isinstance(model, MM_FiBiNET) or not isinstance(optimizer, (FusedAdam, FusedAdagrad)):
+            raise TypeError("TrainStep needs a ctr_recommendation_b200 MM_FiBiNET and its FusedAdam / FusedAdagrad")
         self.model, self.opt, self.max_norm = model, optimizer, max_norm
         self.lib = _lib.load()
         model._ensure_flat()
@@ -178,12 +178,7 @@ class TrainStep:
         if self.max_norm is not None:
             _lib.check(lib.fbn_clip_coef(_lib.ptr(m._grad_sumsq), 2, float(self.max_norm), _lib.ptr(o._clip), st), "fbn_clip_coef")
             clip = _lib.ptr(o._clip)
-        w = m.item_emb.weight.data
-        _lib.check(lib.fbn_adam_table(_lib.ptr(w), _lib.ptr(o._m_item), _lib.ptr(o._v_item), _lib.ptr(m._item_grad),
-                                      None if m._dense_table_grad else _lib.ptr(m._row_touched), w.shape[0], clip, None,
-                                      _lib.ptr(self.hyper_dev), st), "fbn_adam_table")
-        _lib.check(lib.fbn_adam_dense(_lib.ptr(m._flat), _lib.ptr(o._m_flat), _lib.ptr(o._v_flat), _lib.ptr(m._gflat), m._flat.numel(),
-                                      clip, None, _lib.ptr(self.hyper_dev), st), "fbn_adam_dense")
+        o._launch_update(lib, clip, _lib.ptr(self.hyper_dev), st, m._dense_table_grad)      # Adam / AdamW / Adagrad row + dense update
         self.step_counter += 1
 
     def check_ids(self):
@@ -222,21 +217,12 @@ class TrainStep:
         self.kernels_per_step = int(self.lib.fbn_launch_count() - n0)   # library kernels inside the captured step
 
     def _write_hyper(self):
-        g = self.opt.param_groups[0]
-        self.opt._step += 1
-        t = self.opt._step
-        lr, b1, b2 = float(g["lr"]), float(g["betas"][0]), float(g["betas"][1])
         slot = self._hyper_pos % self.HYPER_SLOTS
         self._hyper_pos += 1
         if self._hyper_ev[slot] is not None:
             self._hyper_ev[slot].synchronize()      # the copy that last read this slot has executed
         h = self._hyper_ring[slot]
-        h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, float(g["eps"]), float(g["weight_decay"])
-        h[5] = lr / (1.0 - b1 ** t)
-        h[6] = math.sqrt(1.0 - b2 ** t)
-        h[7] = float(t)
-        h[8], h[9] = 1.0 - b1, 1.0 - b2          # evaluated in double like torch, rounded to fp32 by the store
-        h[10] = (1.0 - lr * float(g["weight_decay"])) if self.opt.decoupled else 0.0     # AdamW decay multiplier
+        self.opt._fill_hyper(h)                     # advances the optimizer's step count
         self.hyper_dev.copy_(h, non_blocking=True)
         ev = self._hyper_ev[slot] or torch.cuda.Event()
         ev.record()
@@ -330,6 +316,8 @@ class ShardedTrainStep(TrainStep):
                  lazy: bool = False, merge_cap: int | None = None, global_batch: int | None = None):
         if model._shard is None:
             raise TypeError("ShardedTrainStep needs a model built with table_sharding='row'")
+        if not isinstance(optimizer, FusedAdam):
+            raise TypeError("the row-sharded table is updated by (lazy or dense-exact) Adam: pass a FusedAdam")
         self.lazy = bool(lazy)
         self._merge_cap = merge_cap
         super().__init__(model, optimizer, batch_size, seq_len, idx_dtype, seq_dtype, max_norm, use_mm_table, graph, global_batch)

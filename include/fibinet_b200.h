@@ -205,6 +205,18 @@ int fbn_adam_table(float* p, float* m, float* v, const float* grad, const int32_
 int fbn_adam_dense(float* p, float* m, float* v, const float* grad, int64_t n, const float* clip,
                    const fbn_adam_t* h, const float* hyper_dev, fbn_stream_t stream);
 
+/* Adagrad row update (BASELINE north_star (2): the sorted-segment sums of fbn_backward "fused into the Adam/Adagrad row update").
+ * Replaces the optimizer site src/train_fibinet.py:78 when the user asks for Adagrad; the reference itself builds Adam, so this is
+ * an extension whose oracle is torch.optim.Adagrad (single-tensor path of torch/optim/adagrad.py):
+ *   g = grad * coef + wd * p ; clr = lr / (1 + (step - 1) * lr_decay) ; state_sum += g * g ; p -= clr * g / (sqrt(state_sum) + eps).
+ * step is the 1-based step count.  hyper_dev (CUDA-graph replay): the same 12-float device array as Adam with
+ * [0] = clr, [3] = eps, [4] = wd.  With wd == 0 an untouched row is the identity and is neither read nor written. */
+typedef struct { float lr, lr_decay, eps, weight_decay; int32_t step; } fbn_adagrad_t;
+int fbn_adagrad_table(float* p, float* state_sum, const float* grad, const int32_t* row_touched, int64_t rows,
+                      const float* clip, const fbn_adagrad_t* h, const float* hyper_dev, fbn_stream_t stream);
+int fbn_adagrad_dense(float* p, float* state_sum, const float* grad, int64_t n, const float* clip,
+                      const fbn_adagrad_t* h, const float* hyper_dev, fbn_stream_t stream);
+
 /* OneCycleLR(cos, two phases, cycle_momentum=True) as built at src/train_fibinet.py:84-92, evaluated on
  * the device: reads *step_counter (optimizer steps taken so far), writes hyper_dev[0..7] for the next
  * step and increments the counter. */

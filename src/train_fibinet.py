@@ -20,7 +20,7 @@ from dataloader import MMCTRDataLoader  # noqa: E402
 from model_fibinet import build_model  # noqa: E402
 from utils import compute_auc, set_seed  # noqa: E402
 
-from ctr_recommendation_b200 import FusedAdam  # noqa: E402
+from ctr_recommendation_b200 import FusedAdagrad, FusedAdam  # noqa: E402
 from ctr_recommendation_b200 import dist as fdist  # noqa: E402
 from ctr_recommendation_b200 import sharded  # noqa: E402
 from ctr_recommendation_b200.engine import Scorer, ShardedTrainStep, TrainStep  # noqa: E402
@@ -108,10 +108,14 @@ def main():
     # torch.optim.Adam semantics (L2-coupled) like the reference, which ignores `optimizer: adamw`; with honor_config: true
     # the key is honoured (decoupled weight decay)
     adamw = bool(model_cfg.get("honor_config", False)) and str(model_cfg.get("optimizer", "adam")).lower() == "adamw"
-    optimizer = FusedAdam(model, lr=lr, weight_decay=weight_decay, decoupled_weight_decay=adamw)
+    if bool(model_cfg.get("honor_config", False)) and str(model_cfg.get("optimizer", "adam")).lower() == "adagrad":
+        optimizer = FusedAdagrad(model, lr=lr, weight_decay=weight_decay)     # extension: Adagrad row update (north_star (2))
+    else:
+        optimizer = FusedAdam(model, lr=lr, weight_decay=weight_decay, decoupled_weight_decay=adamw)
     steps_per_epoch = len(train_loader)
     scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=lr * 10, epochs=epochs, steps_per_epoch=steps_per_epoch,
-                                                    pct_start=0.3, div_factor=25.0, final_div_factor=1000.0)
+                                                    pct_start=0.3, div_factor=25.0, final_div_factor=1000.0,
+                                                    cycle_momentum="betas" in optimizer.defaults)    # Adagrad has no beta1 to cycle
     engines = {}
 
     def train_engine(rows, L, dtype, n_global):

@@ -126,3 +126,58 @@ def test_global_batch_loss_weight(gpu):
         grads.append(model._gflat.clone())
     ratio = (grads[1].double().norm() / grads[0].double().norm()).item()
     assert abs(ratio - 200 / 500) <= 1e-5
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-5])
+@pytest.mark.parametrize("engine", [False, True])
+def test_fused_adagrad_vs_oracle(gpu, wd, engine):
+    """FusedAdagrad (module path and TrainStep graph) against the oracle's Adagrad (pinned to torch.optim.Adagrad on CPU) fed the
+    GPU's own gradients: element-wise to fp32 rounding, including untouched table rows (identity for wd == 0, pure decay else)."""
+    from oracle import fibinet_numpy as orc
+    from ctr_recommendation_b200 import FusedAdagrad, clip_grad_norm_
+    from ctr_recommendation_b200.engine import TrainStep
+    from gpu_common import named_grads
+    B, lr = 300, 1e-2
+    model = gpu["make_model"](train=True, precision="fp32")
+    model.dropout_p = 0.0
+    opt = FusedAdagrad(model, lr=lr, lr_decay=0.01, weight_decay=wd, initial_accumulator_value=0.0)
+    oopt = orc.Adagrad(lr=lr, lr_decay=0.01, weight_decay=wd)
+    eng = TrainStep(model, opt, B, 20, idx_dtype=torch.float64, max_norm=10.0) if engine else None
+    P = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    for s in range(4):
+        batch, labels = synth.make_batch(seed=340 + s, batch=B, id_dist="zipf", index_dtype=np.float64)
+        if eng is not None:
+            eng(_pinned(batch), torch.from_numpy(labels).pin_memory())
+            torch.cuda.synchronize()
+            G = {}
+            names = {id(p): n for n, p in model.named_parameters()}
+            for (field, plist), (off, _) in zip(model._dense_params(), model._layout):
+                o = off
+                for p in plist:
+                    G[names[id(p)]] = model._gflat[o:o + p.numel()].view(p.shape).cpu().numpy().copy()
+                    o += (p.numel() + 3) // 4 * 4
+        else:
+            y = model(gpu["to_dev"](batch))
+            torch.nn.BCELoss()(y, torch.from_numpy(labels).cuda()).backward()
+            G = named_grads(model)
+            clip_grad_norm_(model, 10.0)
+            opt.step()
+        G["item_emb.weight"] = (model._item_grad * (model._row_touched > 0).unsqueeze(1)).cpu().numpy()
+        orc.clip_grad_norm_(G, 10.0)
+        oopt.step(P, G)
+        sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        for k in G:
+            d = np.abs(sd[k].astype(np.float64) - P[k])
+            assert d.max() <= 2e-3 * lr + 1e-7, f"step {s} {k}: {d.max():.3e}"
+        acc = opt.accumulators()
+        for k in G:                                   # continue from the GPU state so errors cannot accumulate
+            P[k] = sd[k].copy()
+            oopt.state[k]["sum"] = acc[k].cpu().numpy().copy()
+    untouched = (model._row_touched == 0).cpu().numpy()
+    untouched[0] = False
+    w0 = synth.make_weights(7)["item_emb.weight"]
+    moved = np.abs(sd["item_emb.weight"] - w0)[untouched]
+    if wd == 0.0:
+        assert (acc["item_emb.weight"].cpu().numpy()[untouched & (np.abs(acc["item_emb.weight"].cpu().numpy()).sum(1) == 0)] == 0).all()
+    assert np.all(sd["item_emb.weight"][0] == 0)
+    assert moved.size > 0

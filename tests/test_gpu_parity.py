@@ -349,9 +349,12 @@ def test_full_batch_forward_backward_vs_oracle(gpu, precision, B, id_dist):
     A1 = model.workspace_view("A1", (B, 512)).cpu().numpy()
     A2 = model.workspace_view("A2", (B, 256)).cpu().numpy()
     got = gpu["named_grads"](model)
+    # fp64 oracle: over 1e4..4e4 samples the fp32 oracle's OWN summation error in the batch reductions (item rows of hot
+    # Zipf ids, SENET / bias gradients) is as large as the tolerance, so the CUDA path is held to 1e-5 of the exact value
+    od = np.float64 if B > 4096 else np.float32
     P = synth.make_weights(seed=7)
-    prob, cache = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False)
-    oloss, _ = orc.bce_loss(prob, labels)
+    prob, cache = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False, dtype=od)
+    oloss, _ = orc.bce_loss(prob, labels, od)
     # ---- forward ----
     assert rel_err(logit, cache["logit"]) <= tol, ("logit", rel_err(logit, cache["logit"]))
     assert rel_err(y.detach().cpu().numpy(), prob) <= tol
@@ -365,8 +368,8 @@ def test_full_batch_forward_backward_vs_oracle(gpu, precision, B, id_dist):
         assert mis.sum() <= max(4, int(4 * tol * Y.size)), ("ReLU decisions differ", int(mis.sum()))
         assert (not mis.any()) or float(np.abs(Y[mis]).max()) <= band, ("ReLU flip outside the band", float(np.abs(Y[mis]).max()))
     # ---- (2) gradients under identical decisions ----
-    prob_g, cache_g = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False, relu_gates=(g1, g2))
-    _, dprob = orc.bce_loss(prob_g, labels)
+    prob_g, cache_g = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False, relu_gates=(g1, g2), dtype=od)
+    _, dprob = orc.bce_loss(prob_g, labels, od)
     G = orc.backward(P, cache_g, dprob)
     assert set(got) == set(G)
     bad = []
