@@ -15,6 +15,7 @@ IDX_I32, IDX_I64, IDX_F64, IDX_F32 = 0, 1, 2, 3
 PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
 BILINEAR_ALL, BILINEAR_EACH, BILINEAR_INTERACTION = 0, 1, 2
 PREC_TF32X2 = 3
+BWD_CHAIN, BWD_LEAF1, BWD_LEAF2 = 1, 2, 4
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}          # what the model path accepts
 GEMM_PRECISIONS = dict(PRECISIONS, tf32x2=PREC_TF32X2)                               # fbn_gemm only (K-major x K-major)
 BILINEAR_TYPES = {"all": BILINEAR_ALL, "field_all": BILINEAR_ALL, "each": BILINEAR_EACH, "field_each": BILINEAR_EACH,
@@ -66,6 +67,8 @@ _SIGNATURES = {
     "fbn_embed_forward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _vp]),
     "fbn_backward": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, C.POINTER(Grads), _vp, _i64,
                                _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "fbn_backward_phase": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, C.c_int, _f, _vp, C.POINTER(Grads), _vp, _vp, C.c_int,
+                                     C.c_int, _vp, C.c_int, _vp]),
     "fbn_embed_index": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, _vp, _vp]),
     "fbn_bce_loss": (C.c_int, [_vp, _vp, _i64, _f, _vp, _vp, _vp]),
     "fbn_clip_coef": (C.c_int, [_vp, C.c_int, _f, _vp, _vp]),

@@ -480,13 +480,22 @@ static int wgrad(const float* dOut, long long ldo, const float* In, long long ld
   return reduce_splits(scratch, g.splits, M, N, M * N, nmask, out, st);
 }
 
-extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
-                            const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat, int64_t dense_grad_n,
-                            float* item_grad, int32_t* row_touched, int zero_fill, int index_ready, float* grad_sumsq,
-                            fbn_stream_t stream) {
+// Backward pass in up to three phases (fbn_backward = all of them, interleaved over two streams):
+//   FBN_BWD_CHAIN : the dependency chain  head -> BN2 -> dgrad2 -> BN1 -> dgrad1 -> bilinear -> SENET / projection -> table rows
+//   FBN_BWD_LEAF1 : mlp.0.weight / mlp.0.bias gradients (89 % of the dense gradient bytes)
+//   FBN_BWD_LEAF2 : every other leaf (mlp.4, bilinear W, cate_emb, SENET, LayerNorm, mm_proj gradients)
+// A data-parallel host runs CHAIN first, starts the all-reduce of the table gradient, runs LEAF1 while it is in flight, starts
+// the all-reduce of that bucket, runs LEAF2 (engine.TrainStep, world > 1): the collectives overlap the weight-gradient GEMMs.
+static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
+                         const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat, int64_t dense_grad_n,
+                         float* item_grad, int32_t* row_touched, int zero_fill, int index_ready, float* grad_sumsq,
+                         fbn_stream_t stream, int phases) {
   RC(check_common(p, b, ws, ws_bytes));
-  FBN_REQUIRE(dprob && g && grad_sumsq, FBN_ERR_ARG, "fbn_backward: null pointer");
-  FBN_REQUIRE(item_grad || p->n_shards > 0, FBN_ERR_ARG, "fbn_backward: item_grad may only be NULL for a row-sharded table");
+  FBN_REQUIRE(g && grad_sumsq, FBN_ERR_ARG, "fbn_backward: null pointer");
+  FBN_REQUIRE(phases > 0 && phases <= 7, FBN_ERR_ARG, "fbn_backward_phase: phases must be a non-empty subset of CHAIN | LEAF1 | LEAF2");
+  const bool all = phases == 7, chain = (phases & FBN_BWD_CHAIN) != 0, leaf1 = (phases & FBN_BWD_LEAF1) != 0, leaf2 = (phases & FBN_BWD_LEAF2) != 0;
+  FBN_REQUIRE(dprob || !chain, FBN_ERR_ARG, "fbn_backward: null dprob");
+  FBN_REQUIRE(item_grad || p->n_shards > 0 || !chain, FBN_ERR_ARG, "fbn_backward: item_grad may only be NULL for a row-sharded table");
   FBN_REQUIRE(!(item_grad && p->n_shards > 0), FBN_ERR_ARG, "fbn_backward: a row-sharded table takes its gradient through fbn_shard_*");
   FBN_REQUIRE(aligned16(item_grad), FBN_ERR_ALIGN, "item_grad is not 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -495,7 +504,10 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
   const long long B = b->batch;
   const int prec = p->precision;
   const float scale = (train && dropout_p > 0.f) ? 1.0f / (1.0f - dropout_p) : 1.0f;
-  // operands packed by fbn_forward are still valid: re-register them (no launch), pack the new ones as they appear
+  // operands packed by fbn_forward (and by an earlier phase) are still valid: re-register them (no launch), pack the new ones
+  // as they appear
+  const int type = p->bilinear_type;
+  const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
   tl_reg = PkReg();
   tl_reg.prec = p->precision; tl_reg.st = st;
   {
@@ -506,71 +518,31 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
     tl_reg.describe(w.C, B, K1, w.pk_C);
     tl_reg.describe(w.A1, B, H1, w.pk_A1);
     tl_reg.describe(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm);
+    if (!chain) {      // produced by the CHAIN phase of an earlier call
+      tl_reg.describe(w.dH2, B, H2, w.pk_dH2);
+      tl_reg.describe(w.dH1, B, H1, w.pk_dH1);
+      tl_reg.describe(w.dT, B, (long long)nT * D, w.pk_dT);
+      tl_reg.describe(w.dy, B, D, w.pk_dy);
+    }
   }
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   const unsigned long long amask = active_mask();
+  // leaves run on the library's side stream when the whole pass is issued at once, else on the caller's stream
+  const bool par = all && side_ready(st);
+  cudaStream_t ls = par ? g_side.s : st;
+  float* lp = par ? w.partial_side : w.partial;
+  const int eb = embed_bwd_blocks(B);
 
-  // ---- head + layer 2 ----
-  STAGE("bwd:start");
-  RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
-                    st));
-  RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
-                   tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
-  STAGE("bwd:head + bn2");
-  const bool par = side_ready(st);
-  cudaStream_t ls = par ? g_side.s : st;          // stream of the leaf computations
-  float* lp = par ? w.partial_side : w.partial;   // and their scratch
-  if (par) RC(side_fork(st, 0));
-  RC(colsum(w.dH2, B, H2, lp, g->b2, ls));
-  RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, ls, lp));
-  {
-    GemmArgs d;  // dA1 = dH2 * w2
-    d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
-    RC(tl_reg.run(d, w));
-  }
-  STAGE("bwd:mlp2 dgrad (+side: wgrad2)");
-  // ---- layer 1 ----
-  RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
-  RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
-                   tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
-  STAGE("bwd:bn1");
-  if (par) RC(side_fork(st, 1));
-  RC(colsum(w.dH1, B, H1, lp, g->b1, ls));
-  RC(wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, ls, lp));
-  {
-    GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
-    d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
-    RC(tl_reg.run(d, w));
-  }
-  STAGE("bwd:mlp1 dgrad (+side: wgrad1)");
-  // ---- bilinear ----
-  const int type = p->bilinear_type;
-  const int nT = type == FBN_BILINEAR_INTERACTION ? 10 : 4;
-  RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, tl_reg.dst(w.dT, B, (long long)nT * D, w.pk_dT), st));
-  STAGE("bwd:bilinear pairs");
-  {
-    GemmArgs d;  // dV[src] += dT_t * W^T
-    d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
-    if (type == FBN_BILINEAR_ALL) {
-      d.A = w.dT; d.strideA = D; d.B = p->bil_w; d.strideB = 0; d.C = w.dV + 1 * D; d.strideC = D; d.batch = 4;
-      RC(tl_reg.run(d, w));
-    } else if (type == FBN_BILINEAR_EACH) {
-      d.A = w.dT; d.strideA = D; d.B = p->bil_w + D * D; d.strideB = D * D; d.C = w.dV; d.strideC = D; d.batch = 4;
-      RC(tl_reg.run(d, w));
-    } else {
-      int q = 0;
-      for (int i = 1; i < NF - 1; ++i)
-        for (int j = i + 1; j < NF; ++j, ++q) {
-          const int pidx = i * (2 * NF - i - 1) / 2 + (j - i - 1);
-          d.A = w.dT + q * D; d.B = p->bil_w + (long long)pidx * D * D; d.C = w.dV + (i - 1) * D; d.batch = 1;
-          RC(tl_reg.run(d, w));
-        }
-    }
-  }
-  STAGE("bwd:bilinear dgrad");
-  {
-    // dW[idx] = sum_t V_src^T dT_t  (split-K over the batch, fixed-order reduction) -- a leaf: side stream
-    if (par) RC(side_fork(st, 2));
+  auto leaf_layer2 = [&]() -> int {
+    RC(colsum(w.dH2, B, H2, lp, g->b2, ls));
+    return wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, w, g->w2, ls, lp);
+  };
+  auto leaf_layer1 = [&]() -> int {
+    RC(colsum(w.dH1, B, H1, lp, g->b1, ls));
+    return wgrad(w.dH1, H1, w.C, K1, B, H1, K1, amask, prec, w, g->w1, ls, lp);
+  };
+  auto leaf_bilinear = [&]() -> int {
+    // dW[idx] = sum_t V_src^T dT_t  (split-K over the batch, fixed-order reduction)
     GemmArgs d;
     d.a_t = 1; d.lda = K1; d.b_t = 0; d.ldb = nT * D; d.M = D; d.N = D; d.K = B; d.ldc = D;
     const int S = pick_splits(nT, B);
@@ -599,39 +571,122 @@ extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* w
         RC(reduce_splits(lp + (long long)t * S * D * D, S, D, D, (long long)D * D, ~0ull,
                          g->bil_w + (long long)(NF - 1 + t) * D * D, ls));
     }
+    return FBN_OK;
+  };
+  auto leaf_embed = [&]() -> int {
+    RC(launch_reduce_partials(w.partial_cate, g->cate_emb, eb, p->cate_rows * D, 0, ls));
+    RC(launch_senet_param_grads(w.sestat, B, lp, g->se_w1, g->se_b1, g->se_w2, g->se_b2, ls));
+    RC(colprod2(w.dln, w.xhat, B, D, lp, g->ln_g, g->ln_b, ls));
+    RC(colsum(w.dy, B, D, lp, g->mm_b, ls));
+    return wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, ls, lp);
+  };
+
+  if (chain) {
+    // ---- head + layer 2 ----
+    STAGE("bwd:start");
+    RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
+                      st));
+    RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
+                     tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
+    STAGE("bwd:head + bn2");
+    if (par) RC(side_fork(st, 0));
+    if (all) RC(leaf_layer2());
+    {
+      GemmArgs d;  // dA1 = dH2 * w2
+      d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
+      RC(tl_reg.run(d, w));
+    }
+    STAGE("bwd:mlp2 dgrad (+side: wgrad2)");
+    // ---- layer 1 ----
+    RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
+    RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
+                     tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
+    STAGE("bwd:bn1");
+    if (par) RC(side_fork(st, 1));
+    if (all) RC(leaf_layer1());
+    {
+      GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
+      d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
+      RC(tl_reg.run(d, w));
+    }
+    STAGE("bwd:mlp1 dgrad (+side: wgrad1)");
+    // ---- bilinear ----
+    RC(bilinear_pairs_bwd(type, w.C, w.T, w.dC, B, w.dT, w.dV, tl_reg.dst(w.dT, B, (long long)nT * D, w.pk_dT), st));
+    STAGE("bwd:bilinear pairs");
+    {
+      GemmArgs d;  // dV[src] += dT_t * W^T
+      d.M = B; d.N = D; d.K = D; d.lda = nT * D; d.ldb = D; d.b_t = 1; d.ldc = NA * D; d.accumulate = 1;
+      if (type == FBN_BILINEAR_ALL) {
+        d.A = w.dT; d.strideA = D; d.B = p->bil_w; d.strideB = 0; d.C = w.dV + 1 * D; d.strideC = D; d.batch = 4;
+        RC(tl_reg.run(d, w));
+      } else if (type == FBN_BILINEAR_EACH) {
+        d.A = w.dT; d.strideA = D; d.B = p->bil_w + D * D; d.strideB = D * D; d.C = w.dV; d.strideC = D; d.batch = 4;
+        RC(tl_reg.run(d, w));
+      } else {
+        int q = 0;
+        for (int i = 1; i < NF - 1; ++i)
+          for (int j = i + 1; j < NF; ++j, ++q) {
+            const int pidx = i * (2 * NF - i - 1) / 2 + (j - i - 1);
+            d.A = w.dT + q * D; d.B = p->bil_w + (long long)pidx * D * D; d.C = w.dV + (i - 1) * D; d.batch = 1;
+            RC(tl_reg.run(d, w));
+          }
+      }
+    }
+    STAGE("bwd:bilinear dgrad");
+    if (par) RC(side_fork(st, 2));
+    if (all) RC(leaf_bilinear());
+    // ---- SENET + field stack + projection ----
+    EmbedBwdArgs e{};
+    e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
+    e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.ln_g = p->ln_g; e.B = B; e.cate_rows = (int)p->cate_rows;
+    e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial_cate;
+    e.pkdy = tl_reg.dst(w.dy, B, D, w.pk_dy);
+    FBN_REQUIRE((size_t)eb * p->cate_rows * D <= (size_t)2 * 148 * 4 * MAX_CATE * D, FBN_ERR_ARG, "internal: cate scratch too small");
+    RC(launch_embed_senet_bwd(e, eb, st));
+    STAGE("bwd:embed+senet");
+    if (par) RC(side_fork(st, 3));
+    if (all) RC(leaf_embed());
+    // ---- embedding table rows ----
+    if (item_grad) {
+      EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
+      eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_out = grad_sumsq + 1;
+      if (!index_ready) RC(emb_index(eg, st));
+      RC(emb_rows(eg, st));
+    }
+    STAGE("bwd:table rows");
+    if (par) RC(side_join(st));     // every dense gradient is complete from here on
+    STAGE("bwd:join side stream (leaf gradients)");
   }
-  // ---- SENET + field stack + projection ----
-  EmbedBwdArgs e{};
-  e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
-  e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.ln_g = p->ln_g; e.B = B; e.cate_rows = (int)p->cate_rows;
-  e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial_cate;
-  e.pkdy = tl_reg.dst(w.dy, B, D, w.pk_dy);
-  const int eb = embed_bwd_blocks(B);
-  FBN_REQUIRE((size_t)eb * p->cate_rows * D <= (size_t)2 * 148 * 4 * MAX_CATE * D, FBN_ERR_ARG, "internal: cate scratch too small");
-  RC(launch_embed_senet_bwd(e, eb, st));
-  STAGE("bwd:embed+senet");
-  if (par) RC(side_fork(st, 3));
-  RC(launch_reduce_partials(w.partial_cate, g->cate_emb, eb, p->cate_rows * D, 0, ls));
-  RC(launch_senet_param_grads(w.sestat, B, lp, g->se_w1, g->se_b1, g->se_w2, g->se_b2, ls));
-  RC(colprod2(w.dln, w.xhat, B, D, lp, g->ln_g, g->ln_b, ls));
-  RC(colsum(w.dy, B, D, lp, g->mm_b, ls));
-  RC(wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, ls, lp));
-  // ---- embedding table rows ----
-  if (item_grad) {
-    EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
-    eg.grad = item_grad; eg.zero_fill = zero_fill; eg.sumsq_out = grad_sumsq + 1;
-    if (!index_ready) RC(emb_index(eg, st));
-    RC(emb_rows(eg, st));
+  if (!all) {
+    if (leaf1) RC(leaf_layer1());
+    if (leaf2) {
+      RC(leaf_layer2());
+      RC(leaf_bilinear());
+      RC(leaf_embed());
+    }
+    return FBN_OK;      // the host computes the gradient norms after its collectives
   }
-  STAGE("bwd:table rows");
-  if (par) RC(side_join(st));     // every dense gradient is complete from here on
-  STAGE("bwd:join side stream (leaf gradients)");
   if (dense_grad_flat) {
     FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");
     RC(sumsq(dense_grad_flat, dense_grad_n, w.partial, grad_sumsq, st));
   }
   STAGE("bwd:dense sumsq");
   return FBN_OK;
+}
+
+extern "C" int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
+                            const float* dprob, const fbn_grads_t* g, const float* dense_grad_flat, int64_t dense_grad_n,
+                            float* item_grad, int32_t* row_touched, int zero_fill, int index_ready, float* grad_sumsq,
+                            fbn_stream_t stream) {
+  return backward_impl(p, b, ws, ws_bytes, train, dropout_p, dprob, g, dense_grad_flat, dense_grad_n, item_grad, row_touched, zero_fill,
+                       index_ready, grad_sumsq, stream, 7);
+}
+
+extern "C" int fbn_backward_phase(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train, float dropout_p,
+                                  const float* dprob, const fbn_grads_t* g, float* item_grad, int32_t* row_touched, int zero_fill,
+                                  int index_ready, float* grad_sumsq, int phases, fbn_stream_t stream) {
+  return backward_impl(p, b, ws, ws_bytes, train, dropout_p, dprob, g, nullptr, 0, item_grad, row_touched, zero_fill, index_ready,
+                       grad_sumsq, stream, phases);
 }
 
 // Per-stage device times of the calls made since the last report (see stage_mark): "name<TAB>ms" lines.  Synchronises.
@@ -798,13 +853,14 @@ extern "C" int fbn_time_gemm(const float* A, const float* Bm, float* C, int64_t 
   return FBN_OK;
 }
 
-namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); }
+namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); void set_tc_reserve_sms(int n); }
 
 // runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles
 extern "C" int fbn_set_option(const char* name, int value) {
   FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
   if (strcmp(name, "tc_pair_persistent") == 0) { fbn::set_tc_pair_persistent(value); return FBN_OK; }
+  if (strcmp(name, "tc_reserve_sms") == 0) { fbn::set_tc_reserve_sms(value); return FBN_OK; }
   if (strcmp(name, "side_streams") == 0) { g_use_side = value; return FBN_OK; }
   if (strcmp(name, "tc_persistent") == 0) { fbn::set_tc_persistent(value); return FBN_OK; }
   if (strcmp(name, "stage_events") == 0) { set_stage_events(value); return FBN_OK; }

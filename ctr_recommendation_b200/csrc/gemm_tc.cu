@@ -1267,6 +1267,9 @@ static int launch_tc2(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream
   return FBN_OK;
 }
 
+static int g_tc_reserve_sms = 0;
+void set_tc_reserve_sms(int n) { g_tc_reserve_sms = std::max(0, std::min(n, 64)); }
+
 template <int MODE, bool A_MN, bool B_MN>
 static int launch_tc2p(const TcMaps& maps, const TcArgs& t, cudaStream_t st) {
   using PC = Tc2pCfg<MODE>;
@@ -1283,7 +1286,9 @@ static int launch_tc2p(const TcMaps& maps, const TcArgs& t, cudaStream_t st) {
   if (p.nlive == 0) return FBN_OK;
   p.nNt = (p.nlive + 1) / 2;
   p.ntiles = cdiv(t.M, 256) * t.splits * p.nNt;
-  const int clusters = (int)std::min<long long>(p.ntiles, std::max(1, num_sms() / 2));
+  // fbn_set_option("tc_reserve_sms", n): leave n SMs to a concurrently running collective (its CTAs cannot share an SM with
+  // a 225 KB-smem GEMM CTA; a persistent grid that oversubscribes the free SMs would wait for the collective to finish)
+  const int clusters = (int)std::min<long long>(p.ntiles, std::max(1, (num_sms() - g_tc_reserve_sms) / 2));
   gemm_tc2p_kernel<MODE, A_MN, B_MN><<<2 * clusters, TC2_THREADS, PC::SMEM, st>>>(maps, p);
   FBN_CHECK_LAUNCH();
   return FBN_OK;

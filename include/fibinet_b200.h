@@ -165,6 +165,18 @@ int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t w
                  int64_t dense_grad_n, float* item_grad, int32_t* row_touched, int zero_fill, int index_ready,
                  float* grad_sumsq, fbn_stream_t stream);
 
+/* fbn_backward in phases, for a data-parallel host that overlaps its gradient collectives with the weight-gradient GEMMs
+ * (replaces the grad reduce of nn.DataParallel, src/train_fibinet.py:69-70; BASELINE north_star (5)):
+ *   FBN_BWD_CHAIN : the data-gradient chain down to the embedding-table rows (item_grad / row_touched / grad_sumsq[1] as above,
+ *                   plus the gradients computed along the chain: mlp.8.*, mlp.5.*, mlp.1.*);
+ *   FBN_BWD_LEAF1 : mlp.0.weight / mlp.0.bias;   FBN_BWD_LEAF2 : every other parameter gradient.
+ * Each call runs the requested phases on `stream` in that order; a later phase may be issued by a later call on the same
+ * workspace (dprob is only read by CHAIN).  phases == CHAIN|LEAF1|LEAF2 is fbn_backward without the dense-gradient norm. */
+enum { FBN_BWD_CHAIN = 1, FBN_BWD_LEAF1 = 2, FBN_BWD_LEAF2 = 4 };
+int fbn_backward_phase(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train,
+                       float dropout_p, const float* dprob, const fbn_grads_t* g, float* item_grad, int32_t* row_touched,
+                       int zero_fill, int index_ready, float* grad_sumsq, int phases, fbn_stream_t stream);
+
 /* The occurrence index fbn_backward needs for the embedding gradient (stable sort of the B + B*L row ids, per-row
  * counts and offsets).  It depends on the batch ids only: run it on a second stream concurrently with fbn_forward and
  * pass index_ready = 1 to fbn_backward (same row_touched pointer), or pass index_ready = 0 and let fbn_backward build it. */
