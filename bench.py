@@ -60,6 +60,8 @@ def parse():
                          "(SURVEY 8f-1): batches then carry ids only (188 instead of 700 bytes / sample over PCIe)")
     ap.add_argument("--int32-ids", action="store_true", help="loader delivers int32 ids / history instead of float64 / int64 (100 B / sample)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
+    ap.add_argument("--no-overlap", action="store_true", help="data parallel: blocking gradient all-reduces between two graphs (A/B against "
+                    "the default schedule that overlaps them with the weight-gradient GEMMs)")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
 
@@ -192,7 +194,8 @@ def run_ours(args):
         sdt = torch.int32 if args.int32_ids else torch.int64
         engine = None if args.eager else (
             Scorer(model, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, use_mm_table=args.resident_mm) if infer else
-            TrainStep(model, opt, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0, use_mm_table=args.resident_mm))
+            TrainStep(model, opt, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0, use_mm_table=args.resident_mm,
+                      overlap=False if args.no_overlap else None))
 
     def step(batch, labels):
         if infer:                    # scoring: forward only, predictions read back by the caller
@@ -292,6 +295,9 @@ def run_ours(args):
         "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": workload_config(args, world, infer, sharded, model._shard.item_rows if sharded else None),
         "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
+        "dp_collectives": (None if world == 1 or sharded else
+                           ("blocking all-reduces" if not getattr(engine, "overlap", False) else
+                            "3 async all-reduces (table gradient, MLP-1 bucket, rest) overlapped with the weight-gradient GEMMs")),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 if not infer else 4 * args.batch},
         "gpu_launches": int(getattr(engine, "kernels_per_step", 0) * args.steps) if engine is not None else int(launches),

@@ -28,6 +28,9 @@ def init_from_env(backend: str | None = None):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
+        # the gradient all-reduces run BESIDE the weight-gradient GEMMs (engine.TrainStep, overlap): a collective CTA cannot share an
+        # SM with a 225 KB-smem GEMM CTA, so the GEMMs leave `reserve_sms` SMs free and NCCL is held to that many CTAs
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:

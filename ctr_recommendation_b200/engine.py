@@ -60,7 +60,7 @@ class TrainStep:
 
     def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
                  seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True,
-                 global_batch: int | None = None):
+                 global_batch: int | None = None, overlap: bool | None = None, reserve_sms: int = 8):
         if not isinstance(model, MM_FiBiNET) or not isinstance(optimizer, (FusedAdam, FusedAdagrad)):
             raise TypeError("TrainStep needs a ctr_recommendation_b200 MM_FiBiNET and its FusedAdam / FusedAdagrad")
         self.model, self.opt, self.max_norm = model, optimizer, max_norm
@@ -72,6 +72,12 @@ class TrainStep:
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         if self.world > 1 and model._shard is None:
             model._dense_table_grad = True
+        # overlap the gradient all-reduces with the weight-gradient GEMMs (4 graphs + 3 async collectives per step instead of 2 + 2
+        # blocking ones): worth it once the leaf phase is long enough to hide a 47 MB all-reduce
+        self.overlap = (batch_size >= 8192) if overlap is None else bool(overlap)
+        self.reserve_sms = int(reserve_sms)
+        self._phased_single = overlap is True and self.world == 1
+        self._pending = []
         self.inp = _StaticBatch(batch_size, seq_len, idx_dtype, seq_dtype, dev, with_mm=not use_mm_table)
         if use_mm_table and model._mm_table is None:
             raise ValueError("use_mm_table=True needs model.attach_mm_table(...)")
@@ -127,8 +133,17 @@ class TrainStep:
         """The step as a list of (device work, collective that follows it or None); consecutive stages without a collective
         between them are captured into one CUDA graph."""
         if self.world == 1:
+            if self.overlap and self._phased_single:      # test hook: the phased backward without collectives
+                return [(self._fwd_chain, None), (self._leaf1, None), (self._leaf2, None), (self._update, None)]
             return [(self._fwd_bwd, None), (self._update, None)]
-        return [(self._fwd_bwd, self._allreduce), (self._update, None)]
+        if not self.overlap:
+            return [(self._fwd_bwd, self._allreduce), (self._update, None)]
+        # data parallel, overlapped (north_star (5)):  [forward + loss + data-gradient chain + table rows]
+        #   -> all-reduce(table gradient) starts          || [MLP-1 weight gradient]
+        #   -> all-reduce(MLP-1 bucket) starts            || [all other leaf gradients]
+        #   -> all-reduce(remaining dense gradients), wait for the three -> [norms + clip + Adam]
+        return [(self._fwd_chain, self._ar_table), (self._leaf1, self._ar_bucket1), (self._leaf2, self._ar_rest_wait),
+                (self._update, None)]
 
     def _batch_struct(self):
         t = self.inp.t
@@ -168,10 +183,66 @@ class TrainStep:
                                     C.byref(G), _lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(m._item_grad),
                                     _lib.ptr(m._row_touched), 1 if dense_table else 0, 1, _lib.ptr(m._grad_sumsq), st), "fbn_backward")
 
+    def _fwd_chain(self):
+        """Forward, loss and the data-gradient chain of the backward pass down to the table gradient (no leaf gradients)."""
+        m, lib = self.model, self.lib
+        P, G = m._params_struct(), m._grads_struct()
+        ws = self.ws
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            _lib.check(lib.fbn_embed_index(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), _lib.ptr(m._row_touched),
+                                           _lib.stream_ptr()), "fbn_embed_index")
+        st = _lib.stream_ptr()
+        _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
+                                   _lib.ptr(self.step_counter), _lib.ptr(self.prob), st), "fbn_forward")
+        _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
+                                    _lib.ptr(self.dprob), st), "fbn_bce_loss")
+        cur.wait_stream(self._side)
+        self._backward_phase(_lib.BWD_CHAIN)
+
+    def _backward_phase(self, phases, reserve=0):
+        m, lib = self.model, self.lib
+        P, G = m._params_struct(), m._grads_struct()
+        if reserve:      # leave SMs to the collective running beside the weight-gradient GEMMs (read at launch / capture time)
+            _lib.check(lib.fbn_set_option(b"tc_reserve_sms", int(reserve)), "fbn_set_option")
+        try:
+            _lib.check(lib.fbn_backward_phase(C.byref(P), C.byref(self._bs), _lib.ptr(self.ws), self.ws.numel(), 1, m.dropout_p,
+                                              _lib.ptr(self.dprob), C.byref(G), _lib.ptr(m._item_grad), _lib.ptr(m._row_touched),
+                                              1 if m._dense_table_grad else 0, 1, _lib.ptr(m._grad_sumsq), int(phases),
+                                              _lib.stream_ptr()), "fbn_backward_phase")
+        finally:
+            if reserve:
+                lib.fbn_set_option(b"tc_reserve_sms", 0)
+
+    def _leaf1(self):
+        self._backward_phase(_lib.BWD_LEAF1, self.reserve_sms)
+
+    def _leaf2(self):
+        self._backward_phase(_lib.BWD_LEAF2, self.reserve_sms)
+
+    def _ar_table(self):
+        import torch.distributed as dist
+        self._pending = [dist.all_reduce(self.model._item_grad, op=dist.ReduceOp.SUM, async_op=True)]
+
+    def _ar_bucket1(self):
+        import torch.distributed as dist
+        m = self.model
+        self._pending.append(dist.all_reduce(m._gflat[m._bucket1_offset():], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _ar_rest_wait(self):
+        import torch.distributed as dist
+        m = self.model
+        self._pending.append(dist.all_reduce(m._gflat[:m._bucket1_offset()], op=dist.ReduceOp.SUM, async_op=True))
+        for w in self._pending:
+            w.wait()                 # the compute stream waits for the collectives; the host does not
+        self._pending = []
+
     def _update(self):
         m, o, lib, st = self.model, self.opt, self.lib, _lib.stream_ptr()
-        if self.world > 1:   # norms of the all-reduced gradients
+        if self.world > 1 or self._phased_single:   # norm of the (all-reduced) dense gradients: the phased backward leaves it to the host
             _lib.check(lib.fbn_sumsq(_lib.ptr(m._gflat), m._gflat.numel(), _lib.ptr(self.sumsq_scratch), _lib.ptr(m._grad_sumsq), st))
+        if self.world > 1:                          # and of the all-reduced table gradient
             _lib.check(lib.fbn_sumsq(_lib.ptr(m._item_grad), m._item_grad.numel(), _lib.ptr(self.sumsq_scratch),
                                      fdist.C_ptr_offset(m._grad_sumsq, 1), st))
         clip = None
@@ -278,10 +349,13 @@ class TrainStep:
         return self.loss
 
     def _allreduce(self):
+        # the same collective sequence as the overlapped schedule (a rank without rows must match it call for call)
         import torch.distributed as dist
         m = self.model
-        dist.all_reduce(m._gflat, op=dist.ReduceOp.SUM)
+        off = m._bucket1_offset()
         dist.all_reduce(m._item_grad, op=dist.ReduceOp.SUM)
+        dist.all_reduce(m._gflat[off:], op=dist.ReduceOp.SUM)
+        dist.all_reduce(m._gflat[:off], op=dist.ReduceOp.SUM)
 
     def step_empty(self) -> torch.Tensor:
         """This rank received no rows of the global batch (torch's scatter chunking leaves the last ranks empty when

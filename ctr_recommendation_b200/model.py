@@ -33,9 +33,12 @@ _DENSE = [("cate_emb", "cate_emb.weight"), ("mm_w", "mm_proj.0.weight"), ("mm_b"
           ("se_w1", "senet.excitation.0.weight"), ("se_b1", "senet.excitation.0.bias"),
           ("se_w2", "senet.excitation.2.weight"), ("se_b2", "senet.excitation.2.bias"),
           ("bil_w", None),
-          ("w1", "mlp.0.weight"), ("b1", "mlp.0.bias"), ("bn1_g", "mlp.1.weight"), ("bn1_b", "mlp.1.bias"),
           ("w2", "mlp.4.weight"), ("b2", "mlp.4.bias"), ("bn2_g", "mlp.5.weight"), ("bn2_b", "mlp.5.bias"),
-          ("w3", "mlp.8.weight"), ("b3", "mlp.8.bias")]
+          ("w3", "mlp.8.weight"), ("b3", "mlp.8.bias"),
+          # last: the MLP-1 bucket (89 % of the dense bytes).  Its gradients are complete as soon as the first leaf phase of the
+          # backward pass is, and form one contiguous tail of the flat buffer -> one all-reduce that overlaps the other leaves
+          ("w1", "mlp.0.weight"), ("b1", "mlp.0.bias"), ("bn1_g", "mlp.1.weight"), ("bn1_b", "mlp.1.bias")]
+BUCKET1_FIRST = "w1"
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -297,6 +300,13 @@ class MM_FiBiNET(nn.Module):
         P.bilinear_type = _lib.BILINEAR_TYPES[self.bilinear.bilinear_type]
         P.precision = _lib.PRECISIONS[self.precision]
         return P
+
+    def _bucket1_offset(self) -> int:
+        """Element offset of the MLP-1 gradient bucket (the tail of the flat gradient buffer)."""
+        for (field, _), (off, _n) in zip(self._dense_params(), self._layout):
+            if field == BUCKET1_FIRST:
+                return off
+        raise AssertionError
 
     def _grads_struct(self) -> _lib.Grads:
         G = _lib.Grads()

@@ -181,3 +181,29 @@ def test_fused_adagrad_vs_oracle(gpu, wd, engine):
         assert (acc["item_emb.weight"].cpu().numpy()[untouched & (np.abs(acc["item_emb.weight"].cpu().numpy()).sum(1) == 0)] == 0).all()
     assert np.all(sd["item_emb.weight"][0] == 0)
     assert moved.size > 0
+
+
+def test_phased_backward_equals_single_call(gpu):
+    """fbn_backward_phase (CHAIN, then LEAF1, then LEAF2: the schedule the data-parallel engine interleaves with its gradient
+    all-reduces) produces bit-identical gradients, weights and moments to the single fbn_backward call -- same kernels, same
+    per-tensor summation order; run here on one GPU without the collectives."""
+    from ctr_recommendation_b200 import FusedAdam
+    from ctr_recommendation_b200.engine import TrainStep
+    B = 9000                                             # large enough for the CTA-pair GEMMs (and their SM reservation) to engage
+    pool = [synth.make_batch(seed=1300 + s, batch=B, id_dist="zipf", index_dtype=np.float64, edge_cases=False) for s in range(3)]
+    finals = []
+    for phased in (None, True):
+        model = gpu["make_model"](train=True, precision="tf32x3")
+        opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+        eng = TrainStep(model, opt, B, 20, idx_dtype=torch.float64, overlap=phased)
+        assert eng._phased_single == bool(phased)
+        for b, y in pool:
+            eng(_pinned(b), torch.from_numpy(y).pin_memory())
+        torch.cuda.synchronize()
+        st = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+        st["_gflat"] = model._gflat.cpu().numpy().copy()
+        st["_item_grad"] = (model._item_grad * (model._row_touched > 0).unsqueeze(1)).cpu().numpy()
+        st["_m_item"] = opt._m_item.cpu().numpy().copy()
+        finals.append(st)
+    for k in finals[0]:
+        assert np.array_equal(finals[0][k], finals[1][k]), k
