@@ -71,6 +71,8 @@ _SIGNATURES = {
                                      C.c_int, _vp, C.c_int, _vp]),
     "fbn_embed_index": (C.c_int, [C.POINTER(Params), C.POINTER(Batch), _vp, _sz, _vp, _vp]),
     "fbn_bce_loss": (C.c_int, [_vp, _vp, _i64, _f, _vp, _vp, _vp]),
+    "fbn_bce_scratch_bytes": (_sz, []),
+    "fbn_bce_loss_ws": (C.c_int, [_vp, _vp, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
     "fbn_clip_coef": (C.c_int, [_vp, C.c_int, _f, _vp, _vp]),
     "fbn_adam_table": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(AdamHyper), _vp, _vp]),
     "fbn_adam_dense": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(AdamHyper), _vp, _vp]),
@@ -79,6 +81,14 @@ _SIGNATURES = {
     "fbn_onecycle_hyper": (C.c_int, [_vp, C.c_int, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _vp]),
     "fbn_sumsq": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "fbn_sumsq_partial_floats": (_sz, [_i64]),
+    "fbn_fields_gather": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
+    "fbn_fields_scatter_bytes": (_sz, [_i64, C.c_int, _i64]),
+    "fbn_fields_scatter": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _i64, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "fbn_tower_workspace_bytes": (_sz, [_i64, _i64]),
+    "fbn_tower_forward": (C.c_int, [C.POINTER(Params), _vp, _i64, _i64, _vp, _sz, C.c_int, _f, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "fbn_tower_backward": (C.c_int, [C.POINTER(Params), _vp, _i64, _i64, _vp, _sz, C.c_int, _f, _vp, C.POINTER(Grads), _vp, _vp]),
+    "fbn_bilinear_fwd_ld": (C.c_int, [_vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _vp, _i64, _vp, _sz, C.c_int, _vp]),
+    "fbn_bilinear_bwd_ld": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, C.c_int, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, C.c_int, _vp]),
     "fbn_senet_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "fbn_senet_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _sz, _vp]),

@@ -689,6 +689,144 @@ extern "C" int fbn_backward_phase(const fbn_params_t* p, const fbn_batch_t* b, v
                        grad_sumsq, stream, phases);
 }
 
+// ---- MLP tower for an arbitrary input width (F-field model, general.py) ------------------------------------------------------
+namespace fbn {
+struct TowerWs {
+  float *Hd1, *A1, *Hd2, *A2, *logit, *prob, *bn, *dlogit, *dH2, *dH1, *partial, *partial_side;
+  size_t partial_floats;
+  void *pk_C, *pk_A1, *pk_dH2, *pk_dH1, *pk_w1, *pk_w2;
+  size_t total_bytes;
+};
+
+static void carve_tower(TowerWs& w, void* base, int64_t B, int64_t k1) {
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = base ? p + off : nullptr;
+    off += align_up(bytes);
+    return r;
+  };
+  const size_t f = sizeof(float);
+  const int64_t Bp = std::max<int64_t>(B, 1);
+  w.Hd1 = (float*)take(Bp * H1 * f); w.A1 = (float*)take(Bp * H1 * f);
+  w.Hd2 = (float*)take(Bp * H2 * f); w.A2 = (float*)take(Bp * H2 * f);
+  w.logit = (float*)take(Bp * f); w.prob = (float*)take(Bp * f);
+  w.bn = (float*)take((2 * H1 + 2 * H2) * f);
+  w.dlogit = (float*)take(Bp * f);
+  w.dH2 = (float*)take(Bp * H2 * f); w.dH1 = (float*)take(Bp * H1 * f);
+  size_t pf = std::max<size_t>((size_t)4 * H1 * k1, (size_t)32 * H2 * H1);   // split-K partials of the two weight gradients
+  pf = std::max<size_t>(pf, (size_t)4 * 148 * 3 * H1);
+  w.partial_floats = pf;
+  w.partial = (float*)take(pf * f);
+  w.partial_side = (float*)take((size_t)4 * 148 * 3 * H1 * f);
+  const int PX = FBN_PREC_TF32X3;
+  w.pk_C = take(packed_bytes(Bp, k1, PX));
+  w.pk_A1 = take(packed_bytes(Bp, H1, PX));
+  w.pk_dH2 = take(packed_bytes(Bp, H2, PX));
+  w.pk_dH1 = take(packed_bytes(Bp, H1, PX));
+  w.pk_w1 = take(packed_bytes(H1, k1, PX));
+  w.pk_w2 = take(packed_bytes(H2, H1, PX));
+  w.total_bytes = off;
+}
+
+static int tower_check(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes) {
+  FBN_REQUIRE(p && c && ws, FBN_ERR_ARG, "fbn_tower: null pointer");
+  FBN_REQUIRE(batch >= 1 && k1 >= 128 && k1 % 128 == 0, FBN_ERR_SHAPE, "fbn_tower: the input width must be a multiple of 128");
+  FBN_REQUIRE(p->precision >= FBN_PREC_FP32 && p->precision <= FBN_PREC_BF16, FBN_ERR_ARG, "bad precision");
+  const void* ptrs[] = {c, ws, p->w1, p->b1, p->bn1_g, p->bn1_b, p->bn1_mean, p->bn1_var, p->w2, p->b2, p->bn2_g, p->bn2_b, p->bn2_mean,
+                        p->bn2_var, p->w3};
+  for (const void* q : ptrs) FBN_REQUIRE(q && aligned16(q), FBN_ERR_ALIGN, "fbn_tower: a tensor pointer is missing or not 16-byte aligned");
+  FBN_REQUIRE(p->b3 != nullptr, FBN_ERR_ARG, "fbn_tower: null b3");
+  TowerWs w;
+  carve_tower(w, nullptr, batch, k1);
+  FBN_REQUIRE(ws_bytes >= w.total_bytes, FBN_ERR_ARG, "fbn_tower: workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
+  return FBN_OK;
+}
+}  // namespace fbn
+
+extern "C" size_t fbn_tower_workspace_bytes(int64_t batch, int64_t k1) {
+  TowerWs w;
+  carve_tower(w, nullptr, batch, k1);
+  return w.total_bytes;
+}
+
+extern "C" int fbn_tower_forward(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes, int train,
+                                 float dropout_p, const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset,
+                                 const int32_t* step_counter_dev, float* prob_out, float* logit_out, fbn_stream_t stream) {
+  RC(tower_check(p, c, batch, k1, ws, ws_bytes));
+  FBN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, FBN_ERR_ARG, "dropout_p must be in [0,1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  TowerWs w;
+  carve_tower(w, ws, batch, k1);
+  Workspace shell{};                       // the GEMM helpers only look at the operand scratch (unused: everything is pre-packed)
+  const long long B = batch;
+  tl_reg = PkReg();
+  tl_reg.prec = p->precision; tl_reg.st = st;
+  RC(tl_reg.pack(p->w1, H1, k1, w.pk_w1));
+  RC(tl_reg.pack(p->w2, H2, H1, w.pk_w2));
+  RC(tl_reg.pack(c, B, k1, w.pk_C));
+  float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
+  GemmArgs g1;
+  g1.A = c; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = k1; g1.lda = k1; g1.ldb = k1; g1.ldc = H1; g1.b_t = 1;
+  RC(tl_reg.run(g1, shell));
+  if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
+  else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
+  DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
+  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst(w.A1, B, H1, w.pk_A1), st));
+  GemmArgs g2;
+  g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2; g2.b_t = 1;
+  RC(tl_reg.run(g2, shell));
+  if (train) RC(bn_train_stats(w.Hd2, B, H2, w.partial, mean2, rstd2, p->bn2_mean, p->bn2_var, st));
+  else RC(bn_eval_stats(p->bn2_mean, p->bn2_var, H2, mean2, rstd2, st));
+  DropArgs d2; d2.p = train ? dropout_p : 0.f; d2.mask = keep_mask2; d2.seed = seed; d2.offset = offset; d2.stream = 2; d2.step_dev = step_counter_dev;
+  RC(head_fwd(w.Hd2, mean2, rstd2, p->bn2_g, p->bn2_b, p->w3, p->b3, B, d2, w.A2, w.logit, w.prob, st));
+  if (prob_out) FBN_CHECK_CUDA(cudaMemcpyAsync(prob_out, w.prob, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  if (logit_out) FBN_CHECK_CUDA(cudaMemcpyAsync(logit_out, w.logit, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  return FBN_OK;
+}
+
+extern "C" int fbn_tower_backward(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes, int train,
+                                  float dropout_p, const float* dprob, const fbn_grads_t* g, float* dc, fbn_stream_t stream) {
+  RC(tower_check(p, c, batch, k1, ws, ws_bytes));
+  FBN_REQUIRE(dprob && g && dc && aligned16(dc), FBN_ERR_ARG, "fbn_tower_backward: null / unaligned pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TowerWs w;
+  carve_tower(w, ws, batch, k1);
+  Workspace shell{};
+  shell.partial_floats = w.partial_floats;
+  const long long B = batch;
+  const int prec = p->precision;
+  const float scale = (train && dropout_p > 0.f) ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  tl_reg = PkReg();
+  tl_reg.prec = p->precision; tl_reg.st = st;
+  tl_reg.describe(p->w1, H1, k1, w.pk_w1);
+  tl_reg.describe(p->w2, H2, H1, w.pk_w2);
+  tl_reg.describe(c, B, k1, w.pk_C);
+  tl_reg.describe(w.A1, B, H1, w.pk_A1);
+  float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
+  RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3, st));
+  RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
+                   tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
+  RC(colsum(w.dH2, B, H2, w.partial, g->b2, st));
+  RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, shell, g->w2, st, w.partial));
+  {
+    GemmArgs d;  // dA1 = dH2 * w2
+    d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
+    RC(tl_reg.run(d, shell));
+  }
+  RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
+  RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
+                   tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
+  RC(colsum(w.dH1, B, H1, w.partial, g->b1, st));
+  RC(wgrad(w.dH1, H1, c, k1, B, H1, k1, ~0ull, prec, shell, g->w1, st, w.partial));
+  {
+    GemmArgs d;  // dC = dH1 * w1
+    d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = k1; d.b_t = 0; d.C = dc; d.ldc = k1; d.M = B; d.N = k1; d.K = H1;
+    RC(tl_reg.run(d, shell));
+  }
+  return FBN_OK;
+}
+
 // Per-stage device times of the calls made since the last report (see stage_mark): "name<TAB>ms" lines.  Synchronises.
 extern "C" int fbn_stage_report(char* buf, size_t buf_bytes) {
   FBN_REQUIRE(buf && buf_bytes > 0, FBN_ERR_ARG, "fbn_stage_report: null buffer");
@@ -791,10 +929,74 @@ __global__ void bce_kernel(const float* __restrict__ prob, const float* __restri
 }
 }  // namespace fbn
 
+namespace fbn {
+// multi-block BCELoss: every block handles one contiguous chunk (dprob + a double partial of the loss); the block that arrives
+// last adds the partials in block order (fixed order -> run-to-run deterministic) and re-arms the counter for the next launch.
+// (The single-block kernel above costs 148 us at B = 65536 -- on the critical path between forward and backward.)
+constexpr int BCE_MAX_BLOCKS = 512;
+__global__ void __launch_bounds__(256) bce_multi_kernel(const float* __restrict__ prob, const float* __restrict__ y, long long B, long long per,
+                                                        float scale, float* loss_out, float* __restrict__ dprob, double* partial,
+                                                        unsigned int* counter) {
+  __shared__ double s[256];
+  __shared__ bool last;
+  const long long b0 = (long long)blockIdx.x * per, b1 = min(B, b0 + per);
+  const float invB = 1.0f / (float)B;
+  double t = 0.0;
+  for (long long i = b0 + threadIdx.x; i < b1; i += 256) {
+    const float p = prob[i], yy = y[i];
+    const float lp = fmaxf(logf(p), -100.0f), l1p = fmaxf(log1pf(-p), -100.0f);
+    t += (double)(-(yy * lp + (1.0f - yy) * l1p));
+    if (dprob) dprob[i] = scale * ((p - yy) / fmaxf((1.0f - p) * p, 1e-12f)) * invB;
+  }
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s[0];
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double u = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) u += ((volatile double*)partial)[i];
+  s[threadIdx.x] = u;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (loss_out) loss_out[0] = (float)(s[0] / (double)B);
+    *counter = 0;
+  }
+}
+}  // namespace fbn
+
 extern "C" int fbn_bce_loss(const float* prob, const float* labels, int64_t batch, float loss_scale, float* loss_out, float* dprob_out,
                             fbn_stream_t stream) {
   FBN_REQUIRE(prob && labels && batch >= 1, FBN_ERR_ARG, "fbn_bce_loss: bad arguments");
   bce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(prob, labels, batch, loss_scale, loss_out, dprob_out);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+extern "C" size_t fbn_bce_scratch_bytes(void) { return (size_t)BCE_MAX_BLOCKS * sizeof(double) + 64; }
+
+extern "C" int fbn_bce_loss_ws(const float* prob, const float* labels, int64_t batch, float loss_scale, float* loss_out, float* dprob_out,
+                               void* scratch, size_t scratch_bytes, fbn_stream_t stream) {
+  FBN_REQUIRE(prob && labels && batch >= 1 && scratch, FBN_ERR_ARG, "fbn_bce_loss_ws: bad arguments");
+  FBN_REQUIRE(scratch_bytes >= fbn_bce_scratch_bytes() && (reinterpret_cast<uintptr_t>(scratch) & 7u) == 0, FBN_ERR_ARG,
+              "fbn_bce_loss_ws: scratch too small / unaligned");
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(batch, 1024), std::min(BCE_MAX_BLOCKS, 2 * num_sms())));
+  const long long per = cdiv(batch, blocks);
+  double* partial = static_cast<double*>(scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + BCE_MAX_BLOCKS);
+  bce_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(prob, labels, batch, per, loss_scale, loss_out, dprob_out, partial, counter);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }

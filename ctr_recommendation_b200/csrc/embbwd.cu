@@ -94,4 +94,106 @@ int emb_rows(const EmbGradArgs& a, cudaStream_t st) {
   return FBN_OK;
 }
 
+// ---- F-field model (general.py): lookups of F tables stored back to back, and their dense gradient -------------------------------
+__global__ void fields_gather_kernel(const float* __restrict__ table, const long long* __restrict__ offsets, const void* __restrict__ ids,
+                                     int idx_dtype, long long n, int F, float* __restrict__ x, int32_t* flag) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {   // one warp per (sample, field)
+    const int f = (int)(i % F);
+    const long long lo = offsets[f], vocab = offsets[f + 1] - lo;
+    long long id = load_index(ids, idx_dtype, i);
+    if (lane == 0 && (id < 0 || id >= vocab)) flag[0] = 1;          // torch: IndexError (the host raises it)
+    id = min(max(id, 0LL), vocab - 1);
+    st4(x + i * D + 4 * lane, ld4(table + (lo + id) * D + 4 * lane));
+  }
+}
+
+__global__ void fields_build_keys_kernel(const long long* __restrict__ offsets, const void* __restrict__ ids, int idx_dtype, long long n,
+                                         int F, int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long lo = offsets[f], vocab = offsets[f + 1] - lo;
+    const long long id = min(max(load_index(ids, idx_dtype, i), 0LL), vocab - 1);
+    keys[i] = (int)(lo + id);
+    vals[i] = (int)i;
+  }
+}
+
+struct FieldsScratch { int32_t *keys_in, *keys_out, *vals_in, *vals_out, *row_off, *row_cnt; float* sq_partial; void* cub; size_t total; };
+
+static FieldsScratch fields_carve(void* base, long long n, long long rows) {
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  FieldsScratch s;
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));
+  char* p0 = p;
+  s.keys_in = (int32_t*)p; p += al(n * 4);
+  s.keys_out = (int32_t*)p; p += al(n * 4);
+  s.vals_in = (int32_t*)p; p += al(n * 4);
+  s.vals_out = (int32_t*)p; p += al(n * 4);
+  s.row_off = (int32_t*)p; p += al((rows + 1) * 4);
+  s.row_cnt = (int32_t*)p; p += al((rows + 1) * 4);
+  s.sq_partial = (float*)p; p += al(((size_t)cdiv(rows, 8) + 1024) * 4);
+  s.cub = p; p += emb_sort_temp_bytes(n, rows);
+  s.total = (size_t)(p - p0) + 256;
+  return s;
+}
+
 }  // namespace fbn
+
+using namespace fbn;
+
+extern "C" int fbn_fields_gather(const float* table, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields,
+                                 float* x, int32_t* flag, fbn_stream_t stream) {
+  FBN_REQUIRE(table && offsets && ids && x && flag, FBN_ERR_ARG, "fbn_fields_gather: null pointer");
+  FBN_REQUIRE(idx_dtype == FBN_IDX_I32 || idx_dtype == FBN_IDX_I64, FBN_ERR_DTYPE, "fbn_fields_gather: ids must be int32 or int64");
+  FBN_REQUIRE(fields >= 1 && fields <= 64 && batch >= 1, FBN_ERR_SHAPE, "fbn_fields_gather: need 1 <= fields <= 64");
+  FBN_REQUIRE(aligned16(table) && aligned16(x), FBN_ERR_ALIGN, "fbn_fields_gather: unaligned pointer");
+  const long long n = (long long)batch * fields;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, 8), 16LL * num_sms()));
+  fields_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, reinterpret_cast<const long long*>(offsets), ids, idx_dtype, n, fields, x,
+                                                                 flag);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+extern "C" size_t fbn_fields_scatter_bytes(int64_t batch, int fields, int64_t rows) {
+  return fields_carve(nullptr, (long long)batch * fields, rows).total;
+}
+
+extern "C" int fbn_fields_scatter(const float* dx, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields,
+                                  int64_t rows, float* grad, int32_t* row_touched, int zero_fill, float* sumsq_out, void* scratch,
+                                  size_t scratch_bytes, fbn_stream_t stream) {
+  FBN_REQUIRE(dx && offsets && ids && grad && sumsq_out && scratch, FBN_ERR_ARG, "fbn_fields_scatter: null pointer");
+  FBN_REQUIRE(idx_dtype == FBN_IDX_I32 || idx_dtype == FBN_IDX_I64, FBN_ERR_DTYPE, "fbn_fields_scatter: ids must be int32 or int64");
+  const long long n = (long long)batch * fields;
+  FBN_REQUIRE(fields >= 1 && fields <= 64 && batch >= 1 && rows >= 1 && n < (1LL << 31) && rows < (1LL << 30), FBN_ERR_SHAPE,
+              "fbn_fields_scatter: bad shape");
+  FBN_REQUIRE(aligned16(dx) && aligned16(grad), FBN_ERR_ALIGN, "fbn_fields_scatter: unaligned pointer");
+  FBN_REQUIRE(scratch_bytes >= fbn_fields_scatter_bytes(batch, fields, rows), FBN_ERR_ARG, "fbn_fields_scatter: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  FieldsScratch s = fields_carve(scratch, n, rows);
+  int32_t* cnt = row_touched ? row_touched : s.row_cnt;
+  FBN_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * rows, st));
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, 256), 8LL * num_sms()));
+  fields_build_keys_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(offsets), ids, idx_dtype, n, fields, s.keys_in, s.vals_in);
+  FBN_CHECK_LAUNCH();
+  size_t bytes = sort_bytes(n, rows);
+  FBN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(s.cub, bytes, (const int32_t*)s.keys_in, s.keys_out, (const int32_t*)s.vals_in, s.vals_out,
+                                                 (int)n, 0, key_bits(rows), st));
+  g_launches += 4;
+  emb_runs_kernel<<<blocks, 256, 0, st>>>(s.keys_out, n, (int)rows, cnt, s.row_off);
+  FBN_CHECK_LAUNCH();
+  // every occurrence i reads its own gradient row dx[i]: B = 0 and L = 1 in the shared segment-sum addressing
+  const int nb = emb_grad_partial_count(rows);
+  SegArgs a{};
+  a.off = s.row_off; a.cnt = cnt; a.nseg_dev = nullptr; a.nseg = rows; a.src = s.vals_out;
+  a.dXitem = dx; a.dXhist = dx; a.B = 0; a.L = 1;
+  a.out = grad; a.zero_fill = zero_fill; a.sq_partial = s.sq_partial; a.nseg_bound = rows;
+  a.hot = seg_carve(static_cast<char*>(s.cub) + sort_bytes(n, rows), n);
+  FBN_CHECK_CUDA(seg_sum_launch(a, nb, n, st));
+  g_launches += 3;
+  seg_sumsq_final_kernel<<<1, 256, 0, st>>>(s.sq_partial, nb, a.hot.hot_sq, (int)a.hot.max_hot, sumsq_out);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}

@@ -1,5 +1,6 @@
 // Stand-alone SENetLayer / BilinearInteraction entry points (module-level API of the reference,
-// src/model_fibinet.py:5-89) for arbitrary field counts (F <= 32, hidden <= 32, D % 4 == 0).
+// src/model_fibinet.py:5-89) for arbitrary field counts (F <= 64, hidden <= 64, D % 4 == 0).  The *_ld variants take row
+// strides so that the F-field model (general.py) can keep V and the pair products inside one (B, (F+P)*D) MLP-input buffer.
 #include <algorithm>
 
 #include "common.cuh"
@@ -8,13 +9,13 @@
 
 namespace fbn {
 
-constexpr int SE_MAXF = 32;
+constexpr int SE_MAXF = 64;
 
 // ---- SENET forward: warp per sample -----------------------------------------------------------
 __global__ void __launch_bounds__(256) senet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, long long B, int F, int Dm, int R,
-                                                        float* __restrict__ y, float* __restrict__ gate) {
+                                                        float* __restrict__ y, long long ldy, float* __restrict__ gate) {
   __shared__ float zs[8][SE_MAXF], hs[8][SE_MAXF], ss[8][SE_MAXF];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -27,23 +28,23 @@ __global__ void __launch_bounds__(256) senet_fwd_kernel(const float* __restrict_
       if (lane == 0) zs[w][f] = t / (float)Dm;
     }
     __syncwarp();
-    if (lane < R) {                                     // excitation (ref :17-21)
-      float a = b1[lane];
-      for (int f = 0; f < F; ++f) a = fmaf(zs[w][f], w1[lane * F + f], a);
-      hs[w][lane] = fmaxf(a, 0.f);
+    for (int r = lane; r < R; r += 32) {                // excitation (ref :17-21)
+      float a = b1[r];
+      for (int f = 0; f < F; ++f) a = fmaf(zs[w][f], w1[r * F + f], a);
+      hs[w][r] = fmaxf(a, 0.f);
     }
     __syncwarp();
-    if (lane < F) {
-      float a = b2[lane];
-      for (int r = 0; r < R; ++r) a = fmaf(hs[w][r], w2[lane * R + r], a);
+    for (int f = lane; f < F; f += 32) {
+      float a = b2[f];
+      for (int r = 0; r < R; ++r) a = fmaf(hs[w][r], w2[f * R + r], a);
       const float s = sigmoidf_(a);
-      ss[w][lane] = s;
-      gate[b * F + lane] = s;
+      ss[w][f] = s;
+      gate[b * F + f] = s;
     }
     __syncwarp();
     for (int f = 0; f < F; ++f) {                       // re-weight (ref :35)
       const float s = ss[w][f];
-      for (int d = lane * 4; d < Dm; d += 128) st4(y + b * F * Dm + f * Dm + d, ld4(xb + f * Dm + d) * s);
+      for (int d = lane * 4; d < Dm; d += 128) st4(y + b * ldy + f * Dm + d, ld4(xb + f * Dm + d) * s);
     }
     __syncwarp();
   }
@@ -77,25 +78,25 @@ __global__ void __launch_bounds__(256) senet_bwd_kernel(const float* __restrict_
       }
     }
     __syncwarp();
-    if (lane < R) {
-      float a = b1[lane];
-      for (int f = 0; f < F; ++f) a = fmaf(zs[w][f], w1[lane * F + f], a);
+    for (int r = lane; r < R; r += 32) {
+      float a = b1[r];
+      for (int f = 0; f < F; ++f) a = fmaf(zs[w][f], w1[r * F + f], a);
       const float h = fmaxf(a, 0.f);
       float t = 0.f;
-      for (int f = 0; f < F; ++f) t = fmaf(da2[w][f], w2[f * R + lane], t);
-      hs[w][lane] = h;
-      da1[w][lane] = h > 0.f ? t : 0.f;
+      for (int f = 0; f < F; ++f) t = fmaf(da2[w][f], w2[f * R + r], t);
+      hs[w][r] = h;
+      da1[w][r] = h > 0.f ? t : 0.f;
     }
     __syncwarp();
-    if (lane < F) {
+    for (int f = lane; f < F; f += 32) {
       float t = 0.f;
-      for (int r = 0; r < R; ++r) t = fmaf(da1[w][r], w1[r * F + lane], t);
-      dz[w][lane] = t / (float)Dm;
+      for (int r = 0; r < R; ++r) t = fmaf(da1[w][r], w1[r * F + f], t);
+      dz[w][f] = t / (float)Dm;
     }
     __syncwarp();
     float* rb = rec + b * RS;
-    if (lane < F) { rb[lane] = da2[w][lane]; rb[F + R + lane] = zs[w][lane]; }
-    if (lane < R) { rb[F + lane] = hs[w][lane]; rb[2 * F + R + lane] = da1[w][lane]; }
+    for (int f = lane; f < F; f += 32) { rb[f] = da2[w][f]; rb[F + R + f] = zs[w][f]; }
+    for (int r = lane; r < R; r += 32) { rb[F + r] = hs[w][r]; rb[2 * F + R + r] = da1[w][r]; }
     for (int f = 0; f < F; ++f) {
       const float s = gate[b * F + f], z = dz[w][f];
       for (int d = lane * 4; d < Dm; d += 128) st4(dx + b * F * Dm + f * Dm + d, ld4(db + f * Dm + d) * s + f4(z));
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(256) senet_pgrad_final_kernel(const float* __r
 __host__ __device__ inline int pair_index(int i, int j, int F) { return i * (2 * F - i - 1) / 2 + (j - i - 1); }
 
 // forward: p[b][q(i,j)] = left * right with (ALL) v_i * T_j, (EACH) T_i * v_j, (INTERACTION) T_q * v_j
-__global__ void bil_pairs_fwd_kernel(const float* __restrict__ v, const float* __restrict__ T, int type, long long B, int F, int Dm,
-                                     float* __restrict__ p) {
+__global__ void bil_pairs_fwd_kernel(const float* __restrict__ v, long long ldv, const float* __restrict__ T, int type, long long B,
+                                     int F, int Dm, float* __restrict__ p, long long ldp) {
   const int P = F * (F - 1) / 2, nT = type == FBN_BILINEAR_ALL ? F : (type == FBN_BILINEAR_EACH ? F - 1 : P);
   const int d4 = Dm / 4;
   const long long total = B * P * d4;
@@ -158,19 +159,20 @@ __global__ void bil_pairs_fwd_kernel(const float* __restrict__ v, const float* _
     int i = 0, rem = q;
     while (rem >= F - 1 - i) { rem -= F - 1 - i; ++i; }
     const int j = i + 1 + rem;
-    const float* vb = v + b * F * Dm;
+    const float* vb = v + b * ldv;
     const float* Tb = T + b * nT * Dm;
     float4 o;
     if (type == FBN_BILINEAR_ALL) o = ld4(vb + i * Dm + d) * ld4(Tb + j * Dm + d);
     else if (type == FBN_BILINEAR_EACH) o = ld4(Tb + i * Dm + d) * ld4(vb + j * Dm + d);
     else o = ld4(Tb + q * Dm + d) * ld4(vb + j * Dm + d);
-    st4(p + idx * 4, o);
+    st4(p + b * ldp + (long long)q * Dm + d, o);
   }
 }
 
 // backward (elementwise part): dT and the direct dv terms; thread per (b, field f, d4)
-__global__ void bil_pairs_bwd_kernel(const float* __restrict__ v, const float* __restrict__ T, const float* __restrict__ dp, int type,
-                                     long long B, int F, int Dm, float* __restrict__ dv, float* __restrict__ dT) {
+__global__ void bil_pairs_bwd_kernel(const float* __restrict__ v, long long ldv, const float* __restrict__ T, const float* __restrict__ dp,
+                                     long long lddp, const float* __restrict__ dv_init, long long ldi, int type, long long B, int F,
+                                     int Dm, float* __restrict__ dv, float* __restrict__ dT) {
   const int P = F * (F - 1) / 2, nT = type == FBN_BILINEAR_ALL ? F : (type == FBN_BILINEAR_EACH ? F - 1 : P);
   const int d4 = Dm / 4;
   const long long total = B * F * d4;
@@ -179,10 +181,10 @@ __global__ void bil_pairs_bwd_kernel(const float* __restrict__ v, const float* _
     const long long bf = idx / d4;
     const int f = (int)(bf % F);
     const long long b = bf / F;
-    const float* vb = v + b * F * Dm;
+    const float* vb = v + b * ldv;
     const float* Tb = T + b * nT * Dm;
-    const float* dpb = dp + b * P * Dm;
-    float4 gv = f4(0.f), gt = f4(0.f);
+    const float* dpb = dp + b * lddp;
+    float4 gv = dv_init ? ld4(dv_init + b * ldi + f * Dm + d) : f4(0.f), gt = f4(0.f);   // dv_init: gradient that reached v directly
     if (type == FBN_BILINEAR_ALL) {
       for (int j = f + 1; j < F; ++j) gv += ld4(dpb + pair_index(f, j, F) * Dm + d) * ld4(Tb + j * Dm + d);   // as v_i
       for (int i = 0; i < f; ++i) gt += ld4(dpb + pair_index(i, f, F) * Dm + d) * ld4(vb + i * Dm + d);       // as T_j
@@ -222,11 +224,11 @@ extern "C" int fbn_senet_fwd(const float* x, const float* w1, const float* b1, c
                              int dim, int hidden, float* y, float* gate, fbn_stream_t stream) {
   FBN_REQUIRE(x && w1 && b1 && w2 && b2 && y && gate, FBN_ERR_ARG, "fbn_senet_fwd: null pointer");
   FBN_REQUIRE(fields >= 1 && fields <= SE_MAXF && hidden >= 1 && hidden <= SE_MAXF && dim % 4 == 0 && dim >= 4, FBN_ERR_SHAPE,
-              "fbn_senet_fwd: need 1 <= fields, hidden <= 32 and dim %% 4 == 0");
+              "fbn_senet_fwd: need 1 <= fields, hidden <= 64 and dim %% 4 == 0");
   FBN_REQUIRE(aligned16(x) && aligned16(y), FBN_ERR_ALIGN, "fbn_senet_fwd: unaligned pointer");
   if (batch <= 0) return FBN_OK;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(batch, 8), 8LL * num_sms()));
-  senet_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, w1, b1, w2, b2, batch, fields, dim, hidden, y, gate);
+  senet_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, w1, b1, w2, b2, batch, fields, dim, hidden, y, (long long)fields * dim, gate);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -321,24 +323,39 @@ static int bil_check(const float* v, const float* w, int type, int64_t batch, in
 
 extern "C" int fbn_bilinear_fwd(const float* v, const float* w, int type, int64_t batch, int fields, int dim, float* p, void* scratch,
                                 size_t scratch_bytes, int precision, fbn_stream_t stream) {
+  return fbn_bilinear_fwd_ld(v, w, type, batch, fields, dim, p, (int64_t)(fields * (fields - 1) / 2) * dim, scratch, scratch_bytes, precision,
+                             stream);
+}
+
+extern "C" int fbn_bilinear_fwd_ld(const float* v, const float* w, int type, int64_t batch, int fields, int dim, float* p, int64_t ldp,
+                                   void* scratch, size_t scratch_bytes, int precision, fbn_stream_t stream) {
   int rc = bil_check(v, w, type, batch, fields, dim, precision);
   if (rc) return rc;
   FBN_REQUIRE(p && scratch && scratch_bytes >= fbn_bilinear_scratch_bytes(batch, fields, dim, type), FBN_ERR_ARG,
               "fbn_bilinear_fwd: scratch too small");
+  FBN_REQUIRE(ldp >= (int64_t)(fields * (fields - 1) / 2) * dim && ldp % 4 == 0 && aligned16(p), FBN_ERR_SHAPE, "fbn_bilinear_fwd: bad ldp");
   cudaStream_t st = (cudaStream_t)stream;
   BilScratch s = bil_carve(scratch, scratch_bytes, batch, fields, dim, type);
   rc = bil_transform(v, w, type, batch, fields, dim, s.T, precision, s, st);
   if (rc) return rc;
   const long long total = (long long)batch * (fields * (fields - 1) / 2) * (dim / 4);
-  bil_pairs_fwd_kernel<<<ew_blocks(total), 256, 0, st>>>(v, s.T, type, batch, fields, dim, p);
+  bil_pairs_fwd_kernel<<<ew_blocks(total), 256, 0, st>>>(v, (long long)fields * dim, s.T, type, batch, fields, dim, p, ldp);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
 
 extern "C" int fbn_bilinear_bwd(const float* v, const float* w, const float* dp, int type, int64_t batch, int fields, int dim, float* dv,
                                 float* dw, void* scratch, size_t scratch_bytes, int precision, fbn_stream_t stream) {
+  return fbn_bilinear_bwd_ld(v, w, dp, (int64_t)(fields * (fields - 1) / 2) * dim, nullptr, 0, type, batch, fields, dim, dv, dw, scratch,
+                             scratch_bytes, precision, stream);
+}
+
+extern "C" int fbn_bilinear_bwd_ld(const float* v, const float* w, const float* dp, int64_t lddp, const float* dv_init, int64_t ld_init,
+                                   int type, int64_t batch, int fields, int dim, float* dv, float* dw, void* scratch, size_t scratch_bytes,
+                                   int precision, fbn_stream_t stream) {
   int rc = bil_check(v, w, type, batch, fields, dim, precision);
   if (rc) return rc;
+  FBN_REQUIRE(lddp % 4 == 0 && ld_init % 4 == 0 && aligned16(dp) && aligned16(dv_init), FBN_ERR_ALIGN, "fbn_bilinear_bwd: bad strides");
   FBN_REQUIRE(dp && dv && dw && scratch && scratch_bytes >= fbn_bilinear_scratch_bytes(batch, fields, dim, type), FBN_ERR_ARG,
               "fbn_bilinear_bwd: scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -349,7 +366,8 @@ extern "C" int fbn_bilinear_bwd(const float* v, const float* w, const float* dp,
   BilScratch s = bil_carve(scratch, scratch_bytes, batch, fields, dim, type);
   rc = bil_transform(v, w, type, batch, fields, dim, s.T, precision, s, st);     // recompute T (not saved by forward)
   if (rc) return rc;
-  bil_pairs_bwd_kernel<<<ew_blocks(B * F * (Dm / 4)), 256, 0, st>>>(v, s.T, dp, type, B, F, Dm, dv, s.dT);
+  bil_pairs_bwd_kernel<<<ew_blocks(B * F * (Dm / 4)), 256, 0, st>>>(v, (long long)F * Dm, s.T, dp, lddp, dv_init, ld_init, type, B, F, Dm, dv,
+                                                                     s.dT);
   FBN_CHECK_LAUNCH();
   // dv[src] += dT W^T ; dW = sum v_src^T dT
   GemmArgs d;

@@ -292,18 +292,31 @@ int head_fwd(const float* H, const float* mean, const float* rstd, const float* 
   return FBN_OK;
 }
 
-// dlogit = dprob * p * (1-p)  (sigmoid backward); also per-chunk partial sums for db3
-__global__ void head_dlogit_kernel(const float* __restrict__ dprob, const float* __restrict__ prob, long long B, float* dlogit) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+// dlogit = dprob * p * (1-p)  (sigmoid backward) + per-block double partial sums for db3 (contiguous chunk per block, fixed order)
+__global__ void __launch_bounds__(256) head_dlogit_kernel(const float* __restrict__ dprob, const float* __restrict__ prob, long long B,
+                                                          long long per, float* __restrict__ dlogit, double* __restrict__ partial) {
+  __shared__ double s[256];
+  const long long b0 = (long long)blockIdx.x * per, b1 = min(B, b0 + per);
+  double t = 0.0;
+  for (long long i = b0 + threadIdx.x; i < b1; i += 256) {
     const float p = prob[i];
-    dlogit[i] = dprob[i] * ((1.0f - p) * p);
+    const float d = dprob[i] * ((1.0f - p) * p);
+    dlogit[i] = d;
+    t += (double)d;
   }
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
 }
 
-__global__ void sum1_kernel(const float* __restrict__ x, long long n, float* out) {  // single block, fixed order
+__global__ void sum1_kernel(const double* __restrict__ x, int n, float* out) {  // single block over the per-block partials, fixed order
   __shared__ double s[256];
   double t = 0.0;
-  for (long long i = threadIdx.x; i < n; i += 256) t += (double)x[i];
+  for (int i = threadIdx.x; i < n; i += 256) t += x[i];
   s[threadIdx.x] = t;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -318,10 +331,11 @@ __global__ void sum1_kernel(const float* __restrict__ x, long long n, float* out
 int head_bwd_stats(const float* dprob, const float* prob, const float* A2, const float* Hd2, const float* mean, const float* rstd,
                    const float* w3, long long B, float scale, float* partial, float* dlogit, float* dgamma, float* dbeta, float* dw3,
                    float* db3, cudaStream_t st) {
-  int blocks = (int)std::min<long long>((B + 255) / 256, 4LL * num_sms());
-  head_dlogit_kernel<<<std::max(blocks, 1), 256, 0, st>>>(dprob, prob, B, dlogit);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((B + 1023) / 1024, 2LL * num_sms()));
+  double* dpart = reinterpret_cast<double*>(partial);        // <= 296 doubles; consumed before the column reduction reuses `partial`
+  head_dlogit_kernel<<<blocks, 256, 0, st>>>(dprob, prob, B, (B + blocks - 1) / blocks, dlogit, dpart);
   FBN_CHECK_LAUNCH();
-  sum1_kernel<<<1, 256, 0, st>>>(dlogit, B, db3);
+  sum1_kernel<<<1, 256, 0, st>>>(dpart, blocks, db3);
   FBN_CHECK_LAUNCH();
   ColArgs a{}; a.Y = A2; a.Z = Hd2; a.v0 = mean; a.v1 = rstd; a.v2 = w3; a.r0 = dlogit; a.scale = scale; a.B = B; a.N = H2;
   a.partial = partial;

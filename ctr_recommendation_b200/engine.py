@@ -87,6 +87,7 @@ class TrainStep:
         self.prob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.dprob = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._bce_scratch = torch.zeros(self.lib.fbn_bce_scratch_bytes(), dtype=torch.uint8, device=dev)   # partials + arrival counter
         # dropout stream position: ONE counter per model, shared by every engine that drives it (a tail-batch engine must not
         # replay the masks the main engine used at the same local step); model.set_dropout_counter(n) resumes a stream
         self.step_counter = model._dropout_counter(dev)
@@ -175,8 +176,8 @@ class TrainStep:
         st = _lib.stream_ptr()
         _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
                                    _lib.ptr(self.step_counter), _lib.ptr(self.prob), st), "fbn_forward")
-        _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
-                                    _lib.ptr(self.dprob), st), "fbn_bce_loss")
+        _lib.check(lib.fbn_bce_loss_ws(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
+                                       _lib.ptr(self.dprob), _lib.ptr(self._bce_scratch), self._bce_scratch.numel(), st), "fbn_bce_loss_ws")
         dense_table = m._dense_table_grad
         cur.wait_stream(self._side)            # join: the index is ready before the table gradient is summed
         _lib.check(lib.fbn_backward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, _lib.ptr(self.dprob),
@@ -196,8 +197,8 @@ class TrainStep:
         st = _lib.stream_ptr()
         _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
                                    _lib.ptr(self.step_counter), _lib.ptr(self.prob), st), "fbn_forward")
-        _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
-                                    _lib.ptr(self.dprob), st), "fbn_bce_loss")
+        _lib.check(lib.fbn_bce_loss_ws(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
+                                       _lib.ptr(self.dprob), _lib.ptr(self._bce_scratch), self._bce_scratch.numel(), st), "fbn_bce_loss_ws")
         cur.wait_stream(self._side)
         self._backward_phase(_lib.BWD_CHAIN)
 
@@ -435,8 +436,8 @@ class ShardedTrainStep(TrainStep):
         s = _lib.stream_ptr()
         _lib.check(lib.fbn_forward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, None, None, m._seed, 0,
                                    _lib.ptr(self.step_counter), _lib.ptr(self.prob), s), "fbn_forward")
-        _lib.check(lib.fbn_bce_loss(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
-                                    _lib.ptr(self.dprob), s), "fbn_bce_loss")
+        _lib.check(lib.fbn_bce_loss_ws(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
+                                       _lib.ptr(self.dprob), _lib.ptr(self._bce_scratch), self._bce_scratch.numel(), s), "fbn_bce_loss_ws")
         _lib.check(lib.fbn_backward(C.byref(P), C.byref(self._bs), _lib.ptr(ws), ws.numel(), 1, m.dropout_p, _lib.ptr(self.dprob),
                                     C.byref(G), _lib.ptr(m._gflat), m._gflat.numel(), None, None, 0, 1, _lib.ptr(m._grad_sumsq), s),
                    "fbn_backward")

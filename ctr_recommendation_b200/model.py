@@ -482,4 +482,13 @@ class MM_FiBiNET(nn.Module):
 
 
 def build_model(feature_map, model_cfg):
+    """The reference's factory (src/model_fibinet.py:201-202).  ``feature_map`` is None / ignored for the reference's six-field
+    model; a dict with a "fields" list selects the F-field model of general.py (BASELINE config 5)."""
+    from .general import GeneralFiBiNET, fields_from_feature_map
+    fields = fields_from_feature_map(feature_map)
+    if fields is not None:
+        fm = feature_map
+        return GeneralFiBiNET(fields, model_cfg, bilinear_type=fm.get("bilinear_type", "all"),
+                              senet_reduction=int(fm.get("senet_reduction", 2)), dropout=float(fm.get("dropout", 0.2)),
+                              precision=fm.get("precision", "tf32x3"))
     return MM_FiBiNET(feature_map, model_cfg)

@@ -187,6 +187,11 @@ int fbn_embed_index(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_
  * backward divides by max(p(1-p),1e-12)); loss_out (1,) / dprob_out (B,) may be NULL. */
 int fbn_bce_loss(const float* prob, const float* labels, int64_t batch, float loss_scale, float* loss_out,
                  float* dprob_out, fbn_stream_t stream);
+/* The same with a multi-block kernel (fixed-order final sum: deterministic) for large batches; scratch: fbn_bce_scratch_bytes()
+ * bytes, 8-byte aligned, ZERO-INITIALISED once by the caller (it holds the arrival counter, which every launch re-arms). */
+size_t fbn_bce_scratch_bytes(void);
+int fbn_bce_loss_ws(const float* prob, const float* labels, int64_t batch, float loss_scale, float* loss_out,
+                    float* dprob_out, void* scratch, size_t scratch_bytes, fbn_stream_t stream);
 
 /* clip_grad_norm_ coefficient (src/train_fibinet.py:119): coef = min(1, max_norm/(sqrt(sum)+1e-6)),
  * sum = sumsq[0] + ... + sumsq[n-1].  out (2,) = {total_norm, coef}. */
@@ -282,13 +287,44 @@ int fbn_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
 int fbn_ipc_open(const void* handle, void** base_out);
 int fbn_ipc_close(void* base);
 
+/* ---- F-field FiBiNET (BASELINE config 5: "scaled synthetic FiBiNET: 40 fields"): the building blocks of general.py --------------
+ * The reference hard-wires six fields (src/model_fibinet.py:112,179-182); its blocks are generic in F and are what is exposed
+ * here: F embedding lookups (one table per field, stored back to back in ONE (sum of vocabularies, 128) matrix), SENetLayer /
+ * BilinearInteraction for F <= 64 (fbn_senet_*, fbn_bilinear_*_ld) and the MLP tower for any input width K1 = (F + F(F-1)/2) * 128.
+ * Oracle: oracle/fibinet_general.py, pinned against the reference's own SENetLayer / BilinearInteraction classes. */
+
+/* x[b][f][:] = table[offsets[f] + ids[b][f]][:]   (nn.Embedding lookups, src/model_fibinet.py:155-159).  ids: (B,F) int32 / int64
+ * (idx_dtype FBN_IDX_I32 / FBN_IDX_I64); offsets: (F+1) int64 on the DEVICE, offsets[F] = total rows.  flag (4) int32 on the device:
+ * flag[0] is set when an id is outside [0, vocab_f) (the kernel clamps; the host raises IndexError). */
+int fbn_fields_gather(const float* table, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields,
+                      float* x, int32_t* flag, fbn_stream_t stream);
+/* Dense gradient of the lookups above (embedding_dense_backward): grad (rows,128) = scatter-add of dx (B,F,128), by the same
+ * deterministic sorted-segment sum as the item table (stable sort of the B*F global rows, one warp per row in source order, hot rows
+ * chunked).  zero_fill / row_touched / sumsq_out (1,) as in fbn_backward.  scratch: fbn_fields_scatter_bytes(batch, fields, rows). */
+size_t fbn_fields_scatter_bytes(int64_t batch, int fields, int64_t rows);
+int fbn_fields_scatter(const float* dx, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields, int64_t rows,
+                       float* grad, int32_t* row_touched, int zero_fill, float* sumsq_out, void* scratch, size_t scratch_bytes,
+                       fbn_stream_t stream);
+
+/* The MLP tower of the reference for an arbitrary input width k1 (src/model_fibinet.py:125-136,197-199): Linear(k1,512) -> BatchNorm1d ->
+ * ReLU -> Dropout -> Linear(512,256) -> BatchNorm1d -> ReLU -> Dropout -> Linear(256,1) -> sigmoid, and its backward.  Only the MLP
+ * fields of params / grads are read (w1 is (512,k1)).  c: (B,k1) fp32 MLP input; dc: (B,k1) gradient w.r.t. it.  The workspace
+ * (fbn_tower_workspace_bytes, zero-initialised once) keeps the activations between the two calls.  Semantics of train / dropout /
+ * masks / seed / step counter / dprob as in fbn_forward / fbn_backward; the same tcgen05 / SIMT GEMM back ends (params->precision). */
+size_t fbn_tower_workspace_bytes(int64_t batch, int64_t k1);
+int fbn_tower_forward(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes, int train,
+                      float dropout_p, const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset,
+                      const int32_t* step_counter_dev, float* prob_out, float* logit_out, fbn_stream_t stream);
+int fbn_tower_backward(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes, int train,
+                       float dropout_p, const float* dprob, const fbn_grads_t* g, float* dc, fbn_stream_t stream);
+
 /* sum of squares of n floats, deterministic; partial needs fbn_sumsq_partial_floats(n) floats;
  * out (1,) overwritten. */
 int fbn_sumsq(const float* x, int64_t n, float* partial, float* out, fbn_stream_t stream);
 size_t fbn_sumsq_partial_floats(int64_t n);
 
 /* Stand-alone SENetLayer (src/model_fibinet.py:5-35): x (B,F,D) -> y (B,F,D), gate (B,F).
- * F <= 32, hidden <= 32, D % 4 == 0. */
+ * F <= 64, hidden <= 64, D % 4 == 0. */
 int fbn_senet_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                   int64_t batch, int fields, int dim, int hidden, float* y, float* gate, fbn_stream_t stream);
 /* scratch: fbn_senet_scratch_bytes(batch, fields, hidden) bytes */
@@ -304,6 +340,15 @@ int fbn_bilinear_fwd(const float* v, const float* w, int type, int64_t batch, in
 int fbn_bilinear_bwd(const float* v, const float* w, const float* dp, int type, int64_t batch, int fields,
                      int dim, float* dv, float* dw, void* scratch, size_t scratch_bytes, int precision,
                      fbn_stream_t stream);
+
+/* Strided variants for the F-field model (general.py): the pair products are written straight into / read straight from the
+ * (B, (F+P)*dim) MLP-input buffer (row strides ldp / lddp in floats), and dv starts from dv_init (row stride ld_init; NULL = 0) --
+ * the gradient that reached the fields directly through the concat (src/model_fibinet.py:191-194). */
+int fbn_bilinear_fwd_ld(const float* v, const float* w, int type, int64_t batch, int fields, int dim, float* p, int64_t ldp,
+                        void* scratch, size_t scratch_bytes, int precision, fbn_stream_t stream);
+int fbn_bilinear_bwd_ld(const float* v, const float* w, const float* dp, int64_t lddp, const float* dv_init, int64_t ld_init,
+                        int type, int64_t batch, int fields, int dim, float* dv, float* dw, void* scratch, size_t scratch_bytes,
+                        int precision, fbn_stream_t stream);
 size_t fbn_bilinear_scratch_bytes(int64_t batch, int fields, int dim, int type);
 
 /* C[M,N] = op(A) * op(B) (+ bias[N]) in the given precision -- exposed for tests and benches.
