@@ -110,7 +110,7 @@ class GeneralFiBiNET(nn.Module):
         P.bilinear_type = _lib.BILINEAR_TYPES[self.bilinear.bilinear_type]
         return P
 
-    def _buffers(self, B: int) -> dict:
+    def _scratch(self, B: int) -> dict:
         buf = self._buf.get(B)
         if buf is None:
             lib, dev, F = _lib.load(), self.emb.weight.device, self.num_fields
@@ -162,7 +162,7 @@ class GeneralFiBiNET(nn.Module):
         lib, st = _lib.load(), _lib.stream_ptr()
         _require_cuda(self.emb.weight, "GeneralFiBiNET parameters")
         B, F = ids.shape
-        buf = self._buffers(B)
+        buf = self._scratch(B)
         idt = _lib.IDX_I32 if ids.dtype == torch.int32 else _lib.IDX_I64
         e0, e2 = self.senet.excitation[0], self.senet.excitation[2]
         R = self.senet.reduced_size

@@ -47,6 +47,15 @@ def _worker(rank, world, port, out):
     assert abs(wgt - weight) < 1e-12 and shard["item_seq"].shape == (hi - lo, 3)
     pred = fdist.gather_predictions(lab * 2)
     assert torch.equal(pred, torch.arange(n).float() * 2)            # rank order == original row order
+    # a tail batch so small that scatter chunking leaves the last rank without rows: weights still sum to 1, the empty rank still
+    # takes part in the prediction gather (src/train_fibinet.py drives TrainStep.step_empty / an empty tensor for it)
+    n1 = world - 1
+    b1 = {"item_id": torch.arange(n1)}
+    sh1, lab1, w1 = fdist.shard_batch(b1, torch.arange(n1).float(), rank, world)
+    wsum = torch.tensor([w1])
+    dist.all_reduce(wsum)
+    assert abs(wsum.item() - 1.0) < 1e-12 and (lab1.numel() == 0) == (rank == world - 1)
+    assert torch.equal(fdist.gather_predictions(lab1 + 5), torch.arange(n1).float() + 5)
     # row-sharded table host logic: slices -> all_gather -> the full table again; a model built with table_sharding="row"
     # holds exactly its slice of the replicated initialisation
     from ctr_recommendation_b200 import build_model, sharded
