@@ -62,6 +62,11 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: blocking gradient all-reduces between two graphs (A/B against "
                     "the default schedule that overlaps them with the weight-gradient GEMMs)")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="data parallel, overlapped: SMs the weight-gradient GEMMs leave to the collectives")
+    ap.add_argument("--phased", action="store_true", help="1 GPU: run the phased backward (chain / leaf 1 / leaf 2 graphs) without collectives")
+    ap.add_argument("--fields", type=int, default=0, help="F > 0: benchmark the F-field model of ctr_recommendation_b200/general.py "
+                    "(BASELINE config 5's 40 fields; one table per field, --field-vocab rows each) instead of the six-field model")
+    ap.add_argument("--field-vocab", type=int, default=100000)
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
 
@@ -195,7 +200,7 @@ def run_ours(args):
         engine = None if args.eager else (
             Scorer(model, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, use_mm_table=args.resident_mm) if infer else
             TrainStep(model, opt, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0, use_mm_table=args.resident_mm,
-                      overlap=False if args.no_overlap else None))
+                      overlap=False if args.no_overlap else (True if args.phased else None), reserve_sms=args.reserve_sms))
 
     def step(batch, labels):
         if infer:                    # scoring: forward only, predictions read back by the caller
@@ -546,9 +551,58 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def run_general(args):
+    """BASELINE config 5's field count on one GPU: GeneralFiBiNET (F lookups -> SENET -> bilinear -> (F + F(F-1)/2) * 128 wide MLP)
+    forward + BCELoss + backward + clip_grad_norm_(10) + torch.optim.Adam(fused) per step, ids resident on the device."""
+    from ctr_recommendation_b200 import GeneralFiBiNET, _lib
+    torch.cuda.set_device(0)
+    lib = _lib.load()
+    torch.manual_seed(2025)
+    F, V, B = args.fields, args.field_vocab, args.batch
+    model = GeneralFiBiNET([(f"f{i}", V) for i in range(F)], precision=args.precision, bilinear_type=args.bilinear).cuda().train()
+    model.check_ids_every_forward = False
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
+    loss_fn = torch.nn.BCELoss()
+    g = torch.Generator().manual_seed(7)
+    pool = [(torch.randint(0, V, (B, F), generator=g).cuda(), (torch.rand(B, generator=g) < 0.5).float().cuda()) for _ in range(args.pool)]
+
+    def step(k):
+        ids, y = pool[k % len(pool)]
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(model({"ids": ids}), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        return loss
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    n0 = lib.fbn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    model.check_ids()
+    P = F * (F - 1) // 2
+    flops = 3 * 2.0 * B * ((F + P) * 128 * 512 + 512 * 256 + 256)          # forward + two backward GEMMs per layer
+    out = {"metric": "train samples/sec F-field FiBiNET (general.py)", "value": B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
+           "config": {"workload": f"F-field FiBiNET train step, F={F} fields x {V}-row tables (one (F*V,128) parameter), {P} bilinear pairs "
+                                  f"({args.bilinear}), MLP {(F + P) * 128}-512-256-1, batch {B}, uniform ids; unfused building blocks + "
+                                  "torch.optim.Adam(fused)", "global_batch": B, "per_gpu_batch": B, "parallelism": "dp1"},
+           "gpu_launches": int(lib.fbn_launch_count() - n0), "mlp_tflops_useful": flops * args.steps / (ms / 1e3) / 1e12}
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.fields > 0:
+        run_general(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -176,6 +176,8 @@ def main():
         avg_loss = (total_loss.item() / steps) if steps else 0.0
         for k, e in engines.items():
             e.check_ids()                                  # IndexError for ids outside the tables, as nn.Embedding would raise
+            if row_sharded and k[0] == "t":
+                e.check()                                  # RuntimeError if the owner-side merge lists overflowed (rows would be dropped)
 
         model.eval()
         y_trues, y_preds = [], []
