@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: blocking gradient all-reduces between two graphs (A/B against "
                     "the default schedule that overlaps them with the weight-gradient GEMMs)")
+    ap.add_argument("--overlap", default=None, choices=["partial", "full"], help="data-parallel schedule (default: partial for batch >= 8192)")
     ap.add_argument("--reserve-sms", type=int, default=8, help="data parallel, overlapped: SMs the weight-gradient GEMMs leave to the collectives")
     ap.add_argument("--phased", action="store_true", help="1 GPU: run the phased backward (chain / leaf 1 / leaf 2 graphs) without collectives")
     ap.add_argument("--fields", type=int, default=0, help="F > 0: benchmark the F-field model of ctr_recommendation_b200/general.py "
@@ -154,7 +155,8 @@ def run_ours(args):
     from ctr_recommendation_b200 import build_model, FusedAdam, clip_grad_norm_, _lib
     from ctr_recommendation_b200 import dist as fdist
     import torch.distributed as dist
-    rank, local, world = fdist.init_from_env()
+    overlapped = not args.no_overlap and args.sharding != "row" and args.mode == "train" and not args.eager and args.batch >= 8192
+    rank, local, world = fdist.init_from_env(nccl_max_ctas=args.reserve_sms if overlapped else None)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
@@ -200,7 +202,7 @@ def run_ours(args):
         engine = None if args.eager else (
             Scorer(model, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, use_mm_table=args.resident_mm) if infer else
             TrainStep(model, opt, args.batch, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0, use_mm_table=args.resident_mm,
-                      overlap=False if args.no_overlap else (True if args.phased else None), reserve_sms=args.reserve_sms))
+                      overlap=False if args.no_overlap else args.overlap, reserve_sms=args.reserve_sms, phased_single=args.phased))
 
     def step(batch, labels):
         if infer:                    # scoring: forward only, predictions read back by the caller
@@ -301,8 +303,10 @@ def run_ours(args):
         "config": workload_config(args, world, infer, sharded, model._shard.item_rows if sharded else None),
         "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
         "dp_collectives": (None if world == 1 or sharded else
-                           ("blocking all-reduces" if not getattr(engine, "overlap", False) else
-                            "3 async all-reduces (table gradient, MLP-1 bucket, rest) overlapped with the weight-gradient GEMMs")),
+                           {False: "blocking all-reduces between the backward and update graphs",
+                            "partial": "table-gradient all-reduce overlapped with the leaf gradients (all but MLP-1's), then the dense all-reduce",
+                            "full": "3 async all-reduces (table gradient, MLP-1 bucket, rest) overlapped with the weight-gradient GEMMs"}[
+                               getattr(engine, "overlap", False)]),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 if not infer else 4 * args.batch},
         "gpu_launches": int(getattr(engine, "kernels_per_step", 0) * args.steps) if engine is not None else int(launches),

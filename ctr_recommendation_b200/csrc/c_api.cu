@@ -425,6 +425,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
 
 // split-K factor for a weight gradient on the tcgen05 path: with CTA-pair tiles the CTA count is 2 * clusters * splits;
 // choose the split that wastes the least of the last wave of 148 SMs
+namespace fbn { int tc_reserved_sms(); }
 static int pick_splits_pair(long long M, long long N, long long K, unsigned long long nmask, size_t max_floats) {
   // tiles of the persistent CTA-pair kernel: 256 rows x 2 LIVE 128-column blocks, walked by num_sms / 2 clusters
   long long nlive = 0;
@@ -432,7 +433,7 @@ static int pick_splits_pair(long long M, long long N, long long K, unsigned long
     if (nmask == ~0ull || ((nmask >> (n0 / 128)) & 1ull)) ++nlive;
   const long long clusters = cdiv(M, 256) * cdiv(nlive, 2);
   const long long kblocks = std::max<long long>(1, cdiv(K, 32));
-  const long long slots = std::max(1, num_sms() / 2);
+  const long long slots = std::max(1, (num_sms() - tc_reserved_sms()) / 2);   // clusters that can run at once
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= 32; ++s) {
@@ -527,8 +528,9 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
   }
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   const unsigned long long amask = active_mask();
-  // leaves run on the library's side stream when the whole pass is issued at once, else on the caller's stream
-  const bool par = all && side_ready(st);
+  // a leaf requested TOGETHER with the chain runs on the library's side stream, forked where its inputs become ready (so it
+  // fills in beside the data-gradient chain); a leaf requested without the chain runs on the caller's stream
+  const bool par = chain && (leaf1 || leaf2) && side_ready(st);
   cudaStream_t ls = par ? g_side.s : st;
   float* lp = par ? w.partial_side : w.partial;
   const int eb = embed_bwd_blocks(B);
@@ -589,8 +591,8 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
                      tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
     STAGE("bwd:head + bn2");
-    if (par) RC(side_fork(st, 0));
-    if (all) RC(leaf_layer2());
+    if (par && leaf2) RC(side_fork(st, 0));
+    if (leaf2) RC(leaf_layer2());
     {
       GemmArgs d;  // dA1 = dH2 * w2
       d.A = w.dH2; d.lda = H2; d.B = p->w2; d.ldb = H1; d.b_t = 0; d.C = w.dH1; d.ldc = H1; d.M = B; d.N = H1; d.K = H2;
@@ -602,8 +604,8 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
                      tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
     STAGE("bwd:bn1");
-    if (par) RC(side_fork(st, 1));
-    if (all) RC(leaf_layer1());
+    if (par && leaf1) RC(side_fork(st, 1));
+    if (leaf1) RC(leaf_layer1());
     {
       GemmArgs d;  // dC = dH1 * w1 (only the blocks that feed something)
       d.A = w.dH1; d.lda = H1; d.B = p->w1; d.ldb = K1; d.b_t = 0; d.C = w.dC; d.ldc = K1; d.M = B; d.N = K1; d.K = H1; d.nmask = amask;
@@ -633,8 +635,8 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
       }
     }
     STAGE("bwd:bilinear dgrad");
-    if (par) RC(side_fork(st, 2));
-    if (all) RC(leaf_bilinear());
+    if (par && leaf2) RC(side_fork(st, 2));
+    if (leaf2) RC(leaf_bilinear());
     // ---- SENET + field stack + projection ----
     EmbedBwdArgs e{};
     e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
@@ -644,8 +646,8 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     FBN_REQUIRE((size_t)eb * p->cate_rows * D <= (size_t)2 * 148 * 4 * MAX_CATE * D, FBN_ERR_ARG, "internal: cate scratch too small");
     RC(launch_embed_senet_bwd(e, eb, st));
     STAGE("bwd:embed+senet");
-    if (par) RC(side_fork(st, 3));
-    if (all) RC(leaf_embed());
+    if (par && leaf2) RC(side_fork(st, 3));
+    if (leaf2) RC(leaf_embed());
     // ---- embedding table rows ----
     if (item_grad) {
       EmbGradArgs eg = make_emb_args(p, b, w, row_touched);
@@ -657,15 +659,15 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     if (par) RC(side_join(st));     // every dense gradient is complete from here on
     STAGE("bwd:join side stream (leaf gradients)");
   }
-  if (!all) {
+  if (!chain) {
     if (leaf1) RC(leaf_layer1());
     if (leaf2) {
       RC(leaf_layer2());
       RC(leaf_bilinear());
       RC(leaf_embed());
     }
-    return FBN_OK;      // the host computes the gradient norms after its collectives
   }
+  if (!all) return FBN_OK;      // the host computes the gradient norms after its collectives
   if (dense_grad_flat) {
     FBN_REQUIRE(aligned16(dense_grad_flat), FBN_ERR_ALIGN, "dense_grad_flat is not 16-byte aligned");
     RC(sumsq(dense_grad_flat, dense_grad_n, w.partial, grad_sumsq, st));

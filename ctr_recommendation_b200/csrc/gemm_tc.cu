@@ -1269,6 +1269,7 @@ static int launch_tc2(const TcMaps& maps, const TcArgs& t, dim3 grid, cudaStream
 
 static int g_tc_reserve_sms = 0;
 void set_tc_reserve_sms(int n) { g_tc_reserve_sms = std::max(0, std::min(n, 64)); }
+int tc_reserved_sms() { return g_tc_reserve_sms; }
 
 template <int MODE, bool A_MN, bool B_MN>
 static int launch_tc2p(const TcMaps& maps, const TcArgs& t, cudaStream_t st) {

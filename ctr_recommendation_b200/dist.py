@@ -22,15 +22,19 @@ import torch.distributed as dist
 from . import _lib
 
 
-def init_from_env(backend: str | None = None):
-    """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT)."""
+def init_from_env(backend: str | None = None, nccl_max_ctas: int | None = None):
+    """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT).
+
+    ``nccl_max_ctas``: hold NCCL to that many CTAs per collective (NCCL_MAX_CTAS, unless the user already set it).  Pass the
+    ``reserve_sms`` of engine.TrainStep when its overlapped schedule is used: the gradient all-reduces then run BESIDE the
+    weight-gradient GEMMs, a collective CTA cannot share an SM with a 225 KB-smem GEMM CTA, and the GEMMs leave exactly that many SMs
+    free."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
-        # the gradient all-reduces run BESIDE the weight-gradient GEMMs (engine.TrainStep, overlap): a collective CTA cannot share an
-        # SM with a 225 KB-smem GEMM CTA, so the GEMMs leave `reserve_sms` SMs free and NCCL is held to that many CTAs
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        if nccl_max_ctas:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(int(nccl_max_ctas)))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:

@@ -60,10 +60,11 @@ class TrainStep:
 
     def __init__(self, model: MM_FiBiNET, optimizer: FusedAdam, batch_size: int, seq_len: int = 20, idx_dtype=torch.float64,
                  seq_dtype=torch.int64, max_norm: float | None = 10.0, use_mm_table: bool = False, graph: bool = True,
-                 global_batch: int | None = None, overlap: bool | None = None, reserve_sms: int = 8):
+                 global_batch: int | None = None, overlap=None, reserve_sms: int = 8, phased_single: bool = False):
         if not isinstance(model, MM_FiBiNET) or not isinstance(optimizer, (FusedAdam, FusedAdagrad)):
             raise TypeError("TrainStep needs a ctr_recommendation_b200 MM_FiBiNET and its FusedAdam / FusedAdagrad")
         self.model, self.opt, self.max_norm = model, optimizer, max_norm
+        self._want_phased = bool(phased_single)     # one rank: run the phased schedule anyway (tests / A-B runs), without collectives
         self.lib = _lib.load()
         model._ensure_flat()
         optimizer._ensure_state()
@@ -74,9 +75,15 @@ class TrainStep:
             model._dense_table_grad = True
         # overlap the gradient all-reduces with the weight-gradient GEMMs (4 graphs + 3 async collectives per step instead of 2 + 2
         # blocking ones): worth it once the leaf phase is long enough to hide a 47 MB all-reduce
-        self.overlap = (batch_size >= 8192) if overlap is None else bool(overlap)
+        if overlap is None:
+            overlap = "partial" if batch_size >= 8192 else False
+        elif overlap is True:
+            overlap = "partial"
+        if overlap not in (False, "partial", "full"):
+            raise ValueError("overlap must be None, False, True, 'partial' or 'full'")
+        self.overlap = overlap
         self.reserve_sms = int(reserve_sms)
-        self._phased_single = overlap is True and self.world == 1
+        self._phased_single = bool(overlap) and self.world == 1 and batch_size > 0 and getattr(self, "_want_phased", False)
         self._pending = []
         self.inp = _StaticBatch(batch_size, seq_len, idx_dtype, seq_dtype, dev, with_mm=not use_mm_table)
         if use_mm_table and model._mm_table is None:
@@ -135,16 +142,21 @@ class TrainStep:
         between them are captured into one CUDA graph."""
         if self.world == 1:
             if self.overlap and self._phased_single:      # test hook: the phased backward without collectives
-                return [(self._fwd_chain, None), (self._leaf1, None), (self._leaf2, None), (self._update, None)]
+                if self.overlap == "full":
+                    return [(self._fwd_chain, None), (self._leaf1, None), (self._leaf2, None), (self._update, None)]
+                return [(self._fwd_chain, None), (self._leaf2, None), (self._update, None)]
             return [(self._fwd_bwd, None), (self._update, None)]
         if not self.overlap:
             return [(self._fwd_bwd, self._allreduce), (self._update, None)]
-        # data parallel, overlapped (north_star (5)):  [forward + loss + data-gradient chain + table rows]
-        #   -> all-reduce(table gradient) starts          || [MLP-1 weight gradient]
-        #   -> all-reduce(MLP-1 bucket) starts            || [all other leaf gradients]
-        #   -> all-reduce(remaining dense gradients), wait for the three -> [norms + clip + Adam]
-        return [(self._fwd_chain, self._ar_table), (self._leaf1, self._ar_bucket1), (self._leaf2, self._ar_rest_wait),
-                (self._update, None)]
+        if self.overlap == "full":
+            # [forward + loss + data-gradient chain + table rows] -> all-reduce(table gradient) || [MLP-1 weight gradient]
+            #   -> all-reduce(MLP-1 bucket) || [all other leaf gradients] -> all-reduce(rest), wait for the three -> [norms + clip + Adam]
+            return [(self._fwd_chain, self._ar_table), (self._leaf1, self._ar_bucket1), (self._leaf2, self._ar_rest_wait),
+                    (self._update, None)]
+        # "partial" (default): the MLP-1 weight gradient keeps running beside the data-gradient chain on the side stream (that
+        # concurrency is worth more than hiding its bucket); the 47 MB table all-reduce overlaps the remaining leaf gradients
+        #   [forward + loss + chain + MLP-1 leaf + table rows] -> all-reduce(table) || [other leaves] -> all-reduce(dense), wait -> [update]
+        return [(self._fwd_chain, self._ar_table), (self._leaf2, self._ar_dense_wait), (self._update, None)]
 
     def _batch_struct(self):
         t = self.inp.t
@@ -200,7 +212,7 @@ class TrainStep:
         _lib.check(lib.fbn_bce_loss_ws(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
                                        _lib.ptr(self.dprob), _lib.ptr(self._bce_scratch), self._bce_scratch.numel(), st), "fbn_bce_loss_ws")
         cur.wait_stream(self._side)
-        self._backward_phase(_lib.BWD_CHAIN)
+        self._backward_phase(_lib.BWD_CHAIN if self.overlap == "full" else (_lib.BWD_CHAIN | _lib.BWD_LEAF1))
 
     def _backward_phase(self, phases, reserve=0):
         m, lib = self.model, self.lib
@@ -230,6 +242,13 @@ class TrainStep:
         import torch.distributed as dist
         m = self.model
         self._pending.append(dist.all_reduce(m._gflat[m._bucket1_offset():], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _ar_dense_wait(self):
+        import torch.distributed as dist
+        self._pending.append(dist.all_reduce(self.model._gflat, op=dist.ReduceOp.SUM, async_op=True))
+        for w in self._pending:
+            w.wait()
+        self._pending = []
 
     def _ar_rest_wait(self):
         import torch.distributed as dist
@@ -350,13 +369,16 @@ class TrainStep:
         return self.loss
 
     def _allreduce(self):
-        # the same collective sequence as the overlapped schedule (a rank without rows must match it call for call)
+        # the same collective sequence as this engine's overlapped schedule (a rank without rows must match it call for call)
         import torch.distributed as dist
         m = self.model
-        off = m._bucket1_offset()
         dist.all_reduce(m._item_grad, op=dist.ReduceOp.SUM)
-        dist.all_reduce(m._gflat[off:], op=dist.ReduceOp.SUM)
-        dist.all_reduce(m._gflat[:off], op=dist.ReduceOp.SUM)
+        if self.overlap == "full":
+            off = m._bucket1_offset()
+            dist.all_reduce(m._gflat[off:], op=dist.ReduceOp.SUM)
+            dist.all_reduce(m._gflat[:off], op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(m._gflat, op=dist.ReduceOp.SUM)
 
     def step_empty(self) -> torch.Tensor:
         """This rank received no rows of the global batch (torch's scatter chunking leaves the last ranks empty when

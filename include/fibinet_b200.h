@@ -170,8 +170,9 @@ int fbn_backward(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t w
  *   FBN_BWD_CHAIN : the data-gradient chain down to the embedding-table rows (item_grad / row_touched / grad_sumsq[1] as above,
  *                   plus the gradients computed along the chain: mlp.8.*, mlp.5.*, mlp.1.*);
  *   FBN_BWD_LEAF1 : mlp.0.weight / mlp.0.bias;   FBN_BWD_LEAF2 : every other parameter gradient.
- * Each call runs the requested phases on `stream` in that order; a later phase may be issued by a later call on the same
- * workspace (dprob is only read by CHAIN).  phases == CHAIN|LEAF1|LEAF2 is fbn_backward without the dense-gradient norm. */
+ * A leaf requested together with CHAIN runs beside it on the library's side stream (as in fbn_backward); a leaf requested by a later
+ * call on the same workspace runs on `stream` (dprob is only read by CHAIN).  phases == CHAIN|LEAF1|LEAF2 is fbn_backward without
+ * the dense-gradient norm. */
 enum { FBN_BWD_CHAIN = 1, FBN_BWD_LEAF1 = 2, FBN_BWD_LEAF2 = 4 };
 int fbn_backward_phase(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, int train,
                        float dropout_p, const float* dprob, const fbn_grads_t* g, float* item_grad, int32_t* row_touched,

@@ -77,7 +77,10 @@ def main():
     set_seed(model_cfg.get("seed", 2025))
     if not torch.cuda.is_available():
         raise SystemExit("train_fibinet.py: no CUDA device -- this implementation has no CPU path (sm_100a kernels only)")
-    rank, local, world = fdist.init_from_env()
+    # `dp_overlap: false` in the run config: blocking gradient all-reduces (default: overlapped with the leaf gradients once the
+    # per-rank batch is >= 8192; the collectives then get 8 SMs and the weight-gradient GEMMs leave those free)
+    dp_overlap = bool(model_cfg.get("dp_overlap", True))
+    rank, local, world = fdist.init_from_env(nccl_max_ctas=8 if dp_overlap else None)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     log = print if rank == 0 else (lambda *a, **k: None)
@@ -123,7 +126,8 @@ def main():
         key = ("t", rows, L, dtype, n_global)
         if key not in engines:
             cls = ShardedTrainStep if row_sharded else TrainStep
-            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True, global_batch=n_global)
+            kw = {} if row_sharded else {"overlap": None if dp_overlap else False}
+            engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True, global_batch=n_global, **kw)
         return engines[key]
 
     def score_engine(rows, L, dtype):

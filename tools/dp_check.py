@@ -43,7 +43,7 @@ def main():
     def engine(rows, n):
         if (rows, n) not in engines:
             engines[(rows, n)] = TrainStep(model, opt, rows, 20, idx_dtype=torch.float64, global_batch=n,
-                                           overlap=os.environ.get("DP_OVERLAP", "1") == "1")
+                                           overlap={"0": False, "1": "partial", "full": "full"}[os.environ.get("DP_OVERLAP", "1")])
         return engines[(rows, n)]
     batches = [synth.make_batch(seed=700 + s, batch=B, id_dist="zipf", index_dtype=np.float64, edge_cases=B >= 8)
                for s, B in enumerate(sizes)]
@@ -114,7 +114,7 @@ def main():
             rel = d.mean().item()
             worst = max(worst, rel)
             assert rel <= 0.05 * 5e-4, (k, rel)
-        print(f"dp_check OK (collectives {'overlapped with the leaf gradients' if os.environ.get('DP_OVERLAP', '1') == '1' else 'blocking'}): {world} ranks, global batches {sizes} (uneven + empty-shard tails), replicas identical, first-step all-reduced gradients within {grad_worst:.2e} (rel) of the "
+        print(f"dp_check OK (collectives {os.environ.get('DP_OVERLAP', '1')}): {world} ranks, global batches {sizes} (uneven + empty-shard tails), replicas identical, first-step all-reduced gradients within {grad_worst:.2e} (rel) of the "
               f"single-process DataParallel emulation, worst mean |weight diff| after {steps} steps {worst:.2e}")
     dist.barrier()
     dist.destroy_process_group()
