@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: blocking gradient all-reduces between two graphs (A/B against "
                     "the default schedule that overlaps them with the weight-gradient GEMMs)")
-    ap.add_argument("--overlap", default=None, choices=["partial", "full"], help="data-parallel schedule (default: partial for batch >= 8192)")
+    ap.add_argument("--overlap", default=None, choices=["partial", "full", "wgrad"], help="data-parallel schedule (default: partial for batch >= 8192)")
     ap.add_argument("--reserve-sms", type=int, default=8, help="data parallel, overlapped: SMs the weight-gradient GEMMs leave to the collectives")
     ap.add_argument("--phased", action="store_true", help="1 GPU: run the phased backward (chain / leaf 1 / leaf 2 graphs) without collectives")
     ap.add_argument("--fields", type=int, default=0, help="F > 0: benchmark the F-field model of ctr_recommendation_b200/general.py "
@@ -305,6 +305,7 @@ def run_ours(args):
         "dp_collectives": (None if world == 1 or sharded else
                            {False: "blocking all-reduces between the backward and update graphs",
                             "partial": "table-gradient all-reduce overlapped with the leaf gradients (all but MLP-1's), then the dense all-reduce",
+                            "wgrad": "table + small-bucket all-reduces overlapped with the MLP-1 weight gradient, then the MLP-1 bucket",
                             "full": "3 async all-reduces (table gradient, MLP-1 bucket, rest) overlapped with the weight-gradient GEMMs"}[
                                getattr(engine, "overlap", False)]),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,

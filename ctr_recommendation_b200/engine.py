@@ -79,8 +79,8 @@ class TrainStep:
             overlap = "partial" if batch_size >= 8192 else False
         elif overlap is True:
             overlap = "partial"
-        if overlap not in (False, "partial", "full"):
-            raise ValueError("overlap must be None, False, True, 'partial' or 'full'")
+        if overlap not in (False, "partial", "full", "wgrad"):
+            raise ValueError("overlap must be None, False, True, 'partial', 'full' or 'wgrad'")
         self.overlap = overlap
         self.reserve_sms = int(reserve_sms)
         self._phased_single = bool(overlap) and self.world == 1 and batch_size > 0 and getattr(self, "_want_phased", False)
@@ -144,6 +144,8 @@ class TrainStep:
             if self.overlap and self._phased_single:      # test hook: the phased backward without collectives
                 if self.overlap == "full":
                     return [(self._fwd_chain, None), (self._leaf1, None), (self._leaf2, None), (self._update, None)]
+                if self.overlap == "wgrad":
+                    return [(self._fwd_chain, None), (self._leaf1, None), (self._update, None)]
                 return [(self._fwd_chain, None), (self._leaf2, None), (self._update, None)]
             return [(self._fwd_bwd, None), (self._update, None)]
         if not self.overlap:
@@ -153,6 +155,12 @@ class TrainStep:
             #   -> all-reduce(MLP-1 bucket) || [all other leaf gradients] -> all-reduce(rest), wait for the three -> [norms + clip + Adam]
             return [(self._fwd_chain, self._ar_table), (self._leaf1, self._ar_bucket1), (self._leaf2, self._ar_rest_wait),
                     (self._update, None)]
+        if self.overlap == "wgrad":
+            # every leaf except MLP-1's stays interleaved with the data-gradient chain; the table all-reduce (47 MB) and the small
+            # dense bucket then run beside the MLP-1 weight gradient (0.5 ms of tensor work), only the MLP-1 bucket is exposed
+            #   [forward + loss + chain + small leaves + table rows] -> all-reduce(table), all-reduce(rest) || [MLP-1 leaf]
+            #   -> all-reduce(MLP-1 bucket), wait for the three -> [update]
+            return [(self._fwd_chain, self._ar_table_rest), (self._leaf1, self._ar_bucket1_wait), (self._update, None)]
         # "partial" (default): the MLP-1 weight gradient keeps running beside the data-gradient chain on the side stream (that
         # concurrency is worth more than hiding its bucket); the 47 MB table all-reduce overlaps the remaining leaf gradients
         #   [forward + loss + chain + MLP-1 leaf + table rows] -> all-reduce(table) || [other leaves] -> all-reduce(dense), wait -> [update]
@@ -212,7 +220,7 @@ class TrainStep:
         _lib.check(lib.fbn_bce_loss_ws(_lib.ptr(self.prob), _lib.ptr(self.inp.labels), self.B, self.loss_weight, _lib.ptr(self.loss),
                                        _lib.ptr(self.dprob), _lib.ptr(self._bce_scratch), self._bce_scratch.numel(), st), "fbn_bce_loss_ws")
         cur.wait_stream(self._side)
-        self._backward_phase(_lib.BWD_CHAIN if self.overlap == "full" else (_lib.BWD_CHAIN | _lib.BWD_LEAF1))
+        self._backward_phase({"full": _lib.BWD_CHAIN, "wgrad": _lib.BWD_CHAIN | _lib.BWD_LEAF2}.get(self.overlap, _lib.BWD_CHAIN | _lib.BWD_LEAF1))
 
     def _backward_phase(self, phases, reserve=0):
         m, lib = self.model, self.lib
@@ -242,6 +250,20 @@ class TrainStep:
         import torch.distributed as dist
         m = self.model
         self._pending.append(dist.all_reduce(m._gflat[m._bucket1_offset():], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _ar_table_rest(self):
+        import torch.distributed as dist
+        m = self.model
+        self._pending = [dist.all_reduce(m._item_grad, op=dist.ReduceOp.SUM, async_op=True),
+                         dist.all_reduce(m._gflat[:m._bucket1_offset()], op=dist.ReduceOp.SUM, async_op=True)]
+
+    def _ar_bucket1_wait(self):
+        import torch.distributed as dist
+        m = self.model
+        self._pending.append(dist.all_reduce(m._gflat[m._bucket1_offset():], op=dist.ReduceOp.SUM, async_op=True))
+        for w in self._pending:
+            w.wait()
+        self._pending = []
 
     def _ar_dense_wait(self):
         import torch.distributed as dist
@@ -377,6 +399,10 @@ class TrainStep:
             off = m._bucket1_offset()
             dist.all_reduce(m._gflat[off:], op=dist.ReduceOp.SUM)
             dist.all_reduce(m._gflat[:off], op=dist.ReduceOp.SUM)
+        elif self.overlap == "wgrad":
+            off = m._bucket1_offset()
+            dist.all_reduce(m._gflat[:off], op=dist.ReduceOp.SUM)
+            dist.all_reduce(m._gflat[off:], op=dist.ReduceOp.SUM)
         else:
             dist.all_reduce(m._gflat, op=dist.ReduceOp.SUM)
 

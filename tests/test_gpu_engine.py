@@ -183,7 +183,7 @@ def test_fused_adagrad_vs_oracle(gpu, wd, engine):
     assert moved.size > 0
 
 
-@pytest.mark.parametrize("schedule", ["partial", "full"])
+@pytest.mark.parametrize("schedule", ["partial", "full", "wgrad"])
 def test_phased_backward_equals_single_call(gpu, schedule):
     """fbn_backward_phase (the schedules the data-parallel engine interleaves with its gradient all-reduces: CHAIN [+ LEAF1 beside it],
     then the remaining leaves) produces bit-identical gradients, weights and moments to the single fbn_backward call -- same kernels,

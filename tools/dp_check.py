@@ -43,7 +43,7 @@ def main():
     def engine(rows, n):
         if (rows, n) not in engines:
             engines[(rows, n)] = TrainStep(model, opt, rows, 20, idx_dtype=torch.float64, global_batch=n,
-                                           overlap={"0": False, "1": "partial", "full": "full"}[os.environ.get("DP_OVERLAP", "1")])
+                                           overlap={"0": False, "1": "partial", "full": "full", "wgrad": "wgrad"}[os.environ.get("DP_OVERLAP", "1")])
         return engines[(rows, n)]
     batches = [synth.make_batch(seed=700 + s, batch=B, id_dist="zipf", index_dtype=np.float64, edge_cases=B >= 8)
                for s, B in enumerate(sizes)]
