@@ -62,8 +62,8 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="fbn_set_option knob, e.g. tc_persistent=-1 (A/B runs)")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: blocking gradient all-reduces between two graphs (A/B against "
                     "the default schedule that overlaps them with the weight-gradient GEMMs)")
-    ap.add_argument("--overlap", default=None, choices=["partial", "full", "wgrad"], help="data-parallel schedule (default: partial for batch >= 8192)")
-    ap.add_argument("--reserve-sms", type=int, default=8, help="data parallel, overlapped: SMs the weight-gradient GEMMs leave to the collectives")
+    ap.add_argument("--overlap", default=None, choices=["partial", "full", "wgrad"], help="data-parallel schedule (default: wgrad from 4 ranks and 8192 rows per rank, else blocking)")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="data parallel, overlapped: SMs the weight-gradient GEMMs leave to the collectives")
     ap.add_argument("--phased", action="store_true", help="1 GPU: run the phased backward (chain / leaf 1 / leaf 2 graphs) without collectives")
     ap.add_argument("--fields", type=int, default=0, help="F > 0: benchmark the F-field model of ctr_recommendation_b200/general.py "
                     "(BASELINE config 5's 40 fields; one table per field, --field-vocab rows each) instead of the six-field model")
@@ -155,7 +155,9 @@ def run_ours(args):
     from ctr_recommendation_b200 import build_model, FusedAdam, clip_grad_norm_, _lib
     from ctr_recommendation_b200 import dist as fdist
     import torch.distributed as dist
-    overlapped = not args.no_overlap and args.sharding != "row" and args.mode == "train" and not args.eager and args.batch >= 8192
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    overlapped = (not args.no_overlap and args.sharding != "row" and args.mode == "train" and not args.eager and args.batch >= 8192
+                  and (args.overlap is not None or world_env >= 4))
     rank, local, world = fdist.init_from_env(nccl_max_ctas=args.reserve_sms if overlapped else None)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

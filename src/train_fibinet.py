@@ -77,10 +77,12 @@ def main():
     set_seed(model_cfg.get("seed", 2025))
     if not torch.cuda.is_available():
         raise SystemExit("train_fibinet.py: no CUDA device -- this implementation has no CPU path (sm_100a kernels only)")
-    # `dp_overlap: false` in the run config: blocking gradient all-reduces (default: overlapped with the leaf gradients once the
-    # per-rank batch is >= 8192; the collectives then get 8 SMs and the weight-gradient GEMMs leave those free)
+    # `dp_overlap: false` in the run config: blocking gradient all-reduces (default: from 4 ranks and 8192 rows per rank the table
+    # all-reduce runs beside the MLP-1 weight gradient; the collectives then get 16 SMs and the GEMMs leave those free)
     dp_overlap = bool(model_cfg.get("dp_overlap", True))
-    rank, local, world = fdist.init_from_env(nccl_max_ctas=8 if dp_overlap else None)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    overlapping = dp_overlap and world_env >= 4 and int(model_cfg.get("batch_size", 4096)) // max(world_env, 1) >= 8192
+    rank, local, world = fdist.init_from_env(nccl_max_ctas=16 if overlapping else None)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     log = print if rank == 0 else (lambda *a, **k: None)
