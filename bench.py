@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--fields", type=int, default=0, help="F > 0: benchmark the F-field model of ctr_recommendation_b200/general.py "
                     "(BASELINE config 5's 40 fields; one table per field, --field-vocab rows each) instead of the six-field model")
     ap.add_argument("--field-vocab", type=int, default=100000)
+    ap.add_argument("--shard-rows-per-gpu", type=int, default=int(os.environ.get("FBN_BENCH_SHARD_ROWS", "12500000")),
+                    help="N > 1: after the replicated-table measurement the same bench line gets a `sharded` block -- the item table with "
+                         "this many rows PER GPU (12.5 M x 8 = BASELINE config 5's 100 M rows) row-sharded over the ranks; 0 disables it")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches through autograd instead of the CUDA-graph TrainStep")
     return ap.parse_args()
 
@@ -347,6 +350,8 @@ def run_ours(args):
                           "e2e": {"value": 4096 * n1 / (ms1e / 1e3), "unit": UNIT, "ms_per_step": ms1e / n1,
                                   "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pool1[0][0].values()) + 4096 * 4,
                                   "d2h_bytes_per_step": 4}}
+    if world > 1 and not infer and not sharded and engine is not None and args.shard_rows_per_gpu > 0:
+        out["sharded"] = sharded_block(args, rank, world, dev, out, timed)
     if rank == 0:
         out.update(kernels)
         if world == 1 and not args.no_cpu_baseline:
@@ -355,6 +360,56 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_block(args, rank, world, dev, main_line, timed):
+    """BASELINE config 5's table on the same ranks: the item table (--shard-rows-per-gpu x N rows) row-sharded by id % N, remote
+    gather over NVLink inside the forward kernel, owner-side gradient merge, lazy row Adam (engine.ShardedTrainStep).  Reported as a
+    block of the main line so that every multi-GPU run of the bench carries it.  A watchdog prints the main line without the block
+    and ends every rank if this secondary measurement ever stalls -- it must not be able to take the headline number with it."""
+    from ctr_recommendation_b200 import build_model, FusedAdam
+    from ctr_recommendation_b200 import dist as fdist
+    from ctr_recommendation_b200.engine import ShardedTrainStep
+
+    def bail():
+        if rank == 0:
+            line = dict(main_line)
+            line["sharded"] = {"error": "the row-sharded block did not finish within 420 s"}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    dog = threading.Timer(420.0, bail)
+    dog.daemon = True
+    dog.start()
+    try:
+        rows = int(args.shard_rows_per_gpu) * world
+        a2 = argparse.Namespace(**vars(args))
+        a2.item_rows, a2.sharding, a2.lazy = rows, "row", True
+        t0 = time.perf_counter()
+        model = build_model({"precision": args.precision, "table_sharding": "row", "item_rows": rows}, {"embedding_dim": 128}).to(dev).train()
+        fdist.broadcast_parameters(model)
+        opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+        eng = ShardedTrainStep(model, opt, args.batch, L_HIST, idx_dtype=torch.float64, max_norm=10.0, lazy=True,
+                               merge_cap=4 * args.batch * (1 + L_HIST))
+        pool = make_pool(a2, rank, 2)
+        dev_pool = [({k: v.to(dev) for k, v in b.items()}, y.to(dev)) for b, y in pool]
+        setup_s = time.perf_counter() - t0
+        steps = max(3, min(args.steps, 10))
+
+        def res(k):
+            eng(*dev_pool[k % len(dev_pool)])
+        for k in range(3):
+            res(k)
+        ms = timed(res, steps)
+        st = model._shard.stats()
+        blk = {"config": workload_config(a2, world, False, True, rows), "value": args.batch * world * steps / (ms / 1e3), "unit": UNIT,
+               "steps": steps, "ms_per_step": ms / steps, "item_rows": rows, "rows_per_gpu": int(model._shard.shard_rows),
+               "table_and_moments_gb_per_gpu": round(model._shard.shard_rows * 128 * 4 * 3 / 1e9, 2), "optimizer": "lazy row Adam",
+               "merge_overflow": bool(st["overflow"]), "setup_s": round(setup_s, 1)}
+        return blk       # (the slices stay allocated: peers hold CUDA IPC mappings of them until the process ends)
+    except Exception as e:      # never lose the headline line to the secondary measurement
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        dog.cancel()
 
 
 def kernel_rooflines(args, model, dev_batch, peaks, lib):
