@@ -15,7 +15,7 @@
 namespace fbn {
 
 constexpr int EMB_WARPS = 8;
-constexpr int EMB_SPW = 2;  // samples per warp per iteration (register-blocks the projection)
+constexpr int EMB_SPW = 4;  // samples per warp per iteration (register-blocks the projection)
 
 
 // smem: Wt[128][128] (k-major copy of mm_w so lane j reads W[4j..4j+3][k] as one float4)
@@ -141,6 +141,9 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
       if (EMB_SPW == 2) {
         const float2 t = *reinterpret_cast<const float2*>(xs + k * EMB_SPW);
         xv[0] = t.x; xv[EMB_SPW - 1] = t.y;
+      } else if (EMB_SPW == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(xs + k * EMB_SPW);
+        xv[0] = t.x; xv[1 % EMB_SPW] = t.y; xv[2 % EMB_SPW] = t.z; xv[3 % EMB_SPW] = t.w;
       } else {
 #pragma unroll
         for (int s = 0; s < EMB_SPW; ++s) xv[s] = xs[k * EMB_SPW + s];
