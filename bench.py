@@ -185,7 +185,7 @@ def run_ours(args):
         from oracle import synth as _synth
         model.attach_mm_table(torch.from_numpy(_synth.make_item_mm_table(seed=11)))
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
-    total_steps = max(10, 12 * (args.steps + args.warmup) * 2 + 64)
+    total_steps = max(10, 40 * (args.steps + args.warmup) * 2 + 512)
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-2, total_steps=total_steps, pct_start=0.3, div_factor=25.0,
                                                 final_div_factor=1000.0)
     loss_fn = torch.nn.BCELoss()
@@ -352,6 +352,8 @@ def run_ours(args):
                                   "d2h_bytes_per_step": 4}}
     if world > 1 and not infer and not sharded and engine is not None and args.shard_rows_per_gpu > 0:
         out["sharded"] = sharded_block(args, rank, world, dev, out, timed)
+    if world == 1 and not infer and not sharded and engine is not None and not args.no_config1 and not args.resident_mm:
+        out.update(extra_blocks(args, model, opt, sched, dev, timed, idt, sdt))
     if rank == 0:
         out.update(kernels)
         if world == 1 and not args.no_cpu_baseline:
@@ -613,20 +615,18 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def run_general(args):
+def general_measure(precision, bilinear, F, V, B, steps, warmup, pool_n=2):
     """BASELINE config 5's field count on one GPU: GeneralFiBiNET (F lookups -> SENET -> bilinear -> (F + F(F-1)/2) * 128 wide MLP)
     forward + BCELoss + backward + clip_grad_norm_(10) + torch.optim.Adam(fused) per step, ids resident on the device."""
     from ctr_recommendation_b200 import GeneralFiBiNET, _lib
-    torch.cuda.set_device(0)
     lib = _lib.load()
     torch.manual_seed(2025)
-    F, V, B = args.fields, args.field_vocab, args.batch
-    model = GeneralFiBiNET([(f"f{i}", V) for i in range(F)], precision=args.precision, bilinear_type=args.bilinear).cuda().train()
+    model = GeneralFiBiNET([(f"f{i}", V) for i in range(F)], precision=precision, bilinear_type=bilinear).cuda().train()
     model.check_ids_every_forward = False
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
     loss_fn = torch.nn.BCELoss()
     g = torch.Generator().manual_seed(7)
-    pool = [(torch.randint(0, V, (B, F), generator=g).cuda(), (torch.rand(B, generator=g) < 0.5).float().cuda()) for _ in range(args.pool)]
+    pool = [(torch.randint(0, V, (B, F), generator=g).cuda(), (torch.rand(B, generator=g) < 0.5).float().cuda()) for _ in range(pool_n)]
 
     def step(k):
         ids, y = pool[k % len(pool)]
@@ -636,13 +636,13 @@ def run_general(args):
         torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
         opt.step()
         return loss
-    for k in range(args.warmup):
+    for k in range(warmup):
         step(k)
     torch.cuda.synchronize()
     n0 = lib.fbn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
+    for k in range(steps):
         step(k)
     e1.record()
     torch.cuda.synchronize()
@@ -650,14 +650,107 @@ def run_general(args):
     model.check_ids()
     P = F * (F - 1) // 2
     flops = 3 * 2.0 * B * ((F + P) * 128 * 512 + 512 * 256 + 256)          # forward + two backward GEMMs per layer
-    out = {"metric": "train samples/sec F-field FiBiNET (general.py)", "value": B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": 1,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    return {"value": B * steps / (ms / 1e3), "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+            "config": {"workload": f"F-field FiBiNET train step (ctr_recommendation_b200/general.py), F={F} fields x {V}-row tables (one "
+                                   f"(F*V,128) parameter), {P} bilinear pairs ({bilinear}), MLP {(F + P) * 128}-512-256-1, batch {B}, uniform "
+                                   "ids; unfused building blocks + torch.optim.Adam(fused)", "global_batch": B, "per_gpu_batch": B,
+                       "parallelism": "dp1"},
+            "gpu_launches": int(lib.fbn_launch_count() - n0), "mlp_tflops_useful": flops * steps / (ms / 1e3) / 1e12}
+
+
+def run_general(args):
+    torch.cuda.set_device(0)
+    r = general_measure(args.precision, args.bilinear, args.fields, args.field_vocab, args.batch, args.steps, args.warmup, args.pool)
+    out = {"metric": "train samples/sec F-field FiBiNET (general.py)", "value": r["value"], "unit": UNIT, "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
-           "config": {"workload": f"F-field FiBiNET train step, F={F} fields x {V}-row tables (one (F*V,128) parameter), {P} bilinear pairs "
-                                  f"({args.bilinear}), MLP {(F + P) * 128}-512-256-1, batch {B}, uniform ids; unfused building blocks + "
-                                  "torch.optim.Adam(fused)", "global_batch": B, "per_gpu_batch": B, "parallelism": "dp1"},
-           "gpu_launches": int(lib.fbn_launch_count() - n0), "mlp_tflops_useful": flops * args.steps / (ms / 1e3) / 1e12}
+           "config": r["config"], "gpu_launches": r["gpu_launches"], "mlp_tflops_useful": r["mlp_tflops_useful"]}
     print(json.dumps(out), flush=True)
+
+
+def extra_blocks(args, model, opt, sched, dev, timed, idt, sdt):
+    """More of BASELINE's configurations inside the single-GPU line, so that every run of the bench carries them:
+    `sweep` (config 2: batch 1K-64K, bilinear all / each / interaction, bf16), `infer` (config 3: the Prediction.py loop body) and
+    `fields40` (config 5's field count on the F-field model).  Resident inputs, CUDA-event timed, a few seconds each."""
+    from ctr_recommendation_b200 import build_model, FusedAdam
+    from ctr_recommendation_b200.engine import Scorer, TrainStep
+    blocks = {}
+    n = max(args.steps, 10)
+
+    def train_rate(m, o, sc, B, precision_note=None):
+        a = argparse.Namespace(**vars(args))
+        a.batch = B
+        pool = make_pool(a, 0, 2)
+        dp = [({k: v.to(dev) for k, v in b.items()}, y.to(dev)) for b, y in pool]
+        eng = TrainStep(m, o, B, L_HIST, idx_dtype=idt, seq_dtype=sdt, max_norm=10.0)
+
+        def res(k):
+            eng(*dp[k % 2])
+            sc.step()
+        steps = n if B >= 16384 else 4 * n
+        for k in range(3):
+            res(k)
+        ms = timed(res, steps)
+        return {"per_gpu_batch": B, "value": B * steps / (ms / 1e3), "ms_per_step": ms / steps, "launches_per_step": int(eng.kernels_per_step)}
+    try:
+        sweep = []
+        for B in (1024, 4096, 16384):
+            if B != args.batch:
+                r = train_rate(model, opt, sched, B)
+                r.update(bilinear=args.bilinear, precision=args.precision)
+                sweep.append(r)
+        for bil, prec in (("each", args.precision), ("interaction", args.precision), ("all", "bf16")):
+            m2 = build_model({"precision": prec, "bilinear_type": bil}, {"embedding_dim": 128}).to(dev).train()
+            o2 = FusedAdam(m2, lr=1e-3, weight_decay=1e-5)
+            s2 = torch.optim.lr_scheduler.OneCycleLR(o2, max_lr=1e-2, total_steps=100000)
+            r = train_rate(m2, o2, s2, 16384)
+            r.update(bilinear=bil, precision=prec)
+            sweep.append(r)
+            del m2, o2
+        blocks["sweep"] = {"unit": UNIT, "what": "BASELINE config 2: train step, resident inputs; the headline line is the 65536 / all point", "points": sweep}
+    except Exception as e:
+        blocks["sweep"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    try:
+        model.eval()
+        inf = []
+        for B in (8192, 65536):
+            a = argparse.Namespace(**vars(args))
+            a.batch = B
+            pool = make_pool(a, 0, 2)
+            hp = [b for b, _ in pool]
+            dp = [{k: v.to(dev) for k, v in b.items()} for b in hp]
+            sc = Scorer(model, B, L_HIST, idx_dtype=idt, seq_dtype=sdt)
+            steps = 4 * n
+
+            def res(k):
+                sc(dp[k % 2])
+
+            def e2e(k):
+                if not sc._prefetched:
+                    sc.prefetch(hp[k % 2])
+                p = sc()
+                sc.prefetch(hp[(k + 1) % 2])
+                return p.cpu()
+            for k in range(3):
+                res(k)
+            ms = timed(res, steps)
+            for k in range(2):
+                e2e(k)
+            ms2 = timed(e2e, steps)
+            inf.append({"batch": B, "value": B * steps / (ms / 1e3), "e2e_value": B * steps / (ms2 / 1e3), "ms_per_batch": ms / steps,
+                        "h2d_bytes_per_batch": sum(v.numel() * v.element_size() for v in hp[0].values()), "d2h_bytes_per_batch": 4 * B})
+        blocks["infer"] = {"unit": UNIT, "what": "BASELINE config 3: eval forward (Prediction.py loop body; 8192 is the script's batch), one "
+                                                  "CUDA-graph replay per batch; e2e = pinned host batches in the loader's format + predictions read back",
+                           "points": inf}
+    except Exception as e:
+        blocks["infer"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        model.train()
+    try:
+        blocks["fields40"] = general_measure(args.precision, "all", 40, 100000, 4096, 5, 2)
+    except Exception as e:
+        blocks["fields40"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return blocks
 
 
 if __name__ == "__main__":
