@@ -15,7 +15,7 @@
 namespace fbn {
 
 constexpr int EMB_WARPS = 8;
-constexpr int EMB_SPW = 4;  // samples per warp per iteration (register-blocks the projection)
+constexpr int EMB_SPW = 2;  // samples per warp per iteration (register-blocks the projection; 4 measured: 250 vs 254 us at B = 65536 but 42 vs 31 us at 4096 -- half the CTAs)
 
 
 // smem: Wt[128][128] (k-major copy of mm_w so lane j reads W[4j..4j+3][k] as one float4)
