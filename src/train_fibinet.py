@@ -128,7 +128,9 @@ def main():
         key = ("t", rows, L, dtype, n_global)
         if key not in engines:
             cls = ShardedTrainStep if row_sharded else TrainStep
-            kw = {} if row_sharded else {"overlap": None if dp_overlap else False}
+            # ONE collective schedule per run (a rank left without rows replays it through another engine: every engine must issue
+            # the same sequence of all-reduces)
+            kw = {} if row_sharded else {"overlap": "wgrad" if overlapping else False}
             engines[key] = cls(model, optimizer, rows, L, idx_dtype=dtype, max_norm=10.0, use_mm_table=True, global_batch=n_global, **kw)
         return engines[key]
 
