@@ -34,7 +34,7 @@ class Params(C.Structure):
     _fields_ = [("item_emb", _vp), ("item_rows", _i64), ("cate_emb", _vp), ("cate_rows", _i64)] + \
                [(n, _vp) for n in PARAM_FIELDS[2:]] + [("bilinear_type", _i32), ("precision", _i32),
                                                        ("n_shards", _i32), ("shard_rank", _i32), ("shard_rows", _i64),
-                                                       ("shard", _vp * 16)]
+                                                       ("shard", _vp * 16), ("se_hidden", _i32)]
 
 
 class Grads(C.Structure):

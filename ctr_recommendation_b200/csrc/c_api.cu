@@ -104,7 +104,7 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   pf = std::max<size_t>(pf, (size_t)2 * 148 * 4 * MAX_CATE * D);
   pf = std::max<size_t>(pf, (size_t)4 * 148 * 3 * H1);
   pf = std::max<size_t>(pf, (size_t)cdiv(rows, 8) + 1024);
-  pf = std::max<size_t>(pf, (size_t)1024 * 48);
+  pf = std::max<size_t>(pf, (size_t)1024 * 96);
   w.partial_floats = pf;
   w.partial = (float*)take(pf * f);
   w.partial_side = (float*)take(pf * f);
@@ -350,6 +350,7 @@ static int run_embed_fwd(const fbn_params_t* p, const fbn_batch_t* b, Workspace&
   e.C = w.C;
   e.pkC = pkC; e.pkX = pkX;
   e.nshard = p->n_shards;
+  e.se_r = p->se_hidden > 0 ? p->se_hidden : SE_R_DEFAULT;
   for (int r = 0; r < p->n_shards; ++r) e.shard[r] = p->shard[r];
   return launch_embed_senet_fwd(e, st);
 }
@@ -577,7 +578,7 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
   };
   auto leaf_embed = [&]() -> int {
     RC(launch_reduce_partials(w.partial_cate, g->cate_emb, eb, p->cate_rows * D, 0, ls));
-    RC(launch_senet_param_grads(w.sestat, B, lp, g->se_w1, g->se_b1, g->se_w2, g->se_b2, ls));
+    RC(launch_senet_param_grads(w.sestat, B, p->se_hidden > 0 ? p->se_hidden : SE_R_DEFAULT, lp, g->se_w1, g->se_b1, g->se_w2, g->se_b2, ls));
     RC(colprod2(w.dln, w.xhat, B, D, lp, g->ln_g, g->ln_b, ls));
     RC(colsum(w.dy, B, D, lp, g->mm_b, ls));
     return wgrad(w.dy, D, b->item_mm ? b->item_mm : w.xmm, D, B, D, D, ~0ull, prec, w, g->mm_w, ls, lp);
@@ -641,6 +642,7 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     EmbedBwdArgs e{};
     e.dV = w.dV; e.X5 = w.X5; e.sgate = w.sgate; e.xhat = w.xhat; e.rstd = w.rstd; e.cnt = w.cnt; e.ids = w.ids;
     e.se_w1 = p->se_w1; e.se_b1 = p->se_b1; e.se_w2 = p->se_w2; e.ln_g = p->ln_g; e.B = B; e.cate_rows = (int)p->cate_rows;
+    e.se_r = p->se_hidden > 0 ? p->se_hidden : SE_R_DEFAULT;
     e.dXitem = w.dXitem; e.dXhist = w.dXhist; e.dln = w.dln; e.dy = w.dy; e.sestat = w.sestat; e.cate_partial = w.partial_cate;
     e.pkdy = tl_reg.dst(w.dy, B, D, w.pk_dy);
     FBN_REQUIRE((size_t)eb * p->cate_rows * D <= (size_t)2 * 148 * 4 * MAX_CATE * D, FBN_ERR_ARG, "internal: cate scratch too small");

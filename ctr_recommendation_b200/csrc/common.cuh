@@ -15,7 +15,7 @@ constexpr int NA = 5;           // active fields 1..5
 constexpr int K1 = FBN_K1;      // 2688
 constexpr int H1 = FBN_H1;
 constexpr int H2 = FBN_H2;
-constexpr int SE_R = FBN_SE_R;
+constexpr int SE_R_DEFAULT = FBN_SE_R;   // the reference's SENetLayer(6, reduction_ratio=2)
 constexpr int MAX_L = 64;
 constexpr int MAX_CATE = 16;
 

@@ -28,7 +28,7 @@ __device__ __forceinline__ const float* item_row(const EmbedFwdArgs& a, long lon
   return a.shard[g % n] + (long long)(g / n) * D;
 }
 
-template <bool SHARDED>
+template <bool SHARDED, int SE_R>
 __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(EmbedFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* Wt = smem;
@@ -230,23 +230,35 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
 
 size_t embed_fwd_smem() { return (size_t)(D * D + EMB_WARPS * D * EMB_SPW) * sizeof(float); }
 
-int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
+template <int SE_R>
+static int launch_fwd_r(const EmbedFwdArgs& a, unsigned blocks, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = embed_fwd_smem();
   if (!attr_set) {
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<false, SE_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<true, SE_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  if (a.nshard > 0) embed_senet_fwd_kernel<true, SE_R><<<blocks, EMB_WARPS * 32, smem, st>>>(a);
+  else embed_senet_fwd_kernel<false, SE_R><<<blocks, EMB_WARPS * 32, smem, st>>>(a);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+// SENET hidden width = max(1, 6 // reduction_ratio) (ref :13): 3 for the reference's ratio 2; 6 / 2 / 1 for ratios 1 / 3 / >= 4
+int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
+  const size_t smem = embed_fwd_smem();
   const long long ngroups = (a.B + EMB_SPW - 1) / EMB_SPW;
   long long blocks = (ngroups + EMB_WARPS - 1) / EMB_WARPS;
   const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (72 KB smem each; 3 per SM measured slower: 342 vs 320 us)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (a.nshard > 0) embed_senet_fwd_kernel<true><<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);
-  else embed_senet_fwd_kernel<false><<<(unsigned)blocks, EMB_WARPS * 32, smem, st>>>(a);
-  FBN_CHECK_LAUNCH();
-  return FBN_OK;
+  switch (a.se_r) {
+    case 1: return launch_fwd_r<1>(a, (unsigned)blocks, smem, st);
+    case 2: return launch_fwd_r<2>(a, (unsigned)blocks, smem, st);
+    case 3: return launch_fwd_r<3>(a, (unsigned)blocks, smem, st);
+    case 6: return launch_fwd_r<6>(a, (unsigned)blocks, smem, st);
+  }
+  FBN_REQUIRE(false, FBN_ERR_SHAPE, "SENET hidden width %d is not one of 1, 2, 3, 6 (= max(1, 6 // reduction_ratio))", a.se_r);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,6 +267,7 @@ int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
 
 constexpr int EBW_WARPS = 8;
 
+template <int SE_R>
 __global__ void __launch_bounds__(EBW_WARPS * 32) embed_senet_bwd_kernel(EmbedBwdArgs a) {
   extern __shared__ __align__(16) float smem[];  // [EBW_WARPS][cate_rows][128] private accumulators
   __shared__ float s_se[SE_R * NF + SE_R + NF * SE_R];
@@ -325,14 +338,14 @@ __global__ void __launch_bounds__(EBW_WARPS * 32) embed_senet_bwd_kernel(EmbedBw
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         if (lane == f) v = da2[f];
-        if (lane == 9 + f) v = z[f];
+        if (lane == NF + SE_R + f) v = z[f];
       }
 #pragma unroll
       for (int r = 0; r < SE_R; ++r) {
-        if (lane == 6 + r) v = h[r];
-        if (lane == 15 + r) v = da1[r];
+        if (lane == NF + r) v = h[r];
+        if (lane == 2 * NF + SE_R + r) v = da1[r];
       }
-      if (lane < 24) a.sestat[b * 24 + lane] = v;
+      if (lane < 24) a.sestat[b * 24 + lane] = v;      // record {da2[6], h[R], z[6], da1[R]}: 12 + 2R <= 24 floats
     }
     const int4 id = *reinterpret_cast<const int4*>(a.ids + b * 4);
     // fields 1,2 -> cate_emb rows (private per-warp accumulators: deterministic, no atomics)
@@ -383,10 +396,19 @@ int launch_embed_senet_bwd(const EmbedBwdArgs& a, int blocks, cudaStream_t st) {
   const size_t smem = (size_t)EBW_WARPS * a.cate_rows * D * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  embed_senet_bwd_kernel<<<blocks, EBW_WARPS * 32, smem, st>>>(a);
+  switch (a.se_r) {
+    case 1: embed_senet_bwd_kernel<1><<<blocks, EBW_WARPS * 32, smem, st>>>(a); break;
+    case 2: embed_senet_bwd_kernel<2><<<blocks, EBW_WARPS * 32, smem, st>>>(a); break;
+    case 3: embed_senet_bwd_kernel<3><<<blocks, EBW_WARPS * 32, smem, st>>>(a); break;
+    case 6: embed_senet_bwd_kernel<6><<<blocks, EBW_WARPS * 32, smem, st>>>(a); break;
+    default: FBN_REQUIRE(false, FBN_ERR_SHAPE, "SENET hidden width %d is not one of 1, 2, 3, 6", a.se_r);
+  }
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
@@ -408,51 +430,52 @@ int launch_reduce_partials(const float* partial, float* out, int parts, long lon
   return FBN_OK;
 }
 
-// SENET parameter gradients from the per-sample records written above:
-//  sestat[b] = {da2[0..5], h[0..2], z[0..5], da1[0..2], pad}
+// SENET parameter gradients from the per-sample records written above (R = hidden width):
+//  sestat[b] = {da2[0..5], h[0..R-1], z[0..5], da1[0..R-1], pad}
 //  dW2[f][r] = sum_b da2[f] h[r]; db2[f] = sum_b da2[f]; dW1[r][f] = sum_b da1[r] z[f]; db1[r] = sum_b da1[r]
-// output order (45 values): dW1 (18), db1 (3), dW2 (18), db2 (6)
-__global__ void senet_param_partial_kernel(const float* __restrict__ sestat, long long B, long long per, float* __restrict__ partial) {
-  const int t = threadIdx.x;  // 64 threads, 45 active
-  if (t >= 45) return;
+// output order (13R + 6 values): dW1 (6R), db1 (R), dW2 (6R), db2 (6)
+constexpr int SE_PSTRIDE = 96;     // >= 13 * 6 + 6
+__global__ void senet_param_partial_kernel(const float* __restrict__ sestat, long long B, long long per, int R, float* __restrict__ partial) {
+  const int t = threadIdx.x, nout = 13 * R + NF;
+  if (t >= nout) return;
   int ia, ib;  // indices into the 24-float record; ib = -1 -> times 1
-  if (t < 18) { ia = 15 + t / NF; ib = 9 + t % NF; }
-  else if (t < 21) { ia = 15 + (t - 18); ib = -1; }
-  else if (t < 39) { ia = (t - 21) / SE_R; ib = 6 + (t - 21) % SE_R; }
-  else { ia = t - 39; ib = -1; }
+  if (t < NF * R) { ia = 2 * NF + R + t / NF; ib = NF + R + t % NF; }
+  else if (t < NF * R + R) { ia = 2 * NF + R + (t - NF * R); ib = -1; }
+  else if (t < 2 * NF * R + R) { ia = (t - NF * R - R) / R; ib = NF + (t - NF * R - R) % R; }
+  else { ia = t - 2 * NF * R - R; ib = -1; }
   const long long b0 = (long long)blockIdx.x * per, b1 = min(B, b0 + per);
   float acc = 0.f;
   for (long long b = b0; b < b1; ++b) {
     const float* r = sestat + b * 24;
     acc += ib >= 0 ? r[ia] * r[ib] : r[ia];
   }
-  partial[(long long)blockIdx.x * 48 + t] = acc;
+  partial[(long long)blockIdx.x * SE_PSTRIDE + t] = acc;
 }
 
-__global__ void __launch_bounds__(256) senet_param_final_kernel(const float* __restrict__ partial, int parts, float* dw1, float* db1,
+__global__ void __launch_bounds__(256) senet_param_final_kernel(const float* __restrict__ partial, int parts, int R, float* dw1, float* db1,
                                                                 float* dw2, float* db2) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, nout = 13 * R + NF;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);   // warp per output, lanes over the partials (fixed xor tree)
-  if (t >= 45) return;
+  if (t >= nout) return;
   double acc = 0.0;
-  for (int p = lane; p < parts; p += 32) acc += (double)partial[(long long)p * 48 + t];
+  for (int p = lane; p < parts; p += 32) acc += (double)partial[(long long)p * SE_PSTRIDE + t];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane != 0) return;
-  if (t < 18) dw1[t] = (float)acc;
-  else if (t < 21) db1[t - 18] = (float)acc;
-  else if (t < 39) dw2[t - 21] = (float)acc;
-  else db2[t - 39] = (float)acc;
+  if (t < NF * R) dw1[t] = (float)acc;
+  else if (t < NF * R + R) db1[t - NF * R] = (float)acc;
+  else if (t < 2 * NF * R + R) dw2[t - NF * R - R] = (float)acc;
+  else db2[t - 2 * NF * R - R] = (float)acc;
 }
 
-int launch_senet_param_grads(const float* sestat, long long B, float* partial, float* dw1, float* db1, float* dw2, float* db2,
+int launch_senet_param_grads(const float* sestat, long long B, int R, float* partial, float* dw1, float* db1, float* dw2, float* db2,
                              cudaStream_t st) {
   int parts = (int)std::min<long long>((B + 31) / 32, 1024);
   if (parts < 1) parts = 1;
   long long per = (B + parts - 1) / parts;
-  senet_param_partial_kernel<<<parts, 64, 0, st>>>(sestat, B, per, partial);
+  senet_param_partial_kernel<<<parts, 96, 0, st>>>(sestat, B, per, R, partial);
   FBN_CHECK_LAUNCH();
-  senet_param_final_kernel<<<6, 256, 0, st>>>(partial, parts, dw1, db1, dw2, db2);
+  senet_param_final_kernel<<<(13 * R + NF + 7) / 8, 256, 0, st>>>(partial, parts, R, dw1, db1, dw2, db2);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }

@@ -21,6 +21,7 @@ struct EmbedFwdArgs {
   float* X5; float* sgate; float* xhat; float* xmm; float* rstd; float* cnt; float* C;
   PackDst pkC;         // packed copy of the field blocks of C
   PackDst pkX;         // packed copy of the item_emb_d128 rows (B,128)
+  int se_r;            // SENET hidden width: max(1, 6 // reduction_ratio) in {1, 2, 3, 6}
   int nshard;          // > 0: row-sharded item table, row g = shard[g % nshard] + (g / nshard) * 128 (peer-mapped pointers)
   const float* shard[FBN_MAX_SHARDS];
 };
@@ -30,7 +31,7 @@ struct EmbedBwdArgs {
   const float* X5; const float* sgate; const float* xhat; const float* rstd; const float* cnt;
   const int32_t* ids;
   const float* se_w1; const float* se_b1; const float* se_w2; const float* ln_g;
-  long long B; int cate_rows;
+  long long B; int cate_rows; int se_r;
   float* dXitem; float* dXhist; float* dln; float* dy; float* sestat;
   PackDst pkdy;
   float* cate_partial;  // (gridDim.x, cate_rows, 128)

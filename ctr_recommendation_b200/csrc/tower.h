@@ -47,7 +47,7 @@ int reduce_splits(const float* partial, int parts, long long M, long long N, lon
 
 // embed.cu
 int launch_reduce_partials(const float* partial, float* out, int parts, long long n, int accumulate, cudaStream_t st);
-int launch_senet_param_grads(const float* sestat, long long B, float* partial, float* dw1, float* db1, float* dw2, float* db2,
+int launch_senet_param_grads(const float* sestat, long long B, int R, float* partial, float* dw1, float* db1, float* dw2, float* db2,
                              cudaStream_t st);
 int embed_bwd_blocks(long long B);
 

@@ -139,10 +139,14 @@ class MM_FiBiNET(nn.Module):
             raise ValueError(f"embedding_dim={self.emb_dim}: the sm_100a kernels are specialised for "
                              f"embedding_dim == {D} (the value in config/fibinet_config.yaml)")
         opts = dict(feature_map) if isinstance(feature_map, dict) else {}
-        bilinear_type, dropout = "all", 0.2      # hard-coded in the reference (:118,:129,:133)
+        bilinear_type, dropout, senet_reduction = "all", 0.2, 2      # hard-coded in the reference (:114,:118,:129,:133)
         if model_cfg.get("honor_config", False):
             bilinear_type = model_cfg.get("bilinear_type", bilinear_type)
             dropout = float(model_cfg.get("net_dropout", dropout))
+            senet_reduction = int(model_cfg.get("senet_reduction", senet_reduction))
+        senet_reduction = int(opts.get("senet_reduction", senet_reduction))
+        if senet_reduction < 1:
+            raise ValueError("senet_reduction must be >= 1")
         bilinear_type = opts.get("bilinear_type", bilinear_type)
         self.dropout_p = float(opts.get("dropout", dropout))
         self.precision = opts.get("precision", model_cfg.get("precision", "fp32"))
@@ -180,7 +184,7 @@ class MM_FiBiNET(nn.Module):
         self.cate_emb = nn.Embedding(CATE_ROWS, self.emb_dim)
         self.mm_proj = nn.Sequential(nn.Linear(mm_input_dim, self.emb_dim), nn.LayerNorm(self.emb_dim), nn.ReLU())
         self.num_fields = NUM_FIELDS
-        self.senet = SENetLayer(self.num_fields, reduction_ratio=2)
+        self.senet = SENetLayer(self.num_fields, reduction_ratio=senet_reduction)     # hidden = max(1, 6 // ratio) in {6, 3, 2, 1}
         self.bilinear = BilinearInteraction(self.emb_dim, self.num_fields, bilinear_type=bilinear_type)
         num_pairs = (self.num_fields * (self.num_fields - 1)) // 2
         total_input_dim = (self.num_fields + num_pairs) * self.emb_dim
@@ -299,6 +303,7 @@ class MM_FiBiNET(nn.Module):
         P.bn2_var = self.mlp[5].running_var.data_ptr()
         P.bilinear_type = _lib.BILINEAR_TYPES[self.bilinear.bilinear_type]
         P.precision = _lib.PRECISIONS[self.precision]
+        P.se_hidden = self.senet.reduced_size
         return P
 
     def _bucket1_offset(self) -> int:

@@ -69,9 +69,9 @@ typedef struct {
   float* mm_b;       /* mm_proj.0.bias   (128) */
   float* ln_g;       /* mm_proj.1.weight (128) */
   float* ln_b;       /* mm_proj.1.bias   (128) */
-  float* se_w1;      /* senet.excitation.0.weight (3,6) */
-  float* se_b1;      /* senet.excitation.0.bias (3) */
-  float* se_w2;      /* senet.excitation.2.weight (6,3) */
+  float* se_w1;      /* senet.excitation.0.weight (R,6), R = se_hidden (3) */
+  float* se_b1;      /* senet.excitation.0.bias (R) */
+  float* se_w2;      /* senet.excitation.2.weight (6,R) */
   float* se_b2;      /* senet.excitation.2.bias (6) */
   float* bil_w;      /* bilinear.W (128,128); for EACH: 5 matrices contiguous; INTERACTION: 15 */
   float* w1;         /* mlp.0.weight (512,2688) */
@@ -101,6 +101,9 @@ typedef struct {
   int32_t shard_rank;
   int64_t shard_rows;
   const float* shard[16];
+  /* SENetLayer hidden width max(1, 6 // reduction_ratio) (src/model_fibinet.py:13): 0 = the reference's 3 (ratio 2, hard-coded at :114);
+   * 1, 2, 3, 6 = `senet_reduction` of config/fibinet_config.yaml honoured (ratios >= 4, 3, 2, 1). */
+  int32_t se_hidden;
 } fbn_params_t;
 
 #define FBN_MAX_SHARDS 16

@@ -61,12 +61,12 @@ def normal(seed: int, stream: int, n: int) -> np.ndarray:
     return np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
 
 
-def state_dict_shapes(emb_dim: int = 128, bilinear_type: str = "all", num_fields: int = NUM_FIELDS):
+def state_dict_shapes(emb_dim: int = 128, bilinear_type: str = "all", num_fields: int = NUM_FIELDS, senet_reduction: int = 2):
     """The 28 state_dict keys of MM_FiBiNET (src/model_fibinet.py:92-136)."""
     D = emb_dim
     pairs = num_fields * (num_fields - 1) // 2
     k1 = (num_fields + pairs) * D
-    red = max(1, num_fields // 2)
+    red = max(1, num_fields // senet_reduction)      # SENetLayer, src/model_fibinet.py:13 (the reference passes ratio 2, :114)
     shapes = {
         "item_emb.weight": (V_ITEM, D),
         "user_emb.weight": (V_USER, D),
@@ -106,7 +106,7 @@ def state_dict_shapes(emb_dim: int = 128, bilinear_type: str = "all", num_fields
     return shapes
 
 
-def make_weights(seed: int = 7, emb_dim: int = 128, bilinear_type: str = "all") -> dict:
+def make_weights(seed: int = 7, emb_dim: int = 128, bilinear_type: str = "all", senet_reduction: int = 2) -> dict:
     """A full, non-trivial MM_FiBiNET state_dict as numpy arrays (fp32; counters int64).
 
     Scales mimic torch's default initialisers (src/model_fibinet.py:100-135) but every
@@ -114,7 +114,7 @@ def make_weights(seed: int = 7, emb_dim: int = 128, bilinear_type: str = "all") 
     trivial value so that parity tests exercise them.
     """
     out = {}
-    for s, (name, shape) in enumerate(state_dict_shapes(emb_dim, bilinear_type).items()):
+    for s, (name, shape) in enumerate(state_dict_shapes(emb_dim, bilinear_type, senet_reduction=senet_reduction).items()):
         n = int(np.prod(shape)) if shape else 1
         if name.endswith("num_batches_tracked"):
             out[name] = np.array(3, dtype=np.int64)

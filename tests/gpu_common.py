@@ -15,11 +15,11 @@ def load_weights(model, weights: dict):
     return model
 
 
-def make_model(precision="fp32", bilinear_type="all", seed=7, train=False, fused=False):
+def make_model(precision="fp32", bilinear_type="all", seed=7, train=False, fused=False, senet_reduction=2):
     from ctr_recommendation_b200 import build_model
-    fm = {"precision": precision, "bilinear_type": bilinear_type}
+    fm = {"precision": precision, "bilinear_type": bilinear_type, "senet_reduction": senet_reduction}
     model = build_model(fm, {"embedding_dim": 128})
-    load_weights(model, synth.make_weights(seed=seed, bilinear_type=bilinear_type))
+    load_weights(model, synth.make_weights(seed=seed, bilinear_type=bilinear_type, senet_reduction=senet_reduction))
     model = model.cuda()
     model.train(train)
     return model

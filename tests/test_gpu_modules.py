@@ -112,3 +112,38 @@ def test_full_model_other_bilinear_types(golden, bt):
     for k in G:
         scale = max(np.abs(G[k]).max(), 1e-30)
         assert np.abs(got[k].astype(np.float64) - G[k]).max() <= TOL * scale + 2e-7, k
+
+
+@pytest.mark.parametrize("ratio,hidden", [(1, 6), (3, 2), (6, 1), (7, 1)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_senet_reduction_in_the_fused_model(ratio, hidden, precision):
+    """`senet_reduction` of config/fibinet_config.yaml (the reference hard-codes ratio 2, src/model_fibinet.py:114): the fused six-field
+    kernels run SENetLayer(6, ratio) with hidden = max(1, 6 // ratio) and match the oracle (forward and all gradients) at 1e-5."""
+    from gpu_common import make_model, to_dev, named_grads
+    from oracle import fibinet_numpy as orc, synth
+    from helpers import rel_err
+    B = 320
+    model = make_model(train=True, precision=precision, senet_reduction=ratio)
+    assert model.senet.excitation[0].weight.shape == (hidden, 6) and model._params_struct().se_hidden == hidden
+    batch, labels = synth.make_batch(seed=140 + ratio, batch=B, id_dist="zipf", index_dtype=np.float64)
+    m1, m2 = synth.make_dropout_masks(3, B)
+    model._test_masks = (torch.from_numpy(m1), torch.from_numpy(m2))
+    y = model(to_dev(batch))
+    torch.nn.BCELoss()(y, torch.from_numpy(labels).cuda()).backward()
+    P = synth.make_weights(seed=7, senet_reduction=ratio)
+    prob, cache = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False)
+    _, dprob = orc.bce_loss(prob, labels)
+    G = orc.backward(P, cache, dprob)
+    assert rel_err(y.detach().cpu().numpy(), prob) <= 1e-5
+    got = named_grads(model)
+    assert set(got) == set(G)
+    for k in G:
+        err = np.abs(got[k].astype(np.float64) - G[k]).max()
+        assert err <= 1e-5 * max(np.abs(G[k]).max(), 1e-30) + 2e-7, (k, err)
+
+
+def test_honor_config_reads_senet_reduction():
+    from ctr_recommendation_b200 import build_model
+    cfg = {"embedding_dim": 128, "senet_reduction": 3, "bilinear_type": "each", "net_dropout": 0.25}
+    assert build_model(None, cfg).senet.reduced_size == 3                                  # ignored like in the reference
+    assert build_model(None, dict(cfg, honor_config=True)).senet.reduced_size == 2         # honoured: max(1, 6 // 3)
