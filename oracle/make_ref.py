@@ -5,7 +5,7 @@ build.  `/root/reference` exists only in the dev container, so `__graft_entry__.
 legs (`cpu_baseline`, `--impl reference`) then time the reference's own module (kind = "reference") on the GPU box's host
 cores.  Nothing is copied into the git history; the product never imports oracle/_ref.
 
-    python oracle/make_ref.py            # copies /root/reference/src/{model_fibinet,utils}.py byte for byte
+    python oracle/make_ref.py            # copies /root/reference/src/*.py byte for byte
 """
 from __future__ import annotations
 
@@ -16,7 +16,9 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/src"
 DST = os.path.join(HERE, "_ref")
-FILES = ("model_fibinet.py", "utils.py")
+FILES = ("model_fibinet.py", "utils.py")                       # what the CPU arm of bench.py imports
+SCRIPTS = ("train_fibinet.py", "Prediction.py", "dataloader.py")  # the reference's own entry points, driven against the swapped module
+                                                                  # by tests/test_gpu_entrypoints.py ("Entry-point" row)
 
 
 def make_ref() -> str | None:
@@ -24,7 +26,7 @@ def make_ref() -> str | None:
     if os.path.isdir(SRC):
         os.makedirs(DST, exist_ok=True)
         lines = []
-        for f in FILES:
+        for f in FILES + SCRIPTS:
             shutil.copyfile(os.path.join(SRC, f), os.path.join(DST, f))
             with open(os.path.join(DST, f), "rb") as fh:
                 lines.append(f"{hashlib.sha256(fh.read()).hexdigest()}  {f}")

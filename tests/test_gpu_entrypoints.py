@@ -124,3 +124,38 @@ def test_device_resident_dataset_matches_loader(tmp_path):
     for k in a["model"]:
         assert torch.equal(a["model"][k], b["model"][k]), k
     assert torch.equal(a["optimizer"]["m_item"], b["optimizer"]["m_item"])
+
+
+def test_reference_own_scripts_run_on_the_swapped_module(tmp_path):
+    """SURVEY section 4, "Entry-point" row: the REFERENCE'S OWN train_fibinet.py / Prediction.py / dataloader.py / utils.py (byte copies
+    vendored into oracle/_ref by oracle/make_ref.py) run unmodified with only src/model_fibinet.py swapped for this repo's shim --
+    stock torch.optim.Adam, torch clip_grad_norm_, OneCycleLR, the pandas loader with 4 workers, the 28-key checkpoint."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "train_fibinet.py")):
+        pytest.skip("oracle/_ref does not hold the reference scripts (run python oracle/make_ref.py where /root/reference exists)")
+    import shutil
+    from oracle import synth
+    data = tmp_path / "data" / "MicroLens_1M_x1"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_dataset.py"), str(data), "--train", "2500", "--valid", "600",
+                    "--test", "700"], check=True, capture_output=True)
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "fibinet_config.yaml")))
+    cfg[cfg["base_expid"]].update(epochs=2, batch_size=512)
+    (tmp_path / "config").mkdir()
+    yaml.safe_dump(cfg, open(tmp_path / "config" / "fibinet_config.yaml", "w"))
+    cwd = tmp_path / "src"
+    cwd.mkdir()
+    for f in ("train_fibinet.py", "Prediction.py", "dataloader.py", "utils.py"):
+        shutil.copyfile(os.path.join(ref, f), cwd / f)
+    shutil.copyfile(os.path.join(ROOT, "src", "model_fibinet.py"), cwd / "model_fibinet.py")         # the only swapped file
+    env = dict(os.environ, PYTHONPATH=ROOT, PYTHONIOENCODING="utf-8", CUDA_VISIBLE_DEVICES="0")
+    r = subprocess.run([sys.executable, "train_fibinet.py"], cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Valid AUC" in r.stdout
+    sd = torch.load(tmp_path / "checkpoints" / "FiBiNET_best.pth", map_location="cpu")
+    shapes = synth.state_dict_shapes()
+    assert list(sd) == list(shapes) and all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    r = subprocess.run([sys.executable, "Prediction.py"], cwd=cwd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    import pandas as pd
+    sub = pd.read_csv(cwd / "prediction_fibinet.csv")
+    assert list(sub.columns) == ["ID", "Task2"] and len(sub) == 700 and sub["Task2"].between(0, 1).all()
