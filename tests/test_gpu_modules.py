@@ -124,11 +124,12 @@ def test_senet_reduction_in_the_fused_model(ratio, hidden, precision):
     from helpers import rel_err
     B = 320
     model = make_model(train=True, precision=precision, senet_reduction=ratio)
-    assert model.senet.excitation[0].weight.shape == (hidden, 6) and model._params_struct().se_hidden == hidden
+    assert model.senet.excitation[0].weight.shape == (hidden, 6)
     batch, labels = synth.make_batch(seed=140 + ratio, batch=B, id_dist="zipf", index_dtype=np.float64)
     m1, m2 = synth.make_dropout_masks(3, B)
     model._test_masks = (torch.from_numpy(m1), torch.from_numpy(m2))
     y = model(to_dev(batch))
+    assert model._params_struct().se_hidden == hidden
     torch.nn.BCELoss()(y, torch.from_numpy(labels).cuda()).backward()
     P = synth.make_weights(seed=7, senet_reduction=ratio)
     prob, cache = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False)
