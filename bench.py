@@ -501,7 +501,7 @@ def kernel_rooflines(args, model, dev_batch, peaks, lib):
     gk["bytes_8d"] = g8d
     gk["GBps_8d"] = g8d / gk["ms"] / 1e6
     gk["frac_8d"] = gk["GBps_8d"] / peaks["hbm"]
-    roof = {"bound": "tensor", "kernel": f"gemm_tc2 (MLP-1 {shapes[dom]})", "achieved": g["TFLOPs"], "peak": peaks["tf"],
+    roof = {"bound": "tensor", "kernel": f"gemm_tc2p_kernel (MLP-1 {shapes[dom]})", "achieved": g["TFLOPs"], "peak": peaks["tf"],
             "unit": "TFLOP/s", "frac": g["frac_of_bf16_peak"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 dense (burst)",
             "note": f"dominant kernel of the step; algorithmic FLOPs 2*B*1920*512 (structural-zero blocks not counted); precision "
                     f"{args.precision} issues {passes}x these on the tensor pipe and kind::tf32 runs at half the bf16 rate used as "

@@ -102,7 +102,7 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   pf = std::max<size_t>(pf, (size_t)pick_splits(2 * 4, Bp) * H2 * H1);
   pf = std::max<size_t>(pf, (size_t)10 * 32 * D * D);
   pf = std::max<size_t>(pf, (size_t)2 * 148 * 4 * MAX_CATE * D);
-  pf = std::max<size_t>(pf, (size_t)4 * 148 * 3 * H1);
+  pf = std::max<size_t>(pf, (size_t)16 * 148 * 3 * H1);
   pf = std::max<size_t>(pf, (size_t)cdiv(rows, 8) + 1024);
   pf = std::max<size_t>(pf, (size_t)1024 * 96);
   w.partial_floats = pf;
@@ -719,10 +719,10 @@ static void carve_tower(TowerWs& w, void* base, int64_t B, int64_t k1) {
   w.dlogit = (float*)take(Bp * f);
   w.dH2 = (float*)take(Bp * H2 * f); w.dH1 = (float*)take(Bp * H1 * f);
   size_t pf = std::max<size_t>((size_t)4 * H1 * k1, (size_t)32 * H2 * H1);   // split-K partials of the two weight gradients
-  pf = std::max<size_t>(pf, (size_t)4 * 148 * 3 * H1);
+  pf = std::max<size_t>(pf, (size_t)16 * 148 * 3 * H1);
   w.partial_floats = pf;
   w.partial = (float*)take(pf * f);
-  w.partial_side = (float*)take((size_t)4 * 148 * 3 * H1 * f);
+  w.partial_side = (float*)take((size_t)16 * 148 * 3 * H1 * f);
   const int PX = FBN_PREC_TF32X3;
   w.pk_C = take(packed_bytes(Bp, k1, PX));
   w.pk_A1 = take(packed_bytes(Bp, H1, PX));
@@ -1059,13 +1059,14 @@ extern "C" int fbn_time_gemm(const float* A, const float* Bm, float* C, int64_t 
   return FBN_OK;
 }
 
-namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); void set_tc_reserve_sms(int n); }
+namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); void set_tc_reserve_sms(int n); void set_col_chunk_mult(int m); }
 
 // runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles
 extern "C" int fbn_set_option(const char* name, int value) {
   FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
   if (strcmp(name, "tc_pair_persistent") == 0) { fbn::set_tc_pair_persistent(value); return FBN_OK; }
+  if (strcmp(name, "col_chunk_mult") == 0) { fbn::set_col_chunk_mult(value); return FBN_OK; }
   if (strcmp(name, "tc_reserve_sms") == 0) { fbn::set_tc_reserve_sms(value); return FBN_OK; }
   if (strcmp(name, "side_streams") == 0) { g_use_side = value; return FBN_OK; }
   if (strcmp(name, "tc_persistent") == 0) { fbn::set_tc_persistent(value); return FBN_OK; }

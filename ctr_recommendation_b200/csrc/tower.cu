@@ -78,8 +78,12 @@ __global__ void __launch_bounds__(256) colreduce_kernel(ColArgs a) {
   }
 }
 
+// CTAs per SM of the column reductions (fbn_set_option("col_chunk_mult", m); partial buffers hold up to m = 16)
+static int g_col_mult = 4;
+void set_col_chunk_mult(int m) { g_col_mult = std::max(1, std::min(m, 16)); }
+
 int col_chunks(long long B, int N) {
-  long long want = std::max<long long>(1, (2LL * num_sms()) / std::max(1, N / 128));
+  long long want = std::max<long long>(1, ((long long)g_col_mult * num_sms()) / std::max(1, N / 128));
   long long chunks = std::min<long long>(want, (B + 31) / 32);
   return (int)std::max<long long>(1, chunks);
 }
