@@ -94,29 +94,74 @@ int emb_rows(const EmbGradArgs& a, cudaStream_t st) {
   return FBN_OK;
 }
 
-// ---- F-field model (general.py): lookups of F tables stored back to back, and their dense gradient -------------------------------
-__global__ void fields_gather_kernel(const float* __restrict__ table, const long long* __restrict__ offsets, const void* __restrict__ ids,
-                                     int idx_dtype, long long n, int F, float* __restrict__ x, int32_t* flag) {
+// ---- F-field model (general.py): lookups into tables stored back to back, and their dense gradient -----------------------------
+// Field descriptor (5 x int64 per field, on the device): {first row of its table, vocabulary, first id column, bag length, padding id}.
+//   bag length 1 : x[b][f] = table[row0 + id]                                   (nn.Embedding lookup, ref :155-159)
+//   bag length L : x[b][f] = sum over the L ids != padding of their rows / max(count, 1)   (the reference's masked mean pooling of
+//                  item_seq, ref :165-174; item_tags is a bag of 5)
+// Several fields may name the same table (ref: likes_level / views_level share cate_emb, item_id / item_seq share item_emb).
+// An id equal to the padding id contributes nothing and receives no gradient (nn.Embedding(padding_idx=...), ref :100); -1 = none.
+constexpr int FDESC = 5;
+
+__global__ void fields_gather_kernel(const float* __restrict__ table, const long long* __restrict__ desc, const void* __restrict__ ids,
+                                     int idx_dtype, long long B, int F, int cols, float* __restrict__ x, float* __restrict__ cnt,
+                                     int32_t* flag) {
   const int lane = threadIdx.x & 31;
+  const long long n = B * F;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {   // one warp per (sample, field)
     const int f = (int)(i % F);
-    const long long lo = offsets[f], vocab = offsets[f + 1] - lo;
-    long long id = load_index(ids, idx_dtype, i);
-    if (lane == 0 && (id < 0 || id >= vocab)) flag[0] = 1;          // torch: IndexError (the host raises it)
-    id = min(max(id, 0LL), vocab - 1);
-    st4(x + i * D + 4 * lane, ld4(table + (lo + id) * D + 4 * lane));
+    const long long b = i / F;
+    const long long* d = desc + f * FDESC;
+    const long long row0 = d[0], vocab = d[1], c0 = d[2], pad = d[4];
+    const int L = (int)d[3];
+    float4 acc = f4(0.f);
+    int nvalid = 0;
+    for (int l0 = 0; l0 < L; l0 += 8) {               // 8 independent row loads in flight, accumulated in id order
+      long long id[8];
+      float4 r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        id[u] = pad;
+        if (l0 + u < L) {
+          long long v = load_index(ids, idx_dtype, b * cols + c0 + l0 + u);
+          if (lane == 0 && (v < 0 || v >= vocab)) flag[0] = 1;        // torch: IndexError (the host raises it)
+          id[u] = min(max(v, 0LL), vocab - 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r[u] = (l0 + u < L && id[u] != pad) ? ld4(table + (row0 + id[u]) * D + 4 * lane) : f4(0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (l0 + u < L && id[u] != pad) { acc += r[u]; ++nvalid; }
+    }
+    const float c = (float)max(nvalid, 1);
+    st4(x + i * D + 4 * lane, L == 1 ? acc : acc / c);
+    if (lane == 0) cnt[i] = L == 1 ? 1.f : c;
   }
 }
 
-__global__ void fields_build_keys_kernel(const long long* __restrict__ offsets, const void* __restrict__ ids, int idx_dtype, long long n,
-                                         int F, int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+// occurrence keys of the dense gradient: every id column of every sample; padding ids go to the sentinel key (never summed)
+__global__ void fields_build_keys_kernel(const long long* __restrict__ desc, const int32_t* __restrict__ colfield, const void* __restrict__ ids,
+                                         int idx_dtype, long long n, int F, int cols, long long rows, int32_t* __restrict__ keys,
+                                         int32_t* __restrict__ vals) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i % F);
-    const long long lo = offsets[f], vocab = offsets[f + 1] - lo;
-    const long long id = min(max(load_index(ids, idx_dtype, i), 0LL), vocab - 1);
-    keys[i] = (int)(lo + id);
-    vals[i] = (int)i;
+    const int col = (int)(i % cols);
+    const long long b = i / cols;
+    const int f = colfield[col];
+    const long long* d = desc + f * FDESC;
+    const long long id = min(max(load_index(ids, idx_dtype, i), 0LL), d[1] - 1);
+    keys[i] = id == d[4] ? (int)rows : (int)(d[0] + id);
+    vals[i] = (int)(b * F + f);                      // the gradient row this occurrence adds: dx[b][f] (already divided by the bag count)
+  }
+}
+
+__global__ void fields_scale_kernel(float* __restrict__ dx, const float* __restrict__ cnt, long long n) {   // dx[b][f] /= count[b][f]
+  const int lane = threadIdx.x & 31;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+    const float c = __ldg(cnt + i);
+    if (c != 1.f) st4(dx + i * D + 4 * lane, ld4s(dx + i * D + 4 * lane) / c);
   }
 }
 
@@ -143,40 +188,47 @@ static FieldsScratch fields_carve(void* base, long long n, long long rows) {
 
 using namespace fbn;
 
-extern "C" int fbn_fields_gather(const float* table, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields,
-                                 float* x, int32_t* flag, fbn_stream_t stream) {
-  FBN_REQUIRE(table && offsets && ids && x && flag, FBN_ERR_ARG, "fbn_fields_gather: null pointer");
+extern "C" int fbn_fields_gather(const float* table, const int64_t* desc, const void* ids, int idx_dtype, int64_t batch, int fields,
+                                 int id_cols, float* x, float* count, int32_t* flag, fbn_stream_t stream) {
+  FBN_REQUIRE(table && desc && ids && x && count && flag, FBN_ERR_ARG, "fbn_fields_gather: null pointer");
   FBN_REQUIRE(idx_dtype == FBN_IDX_I32 || idx_dtype == FBN_IDX_I64, FBN_ERR_DTYPE, "fbn_fields_gather: ids must be int32 or int64");
-  FBN_REQUIRE(fields >= 1 && fields <= 64 && batch >= 1, FBN_ERR_SHAPE, "fbn_fields_gather: need 1 <= fields <= 64");
+  FBN_REQUIRE(fields >= 1 && fields <= 64 && batch >= 1 && id_cols >= fields, FBN_ERR_SHAPE, "fbn_fields_gather: need 1 <= fields <= 64");
   FBN_REQUIRE(aligned16(table) && aligned16(x), FBN_ERR_ALIGN, "fbn_fields_gather: unaligned pointer");
   const long long n = (long long)batch * fields;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, 8), 16LL * num_sms()));
-  fields_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, reinterpret_cast<const long long*>(offsets), ids, idx_dtype, n, fields, x,
-                                                                 flag);
+  fields_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, reinterpret_cast<const long long*>(desc), ids, idx_dtype, batch, fields,
+                                                                 id_cols, x, count, flag);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
 
-extern "C" size_t fbn_fields_scatter_bytes(int64_t batch, int fields, int64_t rows) {
-  return fields_carve(nullptr, (long long)batch * fields, rows).total;
+extern "C" size_t fbn_fields_scatter_bytes(int64_t batch, int id_cols, int64_t rows) {
+  return fields_carve(nullptr, (long long)batch * id_cols, rows).total;
 }
 
-extern "C" int fbn_fields_scatter(const float* dx, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields,
-                                  int64_t rows, float* grad, int32_t* row_touched, int zero_fill, float* sumsq_out, void* scratch,
-                                  size_t scratch_bytes, fbn_stream_t stream) {
-  FBN_REQUIRE(dx && offsets && ids && grad && sumsq_out && scratch, FBN_ERR_ARG, "fbn_fields_scatter: null pointer");
+extern "C" int fbn_fields_scatter(float* dx, const float* count, const int64_t* desc, const int32_t* col_field, const void* ids, int idx_dtype,
+                                  int64_t batch, int fields, int id_cols, int64_t rows, float* grad, int32_t* row_touched, int zero_fill,
+                                  float* sumsq_out, void* scratch, size_t scratch_bytes, fbn_stream_t stream) {
+  FBN_REQUIRE(dx && count && desc && col_field && ids && grad && sumsq_out && scratch, FBN_ERR_ARG, "fbn_fields_scatter: null pointer");
   FBN_REQUIRE(idx_dtype == FBN_IDX_I32 || idx_dtype == FBN_IDX_I64, FBN_ERR_DTYPE, "fbn_fields_scatter: ids must be int32 or int64");
-  const long long n = (long long)batch * fields;
-  FBN_REQUIRE(fields >= 1 && fields <= 64 && batch >= 1 && rows >= 1 && n < (1LL << 31) && rows < (1LL << 30), FBN_ERR_SHAPE,
-              "fbn_fields_scatter: bad shape");
+  const long long n = (long long)batch * id_cols;
+  FBN_REQUIRE(fields >= 1 && fields <= 64 && id_cols >= fields && batch >= 1 && rows >= 1 && n < (1LL << 31) && rows < (1LL << 30) &&
+                  (long long)batch * fields < (1LL << 31), FBN_ERR_SHAPE, "fbn_fields_scatter: bad shape");
   FBN_REQUIRE(aligned16(dx) && aligned16(grad), FBN_ERR_ALIGN, "fbn_fields_scatter: unaligned pointer");
-  FBN_REQUIRE(scratch_bytes >= fbn_fields_scatter_bytes(batch, fields, rows), FBN_ERR_ARG, "fbn_fields_scatter: scratch too small");
+  FBN_REQUIRE(scratch_bytes >= fbn_fields_scatter_bytes(batch, id_cols, rows), FBN_ERR_ARG, "fbn_fields_scatter: scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
   FieldsScratch s = fields_carve(scratch, n, rows);
   int32_t* cnt = row_touched ? row_touched : s.row_cnt;
   FBN_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * rows, st));
+  {
+    const long long nf = (long long)batch * fields;
+    const int sb = (int)std::max<long long>(1, std::min<long long>(cdiv(nf, 8), 8LL * num_sms()));
+    fields_scale_kernel<<<sb, 256, 0, st>>>(dx, count, nf);          // mean pooling: every id of a bag receives dx / count (ref :174)
+    FBN_CHECK_LAUNCH();
+  }
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, 256), 8LL * num_sms()));
-  fields_build_keys_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(offsets), ids, idx_dtype, n, fields, s.keys_in, s.vals_in);
+  fields_build_keys_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(desc), col_field, ids, idx_dtype, n, fields, id_cols, rows,
+                                                   s.keys_in, s.vals_in);
   FBN_CHECK_LAUNCH();
   size_t bytes = sort_bytes(n, rows);
   FBN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(s.cub, bytes, (const int32_t*)s.keys_in, s.keys_out, (const int32_t*)s.vals_in, s.vals_out,
@@ -184,7 +236,7 @@ extern "C" int fbn_fields_scatter(const float* dx, const int64_t* offsets, const
   g_launches += 4;
   emb_runs_kernel<<<blocks, 256, 0, st>>>(s.keys_out, n, (int)rows, cnt, s.row_off);
   FBN_CHECK_LAUNCH();
-  // every occurrence i reads its own gradient row dx[i]: B = 0 and L = 1 in the shared segment-sum addressing
+  // occurrence value s = gradient row index b * F + f: B = 0 and L = 1 in the shared segment-sum addressing reads dx[s]
   const int nb = emb_grad_partial_count(rows);
   SegArgs a{};
   a.off = s.row_off; a.cnt = cnt; a.nseg_dev = nullptr; a.nseg = rows; a.src = s.vals_out;

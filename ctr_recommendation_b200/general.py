@@ -13,10 +13,18 @@ field list, every FLOP in libfibinet_b200.so:
     feature_map = {"fields": [("user_id", 20000), ("item_id", 91718), ("likes_level", 11), ...],      # (name, vocabulary)
                    "bilinear_type": "all" | "each" | "interaction", "senet_reduction": 2, "dropout": 0.2, "precision": "tf32x3"}
 
-``forward(batch_dict)`` takes one integer id tensor (B,) per field name (or a ready (B,F) tensor under "ids") and returns (B,)
-probabilities.  The F tables are stored back to back in ONE (sum of vocabularies, 128) parameter ``emb.weight`` (field f owns rows
-offsets[f] .. offsets[f+1]), so the deterministic sorted-segment scatter-add and the table optimizers are shared with the
-six-field model.  Parameters are ordinary nn.Parameters with ordinary ``.grad`` tensors: any torch optimizer drives it.
+A field may also be a dict -- what the reference's commented-out tag lookup (src/dataloader.py:100-102), its unused ``user_emb``
+(src/model_fibinet.py:101,152) and its shared tables (:155-156,159,167) need:
+
+    {"name": "item_seq", "table": "item_id", "bag": 20}      # 20 ids per sample into item_id's table, id 0 = padding, masked MEAN
+    {"name": "item_tags", "vocab": 3000, "bag": 5}            # pooled exactly like the reference pools item_seq (:165-174)
+    {"name": "item_id", "vocab": 91718, "padding_idx": 0}     # nn.Embedding(padding_idx=0): zero row, zero gradient (:100)
+    {"name": "views_level", "table": "likes_level"}           # two fields, one table (cate_emb)
+
+``forward(batch_dict)`` takes one integer id tensor per field name -- (B,) or, for a bag, (B, bag) -- or a ready (B, id columns)
+tensor under "ids", and returns (B,) probabilities.  The tables are stored back to back in ONE (sum of vocabularies, 128) parameter
+``emb.weight``, so the deterministic sorted-segment scatter-add and the table optimizers are shared with the six-field model.
+Parameters are ordinary nn.Parameters with ordinary ``.grad`` tensors: any torch optimizer drives it.
 
 Oracle: oracle/fibinet_general.py (pinned on CPU against a torch model built from the reference's own SENetLayer /
 BilinearInteraction classes, tests/test_oracle_general.py); GPU parity: tests/test_gpu_general.py.  Unfused by design -- the
@@ -59,22 +67,57 @@ class GeneralFiBiNET(nn.Module):
         model_cfg = model_cfg or {}
         if int(model_cfg.get("embedding_dim", D)) != D:
             raise ValueError(f"embedding_dim must be {D} (the sm_100a kernels move one 512-byte row per warp instruction)")
-        self.field_names: List[str] = [str(n) for n, _ in fields]
-        self.vocabs: List[int] = [int(v) for _, v in fields]
-        F = len(self.field_names)
+        specs = [f if isinstance(f, dict) else {"name": f[0], "vocab": f[1]} for f in fields]
+        self.field_names: List[str] = [str(f["name"]) for f in specs]
+        F = len(specs)
         if not 2 <= F <= 64:
             raise ValueError("GeneralFiBiNET supports 2..64 fields")
+        if len(set(self.field_names)) != F:
+            raise ValueError("field names must be unique")
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {list(_lib.PRECISIONS)}")
         self.num_fields, self.precision, self.dropout_p = F, precision, float(dropout)
-        offs = [0]
-        for v in self.vocabs:
-            if v < 1:
-                raise ValueError("every field needs a vocabulary of at least one row")
-            offs.append(offs[-1] + v)
-        self.register_buffer("offsets", torch.tensor(offs, dtype=torch.int64), persistent=False)
+        # tables (a field either brings its own or names an earlier field's), stored back to back
+        table_of, row0, vocab_of, pad_of = {}, [], [], []
+        self.bags: List[int] = []
+        desc, col_field, col = [], [], 0
+        total = 0
+        for fi, f in enumerate(specs):
+            name = str(f["name"])
+            if f.get("table") is not None:
+                t = table_of.get(str(f["table"]))
+                if t is None:
+                    raise ValueError(f"field {name!r}: table {f['table']!r} must name an earlier field that owns a table")
+            else:
+                v = int(f.get("vocab", f.get("vocab_size", 0)))
+                if v < 1:
+                    raise ValueError(f"field {name!r} needs a vocabulary of at least one row")
+                t = len(row0)
+                row0.append(total)
+                vocab_of.append(v)
+                pad_of.append(int(f["padding_idx"]) if f.get("padding_idx") is not None else -1)
+                total += v
+            table_of[name] = t
+            bag = int(f.get("bag", 1))
+            if bag < 1:
+                raise ValueError(f"field {name!r}: bag must be >= 1")
+            # a bag masks its padding id (0 unless the table says otherwise); a single lookup only if the table has a padding row
+            pad = pad_of[t] if pad_of[t] >= 0 else (0 if bag > 1 else -1)
+            desc.append([row0[t], vocab_of[t], col, bag, pad])
+            col_field += [fi] * bag
+            col += bag
+            self.bags.append(bag)
+        self.id_cols = col
+        self.vocabs: List[int] = vocab_of
+        self._pad_rows = [r + p for r, p in zip(row0, pad_of) if p >= 0]
+        self.register_buffer("field_desc", torch.tensor(desc, dtype=torch.int64), persistent=False)
+        self.register_buffer("col_field", torch.tensor(col_field, dtype=torch.int32), persistent=False)
+        offs = [0, total]
         # creation order follows the reference's __init__: tables, SENET, bilinear, MLP (src/model_fibinet.py:100-135)
         self.emb = nn.Embedding(offs[-1], D)
+        with torch.no_grad():
+            for r in self._pad_rows:
+                self.emb.weight[r].zero_()                        # nn.Embedding(padding_idx=...) initialises that row to zero
         self.senet = SENetLayer(F, reduction_ratio=senet_reduction)
         self.bilinear = BilinearInteraction(D, F, bilinear_type=bilinear_type)
         self.num_pairs = F * (F - 1) // 2
@@ -120,12 +163,12 @@ class GeneralFiBiNET(nn.Module):
             if len(self._buf) >= 2:
                 self._buf.pop(next(iter(self._buf)))
             buf = dict(
-                X=torch.empty(B, F, D, **z), V=torch.empty(B, F, D, **z), gate=torch.empty(B, F, **z),
+                X=torch.empty(B, F, D, **z), V=torch.empty(B, F, D, **z), gate=torch.empty(B, F, **z), cnt=torch.empty(B, F, **z),
                 C=torch.zeros(B, self.k1, **z), dC=torch.empty(B, self.k1, **z), dV=torch.empty(B, F, D, **z), dX=torch.empty(B, F, D, **z),
                 tower=torch.zeros(lib.fbn_tower_workspace_bytes(B, self.k1), dtype=torch.uint8, device=dev),
                 bil=torch.empty(lib.fbn_bilinear_scratch_bytes(B, F, D, btype), dtype=torch.uint8, device=dev),
                 se=torch.empty(lib.fbn_senet_scratch_bytes(B, F, R), dtype=torch.uint8, device=dev),
-                scatter=torch.empty(lib.fbn_fields_scatter_bytes(B, F, self.emb.weight.shape[0]), dtype=torch.uint8, device=dev),
+                scatter=torch.empty(lib.fbn_fields_scatter_bytes(B, self.id_cols, self.emb.weight.shape[0]), dtype=torch.uint8, device=dev),
                 flag=torch.zeros(4, dtype=torch.int32, device=dev), sumsq=torch.zeros(2, **z))
             self._buf[B] = buf
         return buf
@@ -137,16 +180,20 @@ class GeneralFiBiNET(nn.Module):
             ids = batch["ids"]
         else:
             cols = []
-            for n in self.field_names:
+            for n, bag in zip(self.field_names, self.bags):
                 t = batch[n]
                 _require_cuda(t, f"batch_dict['{n}']")
-                cols.append(t.reshape(-1).long())             # tensor.long(), like src/model_fibinet.py:140-143
-            ids = torch.stack(cols, 1)
+                t = t.long()                                   # tensor.long(), like src/model_fibinet.py:140-143
+                t = t.reshape(-1, 1) if bag == 1 else t.reshape(t.shape[0], -1)
+                if t.shape[1] != bag:
+                    raise ValueError(f"batch_dict['{n}'] must carry {bag} id(s) per sample, got {tuple(t.shape)}")
+                cols.append(t)
+            ids = torch.cat(cols, 1)
         _require_cuda(ids, "ids")
         if ids.dtype not in (torch.int32, torch.int64):
             ids = ids.long()
-        if ids.dim() != 2 or ids.shape[1] != self.num_fields:
-            raise ValueError(f"ids must be (B, {self.num_fields})")
+        if ids.dim() != 2 or ids.shape[1] != self.id_cols:
+            raise ValueError(f"ids must be (B, {self.id_cols})")
         return ids.contiguous()
 
     def check_ids(self):
@@ -161,15 +208,15 @@ class GeneralFiBiNET(nn.Module):
     def _run_forward(self, ids: torch.Tensor) -> torch.Tensor:
         lib, st = _lib.load(), _lib.stream_ptr()
         _require_cuda(self.emb.weight, "GeneralFiBiNET parameters")
-        B, F = ids.shape
+        B, F = ids.shape[0], self.num_fields
         buf = self._scratch(B)
         idt = _lib.IDX_I32 if ids.dtype == torch.int32 else _lib.IDX_I64
         e0, e2 = self.senet.excitation[0], self.senet.excitation[2]
         R = self.senet.reduced_size
         btype = _lib.BILINEAR_TYPES[self.bilinear.bilinear_type]
         prec = _lib.PRECISIONS[self.precision]
-        _lib.check(lib.fbn_fields_gather(_lib.ptr(self.emb.weight), _lib.ptr(self.offsets), _lib.ptr(ids), idt, B, F, _lib.ptr(buf["X"]),
-                                         _lib.ptr(buf["flag"]), st), "fbn_fields_gather")
+        _lib.check(lib.fbn_fields_gather(_lib.ptr(self.emb.weight), _lib.ptr(self.field_desc), _lib.ptr(ids), idt, B, F, self.id_cols,
+                                         _lib.ptr(buf["X"]), _lib.ptr(buf["cnt"]), _lib.ptr(buf["flag"]), st), "fbn_fields_gather")
         _lib.check(lib.fbn_senet_fwd(_lib.ptr(buf["X"]), _lib.ptr(e0.weight), _lib.ptr(e0.bias), _lib.ptr(e2.weight), _lib.ptr(e2.bias),
                                      B, F, D, R, _lib.ptr(buf["V"]), _lib.ptr(buf["gate"]), st), "fbn_senet_fwd")
         Cm = buf["C"]
@@ -239,9 +286,9 @@ class GeneralFiBiNET(nn.Module):
                                      _lib.ptr(g_sb2), _lib.ptr(buf["se"]), buf["se"].numel(), st), "fbn_senet_bwd")
         rows = self.emb.weight.shape[0]
         g_emb = torch.empty(rows, D, dtype=torch.float32, device=dev)
-        _lib.check(lib.fbn_fields_scatter(_lib.ptr(buf["dX"]), _lib.ptr(self.offsets), _lib.ptr(cur["ids"]), cur["idt"], B, F, rows,
-                                          _lib.ptr(g_emb), None, 1, _lib.ptr(buf["sumsq"]), _lib.ptr(buf["scatter"]), buf["scatter"].numel(),
-                                          st), "fbn_fields_scatter")
+        _lib.check(lib.fbn_fields_scatter(_lib.ptr(buf["dX"]), _lib.ptr(buf["cnt"]), _lib.ptr(self.field_desc), _lib.ptr(self.col_field),
+                                          _lib.ptr(cur["ids"]), cur["idt"], B, F, self.id_cols, rows, _lib.ptr(g_emb), None, 1,
+                                          _lib.ptr(buf["sumsq"]), _lib.ptr(buf["scatter"]), buf["scatter"].numel(), st), "fbn_fields_scatter")
         bil_grads = [dW] if len(self.bilinear.weights()) == 1 else list(dW.unbind(0))
         return [g_emb, g_sw1, g_sb1, g_sw2, g_sb2, *bil_grads, g_w1, g_b1, g_g1, g_be1, g_w2, g_b2, g_g2, g_be2, g_w3, g_b3]
 
@@ -252,14 +299,8 @@ class GeneralFiBiNET(nn.Module):
         return self._run_forward(ids)
 
 
-def fields_from_feature_map(feature_map) -> List[Tuple[str, int]] | None:
-    """[(name, vocabulary), ...] from feature_map["fields"] (pairs, or dicts with name / vocab keys)."""
+def fields_from_feature_map(feature_map):
+    """The field list of feature_map["fields"]: (name, vocabulary) pairs or dicts (name / vocab / table / bag / padding_idx)."""
     if not isinstance(feature_map, dict) or not feature_map.get("fields"):
         return None
-    out = []
-    for f in feature_map["fields"]:
-        if isinstance(f, dict):
-            out.append((str(f["name"]), int(f.get("vocab", f.get("vocab_size")))))
-        else:
-            out.append((str(f[0]), int(f[1])))
-    return out
+    return [dict(f) if isinstance(f, dict) else (str(f[0]), int(f[1])) for f in feature_map["fields"]]

@@ -293,22 +293,27 @@ int fbn_ipc_close(void* base);
 
 /* ---- F-field FiBiNET (BASELINE config 5: "scaled synthetic FiBiNET: 40 fields"): the building blocks of general.py --------------
  * The reference hard-wires six fields (src/model_fibinet.py:112,179-182); its blocks are generic in F and are what is exposed
- * here: F embedding lookups (one table per field, stored back to back in ONE (sum of vocabularies, 128) matrix), SENetLayer /
+ * here: F embedding lookups or mean-pooled id bags (tables stored back to back in ONE (sum of vocabularies, 128) matrix), SENetLayer /
  * BilinearInteraction for F <= 64 (fbn_senet_*, fbn_bilinear_*_ld) and the MLP tower for any input width K1 = (F + F(F-1)/2) * 128.
  * Oracle: oracle/fibinet_general.py, pinned against the reference's own SENetLayer / BilinearInteraction classes. */
 
-/* x[b][f][:] = table[offsets[f] + ids[b][f]][:]   (nn.Embedding lookups, src/model_fibinet.py:155-159).  ids: (B,F) int32 / int64
- * (idx_dtype FBN_IDX_I32 / FBN_IDX_I64); offsets: (F+1) int64 on the DEVICE, offsets[F] = total rows.  flag (4) int32 on the device:
- * flag[0] is set when an id is outside [0, vocab_f) (the kernel clamps; the host raises IndexError). */
-int fbn_fields_gather(const float* table, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields,
-                      float* x, int32_t* flag, fbn_stream_t stream);
-/* Dense gradient of the lookups above (embedding_dense_backward): grad (rows,128) = scatter-add of dx (B,F,128), by the same
- * deterministic sorted-segment sum as the item table (stable sort of the B*F global rows, one warp per row in source order, hot rows
- * chunked).  zero_fill / row_touched / sumsq_out (1,) as in fbn_backward.  scratch: fbn_fields_scatter_bytes(batch, fields, rows). */
-size_t fbn_fields_scatter_bytes(int64_t batch, int fields, int64_t rows);
-int fbn_fields_scatter(const float* dx, const int64_t* offsets, const void* ids, int idx_dtype, int64_t batch, int fields, int64_t rows,
-                       float* grad, int32_t* row_touched, int zero_fill, float* sumsq_out, void* scratch, size_t scratch_bytes,
-                       fbn_stream_t stream);
+/* Field lookups (nn.Embedding, src/model_fibinet.py:155-159) and masked mean-pooled bags (the reference's item_seq pooling, :165-174).
+ * desc: (F,5) int64 on the DEVICE, per field {first row of its table inside `table`, vocabulary, first id column, bag length, padding id
+ * (-1 = none)}; several fields may share a table.  ids: (B, id_cols) int32 / int64, one column per id of every field (id_cols = sum of
+ * the bag lengths).  x (B,F,128): the looked-up row (bag length 1) or the mean of the rows whose id is not the padding id; count (B,F):
+ * max(number of such ids, 1).  flag (4) int32 on the device: flag[0] is set when an id is outside [0, vocab) (the kernel clamps; the
+ * host raises IndexError). */
+int fbn_fields_gather(const float* table, const int64_t* desc, const void* ids, int idx_dtype, int64_t batch, int fields, int id_cols,
+                      float* x, float* count, int32_t* flag, fbn_stream_t stream);
+/* Dense gradient of the lookups above (embedding_dense_backward): grad (rows,128) = scatter-add of dx[b][f] / count[b][f] to every
+ * non-padding id of field f, by the same deterministic sorted-segment sum as the item table (stable sort of the B * id_cols global
+ * rows, one warp per row in source order, hot rows chunked).  dx is divided by count IN PLACE.  col_field: (id_cols) int32 on the
+ * device, the field of every id column.  zero_fill / row_touched / sumsq_out (1,) as in fbn_backward.
+ * scratch: fbn_fields_scatter_bytes(batch, id_cols, rows). */
+size_t fbn_fields_scatter_bytes(int64_t batch, int id_cols, int64_t rows);
+int fbn_fields_scatter(float* dx, const float* count, const int64_t* desc, const int32_t* col_field, const void* ids, int idx_dtype,
+                       int64_t batch, int fields, int id_cols, int64_t rows, float* grad, int32_t* row_touched, int zero_fill,
+                       float* sumsq_out, void* scratch, size_t scratch_bytes, fbn_stream_t stream);
 
 /* The MLP tower of the reference for an arbitrary input width k1 (src/model_fibinet.py:125-136,197-199): Linear(k1,512) -> BatchNorm1d ->
  * ReLU -> Dropout -> Linear(512,256) -> BatchNorm1d -> ReLU -> Dropout -> Linear(256,1) -> sigmoid, and its backward.  Only the MLP

@@ -48,10 +48,36 @@ def make_params(num_fields: int, dim: int, vocab: int, hidden=(512, 256), biline
     return P
 
 
-def forward(P: dict, ids: np.ndarray, masks=None, dropout_p: float = 0.0):
-    """Train-mode forward (batch statistics).  ids: (B, F) integer, one id per field.  Returns (prob (B,), cache)."""
-    B, F = ids.shape
-    X = np.stack([P["tables"][f][ids[:, f]] for f in range(F)], axis=1)          # (B, F, D) field stack
+def default_spec(num_fields: int):
+    """One table and one id column per field: the plain F-lookup model."""
+    return [dict(table=f, col=f, bag=1, pad=-1) for f in range(num_fields)]
+
+
+def field_stack(P: dict, ids: np.ndarray, spec):
+    """X (B,F,D) and the per-field counts.  A field is one lookup into its table (nn.Embedding, src/model_fibinet.py:155-159; an id
+    equal to the table's padding id gives the zero row, :100) or a bag of ids pooled the way the reference pools item_seq
+    (:165-174): rows of the non-padding ids summed and divided by clamp(count, min=1)."""
+    B = ids.shape[0]
+    X, cnt = [], []
+    for f in spec:
+        T = P["tables"][f["table"]]
+        idf = ids[:, f["col"]:f["col"] + f["bag"]]
+        valid = idf != f["pad"]
+        rows = T[idf] * valid[..., None]
+        if f["bag"] == 1:
+            X.append(rows[:, 0]); cnt.append(np.ones(B))
+        else:
+            c = np.maximum(valid.sum(1), 1).astype(T.dtype)
+            X.append(rows.sum(1) / c[:, None]); cnt.append(c)
+    return np.stack(X, axis=1), np.stack(cnt, axis=1)
+
+
+def forward(P: dict, ids: np.ndarray, masks=None, dropout_p: float = 0.0, spec=None):
+    """Train-mode forward (batch statistics).  ids: (B, id columns) integer (one column per field unless ``spec`` says otherwise).
+    Returns (prob (B,), cache)."""
+    spec = default_spec(ids.shape[1]) if spec is None else spec
+    B, F = ids.shape[0], len(spec)
+    X, cnt = field_stack(P, ids, spec)                                           # (B, F, D) field stack
     V, se_saved = orc.senet_forward(X, P["se_w1"], P["se_b1"], P["se_w2"], P["se_b2"])
     W = P["bil_w"][0] if P["bilinear_type"] == "all" else P["bil_w"]
     Pm = orc.bilinear_forward(V, W, P["bilinear_type"])
@@ -72,7 +98,7 @@ def forward(P: dict, ids: np.ndarray, masks=None, dropout_p: float = 0.0):
         a = y
     logit = (a @ P["w_out"].T + P["b_out"])[:, 0]
     prob = 1.0 / (1.0 + np.exp(-logit))
-    return prob, dict(ids=ids, X=X, V=V, se_saved=se_saved, C=C, layers=layers, last=a, prob=prob)
+    return prob, dict(ids=ids, X=X, V=V, se_saved=se_saved, C=C, layers=layers, last=a, prob=prob, spec=spec, cnt=cnt)
 
 
 def backward(P: dict, cache: dict, dprob: np.ndarray) -> dict:
@@ -105,9 +131,10 @@ def backward(P: dict, cache: dict, dprob: np.ndarray) -> dict:
     dV += dVb
     G["bil_w"] = [dW] if P["bilinear_type"] == "all" else dW
     dX, G["se_w1"], G["se_b1"], G["se_w2"], G["se_b2"] = orc.senet_backward(X, P["se_w1"], P["se_w2"], cache["se_saved"], dV)
-    G["tables"] = []
-    for f in range(F):
-        g = np.zeros_like(P["tables"][f])
-        np.add.at(g, ids[:, f], dX[:, f])
-        G["tables"].append(g)
+    G["tables"] = [np.zeros_like(t) for t in P["tables"]]
+    for fi, f in enumerate(cache["spec"]):                                       # embedding_dense_backward of every lookup
+        idf = ids[:, f["col"]:f["col"] + f["bag"]]
+        valid = idf != f["pad"]
+        contrib = (dX[:, fi] / cache["cnt"][:, fi, None])[:, None, :] * valid[..., None]
+        np.add.at(G["tables"][f["table"]], idf.reshape(-1), contrib.reshape(-1, D))
     return G

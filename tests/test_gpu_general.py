@@ -128,3 +128,59 @@ def test_general_model_trains_with_a_torch_optimizer():
         opt.step()
         first = first if first is not None else loss.item()
     assert loss.item() < 0.5 * first
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_bags_shared_tables_and_padding_vs_oracle(precision):
+    """The field kinds the reference model itself is made of, plus the ones it leaves unused: a learned user lookup, two
+    fields on one table (likes / views -> cate_emb), a table with a padding row, a history bag pooled into the item table exactly like
+    src/model_fibinet.py:165-174, and an item_tags bag (src/dataloader.py:100-102) -- forward and every gradient against the oracle."""
+    from ctr_recommendation_b200 import build_model
+    from test_oracle_general import _bag_ids
+    vocabs = [600, 11, 900, 50]
+    spec = [dict(table=0, col=0, bag=1, pad=-1), dict(table=1, col=1, bag=1, pad=-1), dict(table=1, col=2, bag=1, pad=-1),
+            dict(table=2, col=3, bag=1, pad=0), dict(table=2, col=4, bag=6, pad=0), dict(table=3, col=10, bag=3, pad=0)]
+    # same layout as tests/test_oracle_general._bag_spec (history bag of 6 at columns 4..9, tag bag of 3 at 10..12)
+    fm = {"fields": [{"name": "user_id", "vocab": vocabs[0]}, {"name": "likes_level", "vocab": vocabs[1]},
+                     {"name": "views_level", "table": "likes_level"}, {"name": "item_id", "vocab": vocabs[2], "padding_idx": 0},
+                     {"name": "item_seq", "table": "item_id", "bag": 6}, {"name": "item_tags", "vocab": vocabs[3], "bag": 3}],
+          "precision": precision, "dropout": 0.0}
+    F, B, cols = 6, 700, 13
+    P = _round32(gen.make_params(F, D, 5, (512, 256), "all", reduction_ratio=2, seed=21))
+    rng = np.random.default_rng(3)
+    P["tables"] = [(rng.standard_normal((v, D)) * 0.3).astype(np.float32).astype(np.float64) for v in vocabs]
+    P["tables"][2][0] = 0.0
+    ids = _bag_ids(rng, B, vocabs, spec, cols)
+    ids[:, 1] = 4                                             # a hot row of the shared table: > 256 occurrences -> chunked segment sum
+    labels = rng.integers(0, 2, B).astype(np.float64)
+    prob, cache = gen.forward(P, ids, spec=spec)
+    dprob = (prob - labels) / np.maximum(prob * (1 - prob), 1e-12) / B
+    G = gen.backward(P, cache, dprob)
+
+    model = build_model(fm, {"embedding_dim": 128})
+    assert model.id_cols == cols and model.k1 == 21 * D and model.emb.weight.shape[0] == sum(vocabs)
+    _load(model, P, None)
+    model = model.cuda().train()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    batch = {"user_id": t(ids[:, 0]), "likes_level": t(ids[:, 1]), "views_level": t(ids[:, 2]), "item_id": t(ids[:, 3]),
+             "item_seq": t(ids[:, 4:10]), "item_tags": t(ids[:, 10:13])}
+    y = model(batch)
+    torch.nn.BCELoss()(y, torch.from_numpy(labels.astype(np.float32)).cuda()).backward()
+    rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+    assert rel(y.detach().cpu().numpy(), prob) <= 1e-5
+    X = model._buf[B]["X"].cpu().numpy()
+    assert rel(X, cache["X"]) <= 1e-6 and np.all(X[1, 3] == 0) and np.all(X[0, 4] == 0)          # padding lookup / all-padding bag
+    g_emb = model.emb.weight.grad.cpu().numpy()
+    want = np.concatenate(G["tables"], 0)
+    assert rel(g_emb, want) <= 1e-5
+    assert np.all(g_emb[vocabs[0] + vocabs[1]] == 0)                                               # the padding row gets no gradient
+    for got, key in ((model.mlp[0].weight.grad, "w0"), (model.mlp[4].weight.grad, "w1"), (model.senet.excitation[0].weight.grad, "se_w1"),
+                     (model.bilinear.W.grad, None)):
+        ref = G["bil_w"][0] if key is None else G[key]
+        assert rel(got.cpu().numpy(), ref) <= 1e-5, key
+    # same batch as one (B, id columns) tensor
+    with torch.no_grad():
+        model.eval()
+        a = model(batch)
+        b = model({"ids": t(ids)})
+    assert torch.equal(a, b)
