@@ -85,6 +85,7 @@ _SIGNATURES = {
     "fbn_fields_scatter_bytes": (_sz, [_i64, C.c_int, _i64]),
     "fbn_fields_scatter": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _i64, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
     "fbn_tower_workspace_bytes": (_sz, [_i64, _i64]),
+    "fbn_tower_workspace_offset": (_sz, [_i64, _i64, C.c_char_p]),
     "fbn_tower_forward": (C.c_int, [C.POINTER(Params), _vp, _i64, _i64, _vp, _sz, C.c_int, _f, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "fbn_tower_backward": (C.c_int, [C.POINTER(Params), _vp, _i64, _i64, _vp, _sz, C.c_int, _f, _vp, C.POINTER(Grads), _vp, _vp]),
     "fbn_bilinear_fwd_ld": (C.c_int, [_vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _vp, _i64, _vp, _sz, C.c_int, _vp]),

@@ -754,6 +754,17 @@ extern "C" size_t fbn_tower_workspace_bytes(int64_t batch, int64_t k1) {
   return w.total_bytes;
 }
 
+extern "C" size_t fbn_tower_workspace_offset(int64_t batch, int64_t k1, const char* name) {
+  TowerWs w;
+  char* base = reinterpret_cast<char*>(uintptr_t(4096));
+  carve_tower(w, base, batch, k1);
+  struct { const char* n; void* p; } tab[] = {{"H1", w.Hd1}, {"A1", w.A1}, {"H2", w.Hd2}, {"A2", w.A2}, {"logit", w.logit}, {"prob", w.prob},
+                                              {"dH1", w.dH1}, {"dH2", w.dH2}, {"dlogit", w.dlogit}};
+  for (auto& t : tab)
+    if (strcmp(t.n, name) == 0) return (size_t)((char*)t.p - base);
+  return (size_t)-1;
+}
+
 extern "C" int fbn_tower_forward(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes, int train,
                                  float dropout_p, const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset,
                                  const int32_t* step_counter_dev, float* prob_out, float* logit_out, fbn_stream_t stream) {

@@ -196,6 +196,17 @@ class GeneralFiBiNET(nn.Module):
             raise ValueError(f"ids must be (B, {self.id_cols})")
         return ids.contiguous()
 
+    def tower_view(self, name: str, shape) -> torch.Tensor:
+        """Debug/test accessor: a named activation of the most recent forward's MLP tower ("A1", "A2", "logit", ...)."""
+        B = self._cur["B"]
+        off = _lib.load().fbn_tower_workspace_offset(B, self.k1, name.encode())
+        if off == C.c_size_t(-1).value:
+            raise KeyError(name)
+        n = 1
+        for d in shape:
+            n *= d
+        return self._cur["buf"]["tower"][off:off + 4 * n].view(torch.float32).view(*shape)
+
     def check_ids(self):
         """IndexError if a lookup since the last check was outside its field's vocabulary (nn.Embedding raises; the kernel clamps
         and sets a sticky device flag).  Synchronises."""

@@ -321,6 +321,8 @@ int fbn_fields_scatter(float* dx, const float* count, const int64_t* desc, const
  * (fbn_tower_workspace_bytes, zero-initialised once) keeps the activations between the two calls.  Semantics of train / dropout /
  * masks / seed / step counter / dprob as in fbn_forward / fbn_backward; the same tcgen05 / SIMT GEMM back ends (params->precision). */
 size_t fbn_tower_workspace_bytes(int64_t batch, int64_t k1);
+/* byte offset of "H1" / "A1" (B,512), "H2" / "A2" (B,256), "logit" / "prob" / "dlogit" (B), "dH1", "dH2" inside it (tests); (size_t)-1 = unknown */
+size_t fbn_tower_workspace_offset(int64_t batch, int64_t k1, const char* name);
 int fbn_tower_forward(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes, int train,
                       float dropout_p, const uint8_t* keep_mask1, const uint8_t* keep_mask2, uint64_t seed, uint64_t offset,
                       const int32_t* step_counter_dev, float* prob_out, float* logit_out, fbn_stream_t stream);

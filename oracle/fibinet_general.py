@@ -72,9 +72,11 @@ def field_stack(P: dict, ids: np.ndarray, spec):
     return np.stack(X, axis=1), np.stack(cnt, axis=1)
 
 
-def forward(P: dict, ids: np.ndarray, masks=None, dropout_p: float = 0.0, spec=None):
+def forward(P: dict, ids: np.ndarray, masks=None, dropout_p: float = 0.0, spec=None, relu_gates=None):
     """Train-mode forward (batch statistics).  ids: (B, id columns) integer (one column per field unless ``spec`` says otherwise).
-    Returns (prob (B,), cache)."""
+    Returns (prob (B,), cache).  ``relu_gates``: optional list of boolean arrays replacing the MLP ReLU decisions (same test hook as
+    oracle/fibinet_numpy.forward: a pre-activation within rounding distance of zero may legitimately be decided differently by
+    another fp32 implementation, and one flipped decision moves a whole BatchNorm column's gradients)."""
     spec = default_spec(ids.shape[1]) if spec is None else spec
     B, F = ids.shape[0], len(spec)
     X, cnt = field_stack(P, ids, spec)                                           # (B, F, D) field stack
@@ -88,13 +90,15 @@ def forward(P: dict, ids: np.ndarray, masks=None, dropout_p: float = 0.0, spec=N
         mean, var = h.mean(0), h.var(0)                                          # biased variance normalises (BatchNorm1d, train)
         rstd = 1.0 / np.sqrt(var + EPS_BN)
         xhat = (h - mean) * rstd
-        r = np.maximum(xhat * P[f"bn_g{i}"] + P[f"bn_b{i}"], 0)
+        pre = xhat * P[f"bn_g{i}"] + P[f"bn_b{i}"]
+        gate = (pre > 0) if relu_gates is None else np.asarray(relu_gates[i], dtype=bool)
+        r = np.where(gate, pre, 0.0)
         m = None
         y = r
         if dropout_p > 0:
             m = masks[i].astype(h.dtype) / (1.0 - dropout_p)                      # nn.Dropout: keep-mask scaled by 1/(1-p)
             y = r * m
-        layers.append((a, xhat, rstd, r, m))
+        layers.append((a, xhat, rstd, gate, m, pre))
         a = y
     logit = (a @ P["w_out"].T + P["b_out"])[:, 0]
     prob = 1.0 / (1.0 + np.exp(-logit))
@@ -112,10 +116,10 @@ def backward(P: dict, cache: dict, dprob: np.ndarray) -> dict:
     G["b_out"] = dlogit.sum(keepdims=True)
     da = dlogit[:, None] * P["w_out"]
     for i in reversed(range(P["n_hidden"])):
-        a_in, xhat, rstd, r, m = cache["layers"][i]
+        a_in, xhat, rstd, gate, m, _ = cache["layers"][i]
         if m is not None:
             da = da * m
-        dy = da * (r > 0)
+        dy = da * gate
         G[f"bn_g{i}"] = (dy * xhat).sum(0)
         G[f"bn_b{i}"] = dy.sum(0)
         dxhat = dy * P[f"bn_g{i}"]

@@ -41,6 +41,24 @@ def _round32(P):
     return out
 
 
+def _oracle_under_gpu_gates(model, P, ids, labels, B, tol, masks=None, dropout=0.0, spec=None):
+    """Oracle forward / backward with the ReLU decisions of the GPU run (kept elements only), after checking that they differ from the
+    oracle's own decisions only where its pre-activation is within the tolerance band around zero (see test_gpu_parity.py:
+    test_full_batch_forward_backward_vs_oracle)."""
+    prob0, cache0 = gen.forward(P, ids, masks=masks, dropout_p=dropout, spec=spec)
+    gates = []
+    for i, (name, h) in enumerate((("A1", 512), ("A2", 256))):
+        A = model.tower_view(name, (B, h)).cpu().numpy()
+        own, pre = cache0["layers"][i][3], cache0["layers"][i][5]
+        g = (A > 0) if masks is None else np.where(masks[i] > 0, A > 0, own)
+        mis = g != own
+        assert mis.sum() <= 4 and ((not mis.any()) or np.abs(pre[mis]).max() <= tol * max(1.0, np.abs(pre).max())), (name, int(mis.sum()))
+        gates.append(g)
+    prob, cache = gen.forward(P, ids, masks=masks, dropout_p=dropout, spec=spec, relu_gates=gates)
+    dprob = (prob - labels) / np.maximum(prob * (1 - prob), 1e-12) / B
+    return prob0, gen.backward(P, cache, dprob)
+
+
 CASES = [("fp32", 8, 300, "all", 0.0), ("tf32x3", 8, 300, "all", 0.25), ("tf32x3", 8, 257, "each", 0.0), ("tf32x3", 6, 200, "interaction", 0.25),
          ("tf32x3", 40, 256, "all", 0.0), ("bf16", 8, 300, "all", 0.0)]
 
@@ -56,10 +74,6 @@ def test_general_model_vs_oracle(precision, F, B, btype, dropout):
     ids[:, 0] = ids[0, 0]                                   # a hot row: one id owns a whole field (chunked segment sum for B > 256)
     labels = rng.integers(0, 2, B).astype(np.float64)
     masks = [(rng.random((B, h)) >= dropout).astype(np.uint8) for h in (512, 256)] if dropout > 0 else None
-    prob, cache = gen.forward(P, ids, masks=masks, dropout_p=dropout)
-    dprob = (prob - labels) / np.maximum(prob * (1 - prob), 1e-12) / B
-    G = gen.backward(P, cache, dprob)
-
     fm = {"fields": [(f"f{i}", vocab) for i in range(F)], "bilinear_type": btype, "senet_reduction": 2, "dropout": dropout,
           "precision": precision}
     model = build_model(fm, {"embedding_dim": 128})
@@ -73,9 +87,12 @@ def test_general_model_vs_oracle(precision, F, B, btype, dropout):
     loss = torch.nn.BCELoss()(y, torch.from_numpy(labels.astype(np.float32)).cuda())
     loss.backward()
     rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+    if precision == "bf16":                                 # bf16 gradients: unpinned
+        prob, _ = gen.forward(P, ids, masks=masks, dropout_p=dropout)
+        assert rel(y.detach().cpu().numpy(), prob) <= tol
+        return
+    prob, G = _oracle_under_gpu_gates(model, P, ids, labels, B, tol, masks, dropout)
     assert rel(y.detach().cpu().numpy(), prob) <= tol, rel(y.detach().cpu().numpy(), prob)
-    if precision == "bf16":
-        return                                              # bf16 gradients: unpinned
     got = {
         "tables": model.emb.weight.grad.cpu().numpy(), "se_w1": model.senet.excitation[0].weight.grad.cpu().numpy(),
         "se_b1": model.senet.excitation[0].bias.grad.cpu().numpy(), "se_w2": model.senet.excitation[2].weight.grad.cpu().numpy(),
@@ -153,10 +170,7 @@ def test_bags_shared_tables_and_padding_vs_oracle(precision):
     ids = _bag_ids(rng, B, vocabs, spec, cols)
     ids[:, 1] = 4                                             # a hot row of the shared table: > 256 occurrences -> chunked segment sum
     labels = rng.integers(0, 2, B).astype(np.float64)
-    prob, cache = gen.forward(P, ids, spec=spec)
-    dprob = (prob - labels) / np.maximum(prob * (1 - prob), 1e-12) / B
-    G = gen.backward(P, cache, dprob)
-
+    cache = gen.forward(P, ids, spec=spec)[1]
     model = build_model(fm, {"embedding_dim": 128})
     assert model.id_cols == cols and model.k1 == 21 * D and model.emb.weight.shape[0] == sum(vocabs)
     _load(model, P, None)
@@ -167,17 +181,25 @@ def test_bags_shared_tables_and_padding_vs_oracle(precision):
     y = model(batch)
     torch.nn.BCELoss()(y, torch.from_numpy(labels.astype(np.float32)).cuda()).backward()
     rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+    prob, G = _oracle_under_gpu_gates(model, P, ids, labels, B, 1e-5, spec=spec)
     assert rel(y.detach().cpu().numpy(), prob) <= 1e-5
     X = model._buf[B]["X"].cpu().numpy()
     assert rel(X, cache["X"]) <= 1e-6 and np.all(X[1, 3] == 0) and np.all(X[0, 4] == 0)          # padding lookup / all-padding bag
     g_emb = model.emb.weight.grad.cpu().numpy()
     want = np.concatenate(G["tables"], 0)
-    assert rel(g_emb, want) <= 1e-5
-    assert np.all(g_emb[vocabs[0] + vocabs[1]] == 0)                                               # the padding row gets no gradient
-    for got, key in ((model.mlp[0].weight.grad, "w0"), (model.mlp[4].weight.grad, "w1"), (model.senet.excitation[0].weight.grad, "se_w1"),
+    errs = {"emb": rel(g_emb, want)}
+    o = 0
+    for k, v in enumerate(vocabs):
+        errs[f"table{k}"] = rel(g_emb[o:o + v], G["tables"][k])
+        o += v
+    for got, key in ((model.mlp[0].weight.grad, "w0"), (model.mlp[4].weight.grad, "w1"), (model.mlp[8].weight.grad, "w_out"),
+                     (model.senet.excitation[0].weight.grad, "se_w1"), (model.senet.excitation[2].weight.grad, "se_w2"),
                      (model.bilinear.W.grad, None)):
         ref = G["bil_w"][0] if key is None else G[key]
-        assert rel(got.cpu().numpy(), ref) <= 1e-5, key
+        errs[key or "bil_w"] = rel(got.cpu().numpy(), np.asarray(ref).reshape(got.shape))
+    bad = {k: v for k, v in errs.items() if v > 1e-5}
+    assert not bad, "; ".join(f"{k} {v:.2e}" for k, v in errs.items())
+    assert np.all(g_emb[vocabs[0] + vocabs[1]] == 0)                                               # the padding row gets no gradient
     # same batch as one (B, id columns) tensor
     with torch.no_grad():
         model.eval()
