@@ -155,6 +155,7 @@ struct Workspace {
   float* sgate;      // (B,8) sigmoid gates s_0..s_5
   float* xhat;       // (B,128) LayerNorm normalised projection
   float* xmm;        // (B,128) gathered item_emb_d128 rows (resident-table mode only)
+  float* Ymm;        // (B,128) item_emb_d128 x mm_w^T + mm_b from the projection GEMM (batch-vector mode)
   float* rstd;       // (B)
   float* cnt;        // (B) history count clamp(min=1)
   float* C;          // (B,2688) MLP input [V | pairs]; blocks 0 and 6..10 stay zero
@@ -196,7 +197,7 @@ struct Workspace {
   size_t gemm_scratch_bytes;
   // tcgen05 operands packed once per step (tf32 hi|lo or bf16), natural layout
   void* pk_C; void* pk_A1; void* pk_dH2; void* pk_dH1; void* pk_dT; void* pk_dy; void* pk_xmm;
-  void* pk_w1; void* pk_w2; void* pk_bil;
+  void* pk_w1; void* pk_w2; void* pk_bil; void* pk_mmw;
   size_t total_bytes;
 };
 

@@ -28,8 +28,10 @@ __device__ __forceinline__ const float* item_row(const EmbedFwdArgs& a, long lon
   return a.shard[g % n] + (long long)(g / n) * D;
 }
 
-template <bool SHARDED, int SE_R>
-__global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(EmbedFwdArgs a) {
+// EXTP: the item_emb_d128 projection y = x W^T + b was computed for the whole batch by a tcgen05 GEMM beforehand (a.yproj, (B,128));
+// the kernel then needs neither the 64 KB copy of W in shared memory nor the SIMT projection loop, and (EXTP ? 3 : 2) CTAs fit an SM.
+template <bool SHARDED, int SE_R, bool EXTP>
+__global__ void __launch_bounds__(EMB_WARPS * 32, EXTP ? 3 : 2) embed_senet_fwd_kernel(EmbedFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* Wt = smem;
   float* xs_all = smem + D * D;
@@ -37,10 +39,12 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // k-major copy of mm_w, float4 columns XOR-swizzled by k so that the transposing stores below are 4-way instead of 32-way
   // bank-conflicted (the prologue is paid by every CTA and dominates small batches)
+  if (!EXTP) {
 #pragma unroll 8
-  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
-    const int j = i >> 7, k = i & 127;  // mm_w[j][k], coalesced read
-    Wt[k * D + ((((j >> 2) ^ (k & 31)) << 2) | (j & 3))] = __ldg(a.mm_w + i);
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+      const int j = i >> 7, k = i & 127;  // mm_w[j][k], coalesced read
+      Wt[k * D + ((((j >> 2) ^ (k & 31)) << 2) | (j & 3))] = __ldg(a.mm_w + i);
+    }
   }
   if (threadIdx.x < SE_R * NF) s_se[threadIdx.x] = a.se_w1[threadIdx.x];
   if (threadIdx.x < SE_R) s_se[SE_R * NF + threadIdx.x] = a.se_b1[threadIdx.x];
@@ -49,8 +53,8 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
   __syncthreads();
   const float* w1 = s_se; const float* b1 = s_se + SE_R * NF;
   const float* w2 = b1 + SE_R; const float* b2 = w2 + NF * SE_R;
-  float* xs = xs_all + warp * (D * EMB_SPW);
-  const float4 bias = ld4(a.mm_b + 4 * lane), gam = ld4(a.ln_g + 4 * lane), bet = ld4(a.ln_b + 4 * lane);
+  float* xs = EXTP ? nullptr : xs_all + warp * (D * EMB_SPW);
+  const float4 bias = EXTP ? f4(0.f) : ld4(a.mm_b + 4 * lane), gam = ld4(a.ln_g + 4 * lane), bet = ld4(a.ln_b + 4 * lane);
 
   const long long ngroups = (a.B + EMB_SPW - 1) / EMB_SPW;
   for (long long g = (long long)blockIdx.x * EMB_WARPS + warp; g < ngroups; g += (long long)gridDim.x * EMB_WARPS) {
@@ -80,13 +84,15 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
         f_like[s] = ld4(a.cate_emb + lk * D + 4 * lane);
         f_view[s] = ld4(a.cate_emb + vw * D + 4 * lane);
         f_item[s] = ld4(item_row<SHARDED>(a, iid) + 4 * lane);
-        if (a.item_mm) {
-          xm = ld4s(a.item_mm + b * D + 4 * lane);
-        } else {
-          xm = ld4(a.mm_table + iid * D + 4 * lane);
-          if (a.save) st4(a.xmm + b * D + 4 * lane, xm);   // wgrad of mm_proj.0.weight needs the gathered rows
+        if (!EXTP) {
+          if (a.item_mm) {
+            xm = ld4s(a.item_mm + b * D + 4 * lane);
+          } else {
+            xm = ld4(a.mm_table + iid * D + 4 * lane);
+            if (a.save) st4(a.xmm + b * D + 4 * lane, xm);   // wgrad of mm_proj.0.weight needs the gathered rows
+          }
+          if (a.save && a.pkX.mode) store_packed4(a.pkX.base, a.pkX.lo_off, a.pkX.mode, b * D + 4 * lane, xm);
         }
-        if (a.save && a.pkX.mode) store_packed4(a.pkX.base, a.pkX.lo_off, a.pkX.mode, b * D + 4 * lane, xm);
         int nvalid = 0;
         float4 acc = f4(0.f);
         if (a.seq != nullptr) {
@@ -124,19 +130,23 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
           a.cnt[b] = cntv[s];
         }
       }
-      // stage the multimodal vector k-major: xs[k][s]
-      xs[(4 * lane + 0) * EMB_SPW + s] = xm.x;
-      xs[(4 * lane + 1) * EMB_SPW + s] = xm.y;
-      xs[(4 * lane + 2) * EMB_SPW + s] = xm.z;
-      xs[(4 * lane + 3) * EMB_SPW + s] = xm.w;
+      if (!EXTP) {   // stage the multimodal vector k-major: xs[k][s]
+        xs[(4 * lane + 0) * EMB_SPW + s] = xm.x;
+        xs[(4 * lane + 1) * EMB_SPW + s] = xm.y;
+        xs[(4 * lane + 2) * EMB_SPW + s] = xm.z;
+        xs[(4 * lane + 3) * EMB_SPW + s] = xm.w;
+      }
     }
     __syncwarp();
     // projection: y[s][4*lane + c] = sum_k x[s][k] * W[4*lane + c][k]   (ref :106)
     float4 y[EMB_SPW];
 #pragma unroll
-    for (int s = 0; s < EMB_SPW; ++s) y[s] = f4(0.f);
+    for (int s = 0; s < EMB_SPW; ++s) {
+      const long long b = g * EMB_SPW + s;
+      y[s] = (EXTP && b < a.B) ? ld4s(a.yproj + b * D + 4 * lane) : f4(0.f);      // EXTP: x W^T + b from the GEMM
+    }
 #pragma unroll 8
-    for (int k = 0; k < D; ++k) {
+    for (int k = 0; k < (EXTP ? 0 : D); ++k) {
       float xv[EMB_SPW];
       if (EMB_SPW == 2) {
         const float2 t = *reinterpret_cast<const float2*>(xs + k * EMB_SPW);
@@ -228,35 +238,42 @@ __global__ void __launch_bounds__(EMB_WARPS * 32, 2) embed_senet_fwd_kernel(Embe
   }
 }
 
-size_t embed_fwd_smem() { return (size_t)(D * D + EMB_WARPS * D * EMB_SPW) * sizeof(float); }
+size_t embed_fwd_smem(bool extp) { return extp ? 0 : (size_t)(D * D + EMB_WARPS * D * EMB_SPW) * sizeof(float); }
 
-template <int SE_R>
+template <int SE_R, bool EXTP>
 static int launch_fwd_r(const EmbedFwdArgs& a, unsigned blocks, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
-  if (!attr_set) {
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<false, SE_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<true, SE_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!attr_set && smem > 0) {
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<false, SE_R, EXTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBN_CHECK_CUDA(cudaFuncSetAttribute(embed_senet_fwd_kernel<true, SE_R, EXTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  if (a.nshard > 0) embed_senet_fwd_kernel<true, SE_R><<<blocks, EMB_WARPS * 32, smem, st>>>(a);
-  else embed_senet_fwd_kernel<false, SE_R><<<blocks, EMB_WARPS * 32, smem, st>>>(a);
+  if (a.nshard > 0) embed_senet_fwd_kernel<true, SE_R, EXTP><<<blocks, EMB_WARPS * 32, smem, st>>>(a);
+  else embed_senet_fwd_kernel<false, SE_R, EXTP><<<blocks, EMB_WARPS * 32, smem, st>>>(a);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
 }
 
 // SENET hidden width = max(1, 6 // reduction_ratio) (ref :13): 3 for the reference's ratio 2; 6 / 2 / 1 for ratios 1 / 3 / >= 4
 int launch_embed_senet_fwd(const EmbedFwdArgs& a, cudaStream_t st) {
-  const size_t smem = embed_fwd_smem();
+  const bool extp = a.yproj != nullptr;
+  const size_t smem = embed_fwd_smem(extp);
   const long long ngroups = (a.B + EMB_SPW - 1) / EMB_SPW;
   long long blocks = (ngroups + EMB_WARPS - 1) / EMB_WARPS;
-  const long long cap = 2LL * num_sms();  // persistent: 2 resident CTAs per SM (72 KB smem each; 3 per SM measured slower: 342 vs 320 us)
+  // persistent: 2 resident CTAs per SM with the in-kernel projection (72 KB smem each; 3 per SM measured slower: 342 vs 320 us),
+  // 3 without it
+  const long long cap = (extp ? 3LL : 2LL) * num_sms();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  switch (a.se_r) {
-    case 1: return launch_fwd_r<1>(a, (unsigned)blocks, smem, st);
-    case 2: return launch_fwd_r<2>(a, (unsigned)blocks, smem, st);
-    case 3: return launch_fwd_r<3>(a, (unsigned)blocks, smem, st);
-    case 6: return launch_fwd_r<6>(a, (unsigned)blocks, smem, st);
+  switch (a.se_r * 2 + (extp ? 1 : 0)) {
+    case 2: return launch_fwd_r<1, false>(a, (unsigned)blocks, smem, st);
+    case 3: return launch_fwd_r<1, true>(a, (unsigned)blocks, smem, st);
+    case 4: return launch_fwd_r<2, false>(a, (unsigned)blocks, smem, st);
+    case 5: return launch_fwd_r<2, true>(a, (unsigned)blocks, smem, st);
+    case 6: return launch_fwd_r<3, false>(a, (unsigned)blocks, smem, st);
+    case 7: return launch_fwd_r<3, true>(a, (unsigned)blocks, smem, st);
+    case 12: return launch_fwd_r<6, false>(a, (unsigned)blocks, smem, st);
+    case 13: return launch_fwd_r<6, true>(a, (unsigned)blocks, smem, st);
   }
   FBN_REQUIRE(false, FBN_ERR_SHAPE, "SENET hidden width %d is not one of 1, 2, 3, 6 (= max(1, 6 // reduction_ratio))", a.se_r);
 }

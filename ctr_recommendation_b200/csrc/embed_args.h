@@ -13,6 +13,7 @@ struct EmbedFwdArgs {
   const float* se_w1; const float* se_b1; const float* se_w2; const float* se_b2;
   const void* item_id; const void* likes; const void* views; const void* seq;
   const float* item_mm; const float* mm_table;
+  const float* yproj;  // optional (B,128): item_emb_d128 x mm_w^T + mm_b computed beforehand (tcgen05 GEMM); the kernel then skips its own projection
   int idx_dtype, seq_dtype;
   long long B; int L; long long item_rows; int cate_rows;
   int save;            // write the tensors backward needs

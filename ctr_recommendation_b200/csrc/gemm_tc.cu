@@ -1382,7 +1382,9 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     const long long pair_ctas = 2 * cdiv(g.M, 256) * cdiv(g.N, TC2_BN) * g.splits;
     // one bf16 pass with K <= 512 is epilogue-bound: the persistent single-CTA tile loop beats the pair kernel there
     const long long single_tiles = cdiv(g.M, TC_BM) * (g.N / TC_BN);
-    const bool persist = MODE == FBN_PREC_BF16 && g.splits == 1 && g.K <= 512 && single_tiles >= 2LL * num_sms();
+    // (and a short-K, 128-wide tf32x3 GEMM -- the item_emb_d128 projection -- cannot pair at all: the tile loop hides its epilogue too)
+    const bool persist = g.splits == 1 && single_tiles >= 2LL * num_sms() &&
+                         (MODE == FBN_PREC_BF16 ? g.K <= 512 : (g.K <= 256 && g.N == TC_BN));
     if (g_tc_pair && !use_persistent(persist) && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {
       if (g_tc_pair_persistent && g.N / 128 <= 64) {
         if (a_mn && b_mn) rc = launch_tc2p<MODE, true, true>(maps, t, st);
