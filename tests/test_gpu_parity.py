@@ -348,6 +348,7 @@ def test_full_batch_forward_backward_vs_oracle(gpu, precision, B, id_dist):
     logit = model.workspace_view("logit", (B,)).cpu().numpy()
     A1 = model.workspace_view("A1", (B, 512)).cpu().numpy()
     A2 = model.workspace_view("A2", (B, 256)).cpu().numpy()
+    img = model.workspace_view("X5", (B, 5, 128))[:, 3].cpu().numpy()          # the projected field after its ReLU (ref :108)
     got = gpu["named_grads"](model)
     # fp64 oracle: over 1e4..4e4 samples the fp32 oracle's OWN summation error in the batch reductions (item rows of hot
     # Zipf ids, SENET / bias gradients) is as large as the tolerance, so the CUDA path is held to 1e-5 of the exact value
@@ -362,13 +363,14 @@ def test_full_batch_forward_backward_vs_oracle(gpu, precision, B, id_dist):
     # ---- (1) ReLU decisions: kept elements only (a dropped element's gate is unobservable and irrelevant) ----
     g1 = np.where(m1 > 0, A1 > 0, cache["g1"])
     g2 = np.where(m2 > 0, A2 > 0, cache["g2"])
-    for g, go, Y in ((g1, cache["g1"], cache["Y1"]), (g2, cache["g2"], cache["Y2"])):
+    g3 = img > 0
+    for g, go, Y in ((g1, cache["g1"], cache["Y1"]), (g2, cache["g2"], cache["Y2"]), (g3, cache["g_img"], cache["ln"])):
         mis = g != go
         band = tol * max(1.0, float(np.abs(Y).max()))
         assert mis.sum() <= max(4, int(4 * tol * Y.size)), ("ReLU decisions differ", int(mis.sum()))
         assert (not mis.any()) or float(np.abs(Y[mis]).max()) <= band, ("ReLU flip outside the band", float(np.abs(Y[mis]).max()))
     # ---- (2) gradients under identical decisions ----
-    prob_g, cache_g = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False, relu_gates=(g1, g2), dtype=od)
+    prob_g, cache_g = orc.forward(dict(P), batch, train=True, masks=(m1, m2), update_running=False, relu_gates=(g1, g2, g3), dtype=od)
     _, dprob = orc.bce_loss(prob_g, labels, od)
     G = orc.backward(P, cache_g, dprob)
     assert set(got) == set(G)
