@@ -209,3 +209,45 @@ def test_loader_batched_fetch_and_resident_mm_mode(tmp_path):
                            num_workers=0, max_len=20, with_mm=False)
     seen = torch.cat([b["user_id"] for b, _ in a])
     assert seen.numel() == 200 and sorted(seen.tolist()) == sorted(ds.darray[:, ds.column_index["user_id"]].tolist())
+
+
+def test_general_model_field_specs_and_dispatch():
+    """Host logic of the F-field model (no GPU needed to construct it): field descriptors for plain lookups, shared tables, bags and
+    padding rows; build_model dispatch on feature_map["fields"]; errors for malformed specs."""
+    from ctr_recommendation_b200 import GeneralFiBiNET, MM_FiBiNET, build_model
+    fm = {"fields": [{"name": "user_id", "vocab": 50}, ("likes_level", 11), {"name": "views_level", "table": "likes_level"},
+                     {"name": "item_id", "vocab": 100, "padding_idx": 0}, {"name": "item_seq", "table": "item_id", "bag": 20},
+                     {"name": "item_tags", "vocab": 30, "bag": 5}], "senet_reduction": 3, "bilinear_type": "each"}
+    m = build_model(fm, {"embedding_dim": 128})
+    assert isinstance(m, GeneralFiBiNET) and isinstance(build_model(None, {"embedding_dim": 128}), MM_FiBiNET)
+    # {first row of the table, vocabulary, first id column, bag length, padding id}
+    assert m.field_desc.tolist() == [[0, 50, 0, 1, -1], [50, 11, 1, 1, -1], [50, 11, 2, 1, -1], [61, 100, 3, 1, 0], [61, 100, 4, 20, 0],
+                                     [161, 30, 24, 5, 0]]
+    assert m.col_field.tolist() == [0, 1, 2, 3] + [4] * 20 + [5] * 5 and m.id_cols == 29
+    assert m.emb.weight.shape == (191, 128) and torch.all(m.emb.weight[61] == 0) and m._pad_rows == [61]
+    assert m.k1 == (6 + 15) * 128 and m.senet.reduced_size == 2 and len(m.bilinear.weights()) == 5
+    for bad in ([("a", 5)], [("a", 5), ("a", 6)], [("a", 5), {"name": "b", "table": "zzz"}], [("a", 0), ("b", 3)],
+                [("a", 5), {"name": "b", "vocab": 3, "bag": 0}]):
+        with pytest.raises(ValueError):
+            GeneralFiBiNET(bad)
+    with pytest.raises(RuntimeError):                       # no CPU path
+        m({"ids": torch.zeros(4, 29, dtype=torch.int64)})
+
+
+def test_fused_adagrad_is_a_torch_optimizer_and_flat_layout_ends_with_the_mlp1_bucket():
+    from ctr_recommendation_b200 import FusedAdagrad, FusedAdam, build_model
+    model = build_model(None, {"embedding_dim": 128})
+    opt = FusedAdagrad(model, lr=1e-2, weight_decay=1e-5)
+    assert set(opt.param_groups[0]) >= {"lr", "lr_decay", "eps", "weight_decay", "initial_accumulator_value"}
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=0.1, total_steps=10, cycle_momentum="betas" in opt.defaults)
+    sched.step()
+    assert opt.param_groups[0]["lr"] != 1e-2
+    assert all(id(p) != id(model.user_emb.weight) for p in opt.param_groups[0]["params"])      # user_emb: no state, like grad None
+    model._ensure_flat()
+    off = model._bucket1_offset()
+    names = {id(p): n for n, p in model.named_parameters()}
+    tail = [names[id(p)] for (f, pl), (o, _) in zip(model._dense_params(), model._layout) if o >= off for p in pl]
+    assert tail == ["mlp.0.weight", "mlp.0.bias", "mlp.1.weight", "mlp.1.bias"]
+    assert model._flat.numel() - off == 512 * 2688 + 3 * 512
+    with pytest.raises(TypeError):
+        FusedAdam(torch.nn.Linear(2, 2))
