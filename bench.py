@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("FBN_BENCH_BATCH", "65536")),
                     help="per-GPU batch (BASELINE config 2 sweeps 1K-64K; 65536 is its largest point)")
-    ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "f16x3", "bf16"])
     ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows per CPU-baseline step (0 = the per-GPU batch itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,7 +304,7 @@ def run_ours(args):
     out = {
         "metric": METRIC if not infer else "inference samples/sec FiBiNET MicroLens-shape (Prediction.py path)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "dtype": DTYPE_LABEL[args.precision], "data": "synthetic",
         "config": workload_config(args, world, infer, sharded, model._shard.item_rows if sharded else None),
         "precision": args.precision, "launch": "eager" if args.eager else "cuda-graph",
         "dp_collectives": (None if world == 1 or sharded else
@@ -482,7 +482,12 @@ def kernel_rooflines(args, model, dev_batch, peaks, lib):
     tstage("mlp1_dgrad_gemm", "mlp1_dgrad", gemm_flops)
     tstage("mlp1_wgrad_gemm", "mlp1_wgrad", gemm_flops)       # includes the fixed-order split-K reduction
     out["mlp1_gemm"] = out["mlp1_fwd_gemm"]
-    passes = {"tf32x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+    if args.precision == "f16x3":      # the amax + fp16 hi|lo split of the MLP input that precedes the MLP-1 forward GEMM in this mode
+        _lib.check(lib.fbn_time_stage(C.byref(P), C.byref(bs), _lib.ptr(ws), ws.numel(), b"pack_c", _lib.ptr(flush), flush.numel() * 4,
+                                      8, C.byref(msf), st), "fbn_time_stage")
+        pk_bytes = B * live_cols * 12                        # two reads of the fp32 row (amax pass, split pass) + the 4-byte hi|lo pair
+        out["pack_mlp_input"] = {"ms": float(msf.value), "bytes": pk_bytes, "GBps": pk_bytes / float(msf.value) / 1e6,
+                                 "frac": pk_bytes / float(msf.value) / 1e6 / peaks["hbm"]}
     # the kernel with the largest share of the step (ncu launch list, profiles/): the MLP-1 data-gradient GEMM
     dom = max(("mlp1_dgrad_gemm", "mlp1_fwd_gemm", "mlp1_wgrad_gemm"), key=lambda k: out[k]["ms"])
     g = out[dom]
@@ -503,16 +508,23 @@ def kernel_rooflines(args, model, dev_batch, peaks, lib):
     gk["frac_8d"] = gk["GBps_8d"] / peaks["hbm"]
     roof = {"bound": "tensor", "kernel": f"gemm_tc2p_kernel (MLP-1 {shapes[dom]})", "achieved": g["TFLOPs"], "peak": peaks["tf"],
             "unit": "TFLOP/s", "frac": g["frac_of_bf16_peak"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 dense (burst)",
-            "note": f"dominant kernel of the step; algorithmic FLOPs 2*B*1920*512 (structural-zero blocks not counted); precision "
-                    f"{args.precision} issues {passes}x these on the tensor pipe and kind::tf32 runs at half the bf16 rate used as "
-                    "denominator, so 1/6 = 0.167 is this scheme's ceiling (tools/split_precision_sim.py: cheaper operand splits miss the "
-                    "1e-5 gradient tolerance)",
+            "note": "dominant kernel of the step; algorithmic FLOPs 2*B*1920*512 (structural-zero blocks not counted); " + PREC_NOTE[args.precision],
             "all_mlp1_gemms": {k: {"ms": out[k]["ms"], "TFLOPs": out[k]["TFLOPs"], "frac": out[k]["frac_of_bf16_peak"]}
                                for k in ("mlp1_fwd_gemm", "mlp1_dgrad_gemm", "mlp1_wgrad_gemm")},
             "hbm_kernels": {"adam_table": {"achieved_GBps": out["adam_table"]["GBps"], "frac": out["adam_table"]["frac"]},
                             "gather_senet_fwd": {"achieved_GBps_8d_bytes": gk["GBps_8d"], "frac_8d_bytes": gk["frac_8d"],
                                                  "achieved_GBps_incl_saved": gk["GBps"], "frac_incl_saved": gk["frac"]}}}
     return {"roofline": roof, "kernels": out}
+
+
+DTYPE_LABEL = {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "f16x3": "f16x3(f32-grade)", "bf16": "bf16"}
+PREC_NOTE = {
+    "tf32x3": "precision tf32x3 issues 3x these on the tensor pipe and kind::tf32 runs at half the bf16 rate used as denominator, so "
+              "1/6 = 0.167 is this scheme's ceiling",
+    "f16x3": "precision f16x3 (fp16 hi|lo operands under one power-of-two scale per tensor, fp32-grade like tf32x3: "
+             "tools/split_precision_sim.py) issues 3x these as kind::f16 MMAs at the bf16 rate used as denominator, so 1/3 = 0.333 is "
+             "this scheme's ceiling",
+    "bf16": "one bf16 pass", "fp32": "SIMT fp32 FMA (no tensor cores)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -663,7 +675,7 @@ def run_general(args):
     r = general_measure(args.precision, args.bilinear, args.fields, args.field_vocab, args.batch, args.steps, args.warmup, args.pool)
     out = {"metric": "train samples/sec F-field FiBiNET (general.py)", "value": r["value"], "unit": UNIT, "n_gpus": 1,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3(f32-grade)", "bf16": "bf16"}[args.precision], "data": "synthetic",
+           "vs_baseline": None, "dtype": DTYPE_LABEL[args.precision], "data": "synthetic",
            "config": r["config"], "gpu_launches": r["gpu_launches"], "mlp_tflops_useful": r["mlp_tflops_useful"]}
     print(json.dumps(out), flush=True)
 

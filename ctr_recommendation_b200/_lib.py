@@ -15,8 +15,11 @@ IDX_I32, IDX_I64, IDX_F64, IDX_F32 = 0, 1, 2, 3
 PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
 BILINEAR_ALL, BILINEAR_EACH, BILINEAR_INTERACTION = 0, 1, 2
 PREC_TF32X2 = 3
+PREC_F16X3 = 4
 BWD_CHAIN, BWD_LEAF1, BWD_LEAF2 = 1, 2, 4
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}          # what the model path accepts
+# what the model path accepts.  "f16x3": the long-K MLP GEMMs as three fp16 passes under one power-of-two scale per operand tensor
+# (fp32-grade like tf32x3, at the bf16 MMA rate and half the operand bytes); its short-K GEMMs stay tf32x3
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16, "f16x3": PREC_F16X3}
 GEMM_PRECISIONS = dict(PRECISIONS, tf32x2=PREC_TF32X2)                               # fbn_gemm only (K-major x K-major)
 BILINEAR_TYPES = {"all": BILINEAR_ALL, "field_all": BILINEAR_ALL, "each": BILINEAR_EACH, "field_each": BILINEAR_EACH,
                   "interaction": BILINEAR_INTERACTION, "field_interaction": BILINEAR_INTERACTION}

@@ -124,18 +124,22 @@ void carve_workspace(Workspace& w, void* base, int64_t B, int64_t L, int64_t row
   size_t gs = 4096;   // every operand of the model path is pre-packed into the pk_* regions below
   w.gemm_scratch_bytes = gs;
   w.gemm_scratch = take(gs);
-  const int PX = FBN_PREC_TF32X3;   // sized for the larger (hi|lo) format
-  w.pk_C = take(packed_bytes(Bp, K1, PX));
-  w.pk_A1 = take(packed_bytes(Bp, H1, PX));
-  w.pk_dH2 = take(packed_bytes(Bp, H2, PX));
-  w.pk_dH1 = take(packed_bytes(Bp, H1, PX));
-  w.pk_dT = take(packed_bytes(Bp, 10 * D, PX));
-  w.pk_dy = take(packed_bytes(Bp, D, PX));
-  w.pk_xmm = take(packed_bytes(Bp, D, PX));
-  w.pk_w1 = take(packed_bytes(H1, K1, PX));
-  w.pk_w2 = take(packed_bytes(H2, H1, PX));
-  w.pk_bil = take(packed_bytes(FBN_PAIRS * D, D, PX));
-  w.pk_mmw = take(packed_bytes(D, D, PX));
+  // each region is sized for the larger of the formats it may hold (tf32 hi|lo: 8 bytes / element; f16x3: 4 + its scale record)
+  auto pkb = [](long long r, long long c) { return std::max(packed_bytes(r, c, FBN_PREC_TF32X3), packed_bytes(r, c, FBN_PREC_F16X3)); };
+  w.pk_C = take(pkb(Bp, K1));
+  w.pk_A1 = take(pkb(Bp, H1));
+  w.pk_dH2 = take(pkb(Bp, H2));
+  w.pk_dH1 = take(pkb(Bp, H1));
+  w.pk_dT = take(pkb(Bp, 10 * D));
+  w.pk_dy = take(pkb(Bp, D));
+  w.pk_xmm = take(pkb(Bp, D));
+  w.pk_w1 = take(pkb(H1, K1));
+  w.pk_w2 = take(pkb(H2, H1));
+  w.pk_bil = take(pkb(FBN_PAIRS * D, D));
+  w.pk_mmw = take(pkb(D, D));
+  // f16x3: the MLP input is needed twice -- its field blocks as tf32 hi|lo (pk_C, written by the gather kernel for the bilinear
+  // transforms) and the whole live row as fp16 hi|lo under one scale (the MLP-1 forward / weight-gradient GEMMs)
+  w.pk16_C = take(packed_bytes(Bp, K1, FBN_PREC_F16X3));
   w.total_bytes = off;
 }
 
@@ -150,40 +154,69 @@ int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, 
 struct PkReg {
   int prec = FBN_PREC_FP32;
   cudaStream_t st = nullptr;
-  struct E { const float* src; size_t n; Packed pk; } e[16];
+  struct E { const float* src; size_t n; Packed pk; int fmt; } e[24];
   int ne = 0;
   bool on() const { return prec != FBN_PREC_FP32; }
-  int esz() const { return prec == FBN_PREC_TF32X3 ? 4 : 2; }
-  void describe(const float* src, long long rows, long long cols, void* region) {
+  // FBN_PREC_F16X3 is a two-format mode: the operands of the long-K MLP GEMMs are fp16 hi|lo under a per-tensor scale (found by
+  // an amax pass over the finished tensor, so they are packed AFTER their producer), everything the short-K GEMMs read keeps
+  // the tf32 hi|lo format written by the producer kernels themselves
+  bool mlp16() const { return prec == FBN_PREC_F16X3; }
+  int lowfmt() const { return mlp16() ? FBN_PREC_TF32X3 : prec; }
+  int mlpfmt() const { return prec; }
+  static int esz(int fmt) { return fmt == FBN_PREC_TF32X3 ? 4 : 2; }
+  void describe(const float* src, long long rows, long long cols, void* region, int fmt = -1) {
     if (!on()) return;
-    for (int i = 0; i < ne; ++i) if (e[i].src == src) return;
-    e[ne].src = src; e[ne].n = (size_t)rows * cols; e[ne].pk = packed_describe(region, rows, cols);
+    if (fmt < 0) fmt = lowfmt();
+    for (int i = 0; i < ne; ++i) if (e[i].src == src && e[i].fmt == fmt) return;
+    e[ne].src = src; e[ne].n = (size_t)rows * cols; e[ne].pk = packed_describe(region, rows, cols, fmt); e[ne].fmt = fmt;
     ++ne;
   }
-  int pack(const float* src, long long rows, long long cols, void* region, unsigned long long colmask = ~0ull) {
+  int pack(const float* src, long long rows, long long cols, void* region, unsigned long long colmask = ~0ull, int fmt = -1) {
     if (!on()) return FBN_OK;
-    describe(src, rows, cols, region);
+    if (fmt < 0) fmt = lowfmt();
+    describe(src, rows, cols, region, fmt);
     Packed tmp;
-    return pack_operand(src, cols, rows, cols, prec, region, colmask, &tmp, st);
+    return pack_operand(src, cols, rows, cols, fmt, region, colmask, &tmp, st);
   }
+  // an operand of the MLP GEMMs only (weights, or an activation after its producer when the producer could not pack it)
+  int pack_mlp(const float* src, long long rows, long long cols, void* region, unsigned long long colmask = ~0ull) {
+    return pack(src, rows, cols, region, colmask, mlpfmt());
+  }
+  void describe_mlp(const float* src, long long rows, long long cols, void* region) { describe(src, rows, cols, region, mlpfmt()); }
   // register `src` as packed-by-its-producer and return the destination descriptor for that kernel
   PackDst dst(const float* src, long long rows, long long cols, void* region) {
     PackDst d;
     if (!on()) return d;
-    describe(src, rows, cols, region);
-    const Packed pk = packed_describe(region, rows, cols);
-    d.base = pk.data; d.pitch = pk.pitch; d.lo_off = pk.lo_off; d.mode = prec;
+    describe(src, rows, cols, region, lowfmt());
+    const Packed pk = packed_describe(region, rows, cols, lowfmt());
+    d.base = pk.data; d.pitch = pk.pitch; d.lo_off = pk.lo_off; d.mode = lowfmt();
     return d;
   }
-  Packed find(const float* p) const {
+  // the same for a tensor only the MLP GEMMs read: in f16x3 mode the producer writes fp32 only and the caller follows up with
+  // after_mlp() once the tensor is complete
+  PackDst dst_mlp(const float* src, long long rows, long long cols, void* region) {
+    return mlp16() ? PackDst() : dst(src, rows, cols, region);
+  }
+  int after_mlp(const float* src, long long rows, long long cols, void* region, unsigned long long colmask = ~0ull) {
+    return mlp16() ? pack_mlp(src, rows, cols, region, colmask) : FBN_OK;
+  }
+  Packed find(const float* p, int fmt) const {
     for (int i = 0; i < ne; ++i)
-      if (p >= e[i].src && p < e[i].src + e[i].n) return e[i].pk.view_cols((long long)(p - e[i].src), esz());
+      if (e[i].fmt == fmt && p >= e[i].src && p < e[i].src + e[i].n) return e[i].pk.view_cols((long long)(p - e[i].src), esz(fmt));
     return Packed();
   }
   int run(GemmArgs g, Workspace& w) const { return run_on(g, w, st); }
   int run_on(GemmArgs g, Workspace& w, cudaStream_t s) const {
-    if (on()) { g.pkA = find(g.A); g.pkB = find(g.B); }
-    return gemm(g, prec, w.gemm_scratch, w.gemm_scratch_bytes, s);
+    int fmt = prec;
+    if (on()) {
+      fmt = lowfmt();
+      if (mlp16()) {      // both operands available as fp16 hi|lo -> the f16x3 kernel, otherwise the tf32x3 one
+        const Packed a16 = find(g.A, FBN_PREC_F16X3), b16 = find(g.B, FBN_PREC_F16X3);
+        if (a16.data && b16.data) { g.pkA = a16; g.pkB = b16; return gemm(g, FBN_PREC_F16X3, w.gemm_scratch, w.gemm_scratch_bytes, s); }
+      }
+      g.pkA = find(g.A, fmt); g.pkB = find(g.B, fmt);
+    }
+    return gemm(g, fmt, w.gemm_scratch, w.gemm_scratch_bytes, s);
   }
 };
 static thread_local PkReg tl_reg;   // rebuilt at the start of every fbn_forward / fbn_backward call
@@ -240,7 +273,7 @@ static int check_common(const fbn_params_t* p, const fbn_batch_t* b, void* ws, s
   FBN_REQUIRE(b->idx_dtype >= FBN_IDX_I32 && b->idx_dtype <= FBN_IDX_F32, FBN_ERR_DTYPE, "bad idx_dtype");
   FBN_REQUIRE(b->seq_dtype == FBN_IDX_I32 || b->seq_dtype == FBN_IDX_I64, FBN_ERR_DTYPE, "item_seq must be int32 or int64");
   FBN_REQUIRE(p->bilinear_type >= FBN_BILINEAR_ALL && p->bilinear_type <= FBN_BILINEAR_INTERACTION, FBN_ERR_ARG, "bad bilinear_type");
-  FBN_REQUIRE(p->precision >= FBN_PREC_FP32 && p->precision <= FBN_PREC_BF16, FBN_ERR_ARG, "bad precision");
+  FBN_REQUIRE((p->precision >= FBN_PREC_FP32 && p->precision <= FBN_PREC_BF16) || p->precision == FBN_PREC_F16X3, FBN_ERR_ARG, "bad precision");
   const void* ptrs[] = {p->item_emb, p->cate_emb, p->mm_w, p->mm_b, p->ln_g, p->ln_b, p->bil_w, p->w1, p->b1, p->bn1_g, p->bn1_b,
                         p->bn1_mean, p->bn1_var, p->w2, p->b2, p->bn2_g, p->bn2_b, p->bn2_mean, p->bn2_var, p->w3, ws,
                         b->item_mm, b->mm_table};
@@ -400,8 +433,8 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   // the weights are converted on the side stream while the gather kernel runs
   const bool parf = tl_reg.on() && side_ready(st);
   if (parf) { RC(side_fork(st, 4)); tl_reg.st = g_side.s; }
-  RC(tl_reg.pack(p->w1, H1, K1, w.pk_w1, active_mask()));
-  RC(tl_reg.pack(p->w2, H2, H1, w.pk_w2));
+  RC(tl_reg.pack_mlp(p->w1, H1, K1, w.pk_w1, active_mask()));
+  RC(tl_reg.pack_mlp(p->w2, H2, H1, w.pk_w2));
   RC(tl_reg.pack(p->bil_w, (long long)nW * D, D, w.pk_bil));
   tl_reg.st = st;
 
@@ -414,7 +447,8 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   STAGE("fwd:embed+senet (join weight packing)");
   RC(bilinear_transform_fwd(p, w, st));
   STAGE("fwd:bilinear transforms");
-  RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, pkC, st));
+  RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, tl_reg.mlp16() ? PackDst() : pkC, st));   // the pair blocks feed the MLP only
+  RC(tl_reg.after_mlp(w.C, B, K1, w.pk16_C, active_mask()));
   STAGE("fwd:bilinear pairs");
 
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
@@ -426,7 +460,8 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
   DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
-  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst(w.A1, B, H1, w.pk_A1), st));
+  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst_mlp(w.A1, B, H1, w.pk_A1), st));
+  RC(tl_reg.after_mlp(w.A1, B, H1, w.pk_A1));
   STAGE("fwd:bn1 stats+act");
 
   GemmArgs g2;
@@ -533,15 +568,16 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
   tl_reg.prec = p->precision; tl_reg.st = st;
   {
     const int nWr = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
-    tl_reg.describe(p->w1, H1, K1, w.pk_w1);
-    tl_reg.describe(p->w2, H2, H1, w.pk_w2);
+    tl_reg.describe_mlp(p->w1, H1, K1, w.pk_w1);
+    tl_reg.describe_mlp(p->w2, H2, H1, w.pk_w2);
     tl_reg.describe(p->bil_w, (long long)nWr * D, D, w.pk_bil);
     tl_reg.describe(w.C, B, K1, w.pk_C);
-    tl_reg.describe(w.A1, B, H1, w.pk_A1);
+    if (tl_reg.mlp16()) tl_reg.describe_mlp(w.C, B, K1, w.pk16_C);
+    tl_reg.describe_mlp(w.A1, B, H1, w.pk_A1);
     tl_reg.describe(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm);
     if (!chain) {      // produced by the CHAIN phase of an earlier call
-      tl_reg.describe(w.dH2, B, H2, w.pk_dH2);
-      tl_reg.describe(w.dH1, B, H1, w.pk_dH1);
+      tl_reg.describe_mlp(w.dH2, B, H2, w.pk_dH2);
+      tl_reg.describe_mlp(w.dH1, B, H1, w.pk_dH1);
       tl_reg.describe(w.dT, B, (long long)nT * D, w.pk_dT);
       tl_reg.describe(w.dy, B, D, w.pk_dy);
     }
@@ -609,7 +645,8 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3,
                       st));
     RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
-                     tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
+                     tl_reg.dst_mlp(w.dH2, B, H2, w.pk_dH2), st));
+    RC(tl_reg.after_mlp(w.dH2, B, H2, w.pk_dH2));
     STAGE("bwd:head + bn2");
     if (par && leaf2) RC(side_fork(st, 0));
     if (leaf2) RC(leaf_layer2());
@@ -622,7 +659,8 @@ static int backward_impl(const fbn_params_t* p, const fbn_batch_t* b, void* ws, 
     // ---- layer 1 ----
     RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
     RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
-                     tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
+                     tl_reg.dst_mlp(w.dH1, B, H1, w.pk_dH1), st));
+    RC(tl_reg.after_mlp(w.dH1, B, H1, w.pk_dH1));
     STAGE("bwd:bn1");
     if (par && leaf1) RC(side_fork(st, 1));
     if (leaf1) RC(leaf_layer1());
@@ -742,20 +780,20 @@ static void carve_tower(TowerWs& w, void* base, int64_t B, int64_t k1) {
   w.partial_floats = pf;
   w.partial = (float*)take(pf * f);
   w.partial_side = (float*)take((size_t)16 * 148 * 3 * H1 * f);
-  const int PX = FBN_PREC_TF32X3;
-  w.pk_C = take(packed_bytes(Bp, k1, PX));
-  w.pk_A1 = take(packed_bytes(Bp, H1, PX));
-  w.pk_dH2 = take(packed_bytes(Bp, H2, PX));
-  w.pk_dH1 = take(packed_bytes(Bp, H1, PX));
-  w.pk_w1 = take(packed_bytes(H1, k1, PX));
-  w.pk_w2 = take(packed_bytes(H2, H1, PX));
+  auto pkb = [](long long r, long long c) { return std::max(packed_bytes(r, c, FBN_PREC_TF32X3), packed_bytes(r, c, FBN_PREC_F16X3)); };
+  w.pk_C = take(pkb(Bp, k1));
+  w.pk_A1 = take(pkb(Bp, H1));
+  w.pk_dH2 = take(pkb(Bp, H2));
+  w.pk_dH1 = take(pkb(Bp, H1));
+  w.pk_w1 = take(pkb(H1, k1));
+  w.pk_w2 = take(pkb(H2, H1));
   w.total_bytes = off;
 }
 
 static int tower_check(const fbn_params_t* p, const float* c, int64_t batch, int64_t k1, void* ws, size_t ws_bytes) {
   FBN_REQUIRE(p && c && ws, FBN_ERR_ARG, "fbn_tower: null pointer");
   FBN_REQUIRE(batch >= 1 && k1 >= 128 && k1 % 128 == 0, FBN_ERR_SHAPE, "fbn_tower: the input width must be a multiple of 128");
-  FBN_REQUIRE(p->precision >= FBN_PREC_FP32 && p->precision <= FBN_PREC_BF16, FBN_ERR_ARG, "bad precision");
+  FBN_REQUIRE((p->precision >= FBN_PREC_FP32 && p->precision <= FBN_PREC_BF16) || p->precision == FBN_PREC_F16X3, FBN_ERR_ARG, "bad precision");
   const void* ptrs[] = {c, ws, p->w1, p->b1, p->bn1_g, p->bn1_b, p->bn1_mean, p->bn1_var, p->w2, p->b2, p->bn2_g, p->bn2_b, p->bn2_mean,
                         p->bn2_var, p->w3};
   for (const void* q : ptrs) FBN_REQUIRE(q && aligned16(q), FBN_ERR_ALIGN, "fbn_tower: a tensor pointer is missing or not 16-byte aligned");
@@ -796,9 +834,9 @@ extern "C" int fbn_tower_forward(const fbn_params_t* p, const float* c, int64_t 
   const long long B = batch;
   tl_reg = PkReg();
   tl_reg.prec = p->precision; tl_reg.st = st;
-  RC(tl_reg.pack(p->w1, H1, k1, w.pk_w1));
-  RC(tl_reg.pack(p->w2, H2, H1, w.pk_w2));
-  RC(tl_reg.pack(c, B, k1, w.pk_C));
+  RC(tl_reg.pack_mlp(p->w1, H1, k1, w.pk_w1));     // every GEMM of the tower is a long-K MLP GEMM: all operands in the MLP format
+  RC(tl_reg.pack_mlp(p->w2, H2, H1, w.pk_w2));
+  RC(tl_reg.pack_mlp(c, B, k1, w.pk_C));
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   GemmArgs g1;
   g1.A = c; g1.B = p->w1; g1.bias = p->b1; g1.C = w.Hd1; g1.M = B; g1.N = H1; g1.K = k1; g1.lda = k1; g1.ldb = k1; g1.ldc = H1; g1.b_t = 1;
@@ -806,7 +844,8 @@ extern "C" int fbn_tower_forward(const fbn_params_t* p, const float* c, int64_t 
   if (train) RC(bn_train_stats(w.Hd1, B, H1, w.partial, mean1, rstd1, p->bn1_mean, p->bn1_var, st));
   else RC(bn_eval_stats(p->bn1_mean, p->bn1_var, H1, mean1, rstd1, st));
   DropArgs d1; d1.p = train ? dropout_p : 0.f; d1.mask = keep_mask1; d1.seed = seed; d1.offset = offset; d1.stream = 1; d1.step_dev = step_counter_dev;
-  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst(w.A1, B, H1, w.pk_A1), st));
+  RC(bn_act(w.Hd1, mean1, rstd1, p->bn1_g, p->bn1_b, B, H1, d1, w.A1, tl_reg.dst_mlp(w.A1, B, H1, w.pk_A1), st));
+  RC(tl_reg.after_mlp(w.A1, B, H1, w.pk_A1));
   GemmArgs g2;
   g2.A = w.A1; g2.B = p->w2; g2.bias = p->b2; g2.C = w.Hd2; g2.M = B; g2.N = H2; g2.K = H1; g2.lda = H1; g2.ldb = H1; g2.ldc = H2; g2.b_t = 1;
   RC(tl_reg.run(g2, shell));
@@ -833,14 +872,15 @@ extern "C" int fbn_tower_backward(const fbn_params_t* p, const float* c, int64_t
   const float scale = (train && dropout_p > 0.f) ? 1.0f / (1.0f - dropout_p) : 1.0f;
   tl_reg = PkReg();
   tl_reg.prec = p->precision; tl_reg.st = st;
-  tl_reg.describe(p->w1, H1, k1, w.pk_w1);
-  tl_reg.describe(p->w2, H2, H1, w.pk_w2);
-  tl_reg.describe(c, B, k1, w.pk_C);
-  tl_reg.describe(w.A1, B, H1, w.pk_A1);
+  tl_reg.describe_mlp(p->w1, H1, k1, w.pk_w1);
+  tl_reg.describe_mlp(p->w2, H2, H1, w.pk_w2);
+  tl_reg.describe_mlp(c, B, k1, w.pk_C);
+  tl_reg.describe_mlp(w.A1, B, H1, w.pk_A1);
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   RC(head_bwd_stats(dprob, w.prob, w.A2, w.Hd2, mean2, rstd2, p->w3, B, scale, w.partial, w.dlogit, g->bn2_g, g->bn2_b, g->w3, g->b3, st));
   RC(bn_bwd_apply(nullptr, w.dlogit, p->w3, w.A2, w.Hd2, mean2, rstd2, p->bn2_g, g->bn2_g, g->bn2_b, B, H2, scale, train, w.dH2,
-                   tl_reg.dst(w.dH2, B, H2, w.pk_dH2), st));
+                   tl_reg.dst_mlp(w.dH2, B, H2, w.pk_dH2), st));
+  RC(tl_reg.after_mlp(w.dH2, B, H2, w.pk_dH2));
   RC(colsum(w.dH2, B, H2, w.partial, g->b2, st));
   RC(wgrad(w.dH2, H2, w.A1, H1, B, H2, H1, ~0ull, prec, shell, g->w2, st, w.partial));
   {
@@ -850,7 +890,8 @@ extern "C" int fbn_tower_backward(const fbn_params_t* p, const float* c, int64_t
   }
   RC(bn_bwd_stats(w.dH1, w.A1, w.Hd1, mean1, rstd1, B, H1, scale, w.partial, g->bn1_g, g->bn1_b, st));
   RC(bn_bwd_apply(w.dH1, nullptr, nullptr, w.A1, w.Hd1, mean1, rstd1, p->bn1_g, g->bn1_g, g->bn1_b, B, H1, scale, train, w.dH1,
-                   tl_reg.dst(w.dH1, B, H1, w.pk_dH1), st));
+                   tl_reg.dst_mlp(w.dH1, B, H1, w.pk_dH1), st));
+  RC(tl_reg.after_mlp(w.dH1, B, H1, w.pk_dH1));
   RC(colsum(w.dH1, B, H1, w.partial, g->b1, st));
   RC(wgrad(w.dH1, H1, c, k1, B, H1, k1, ~0ull, prec, shell, g->w1, st, w.partial));
   {
@@ -895,13 +936,14 @@ extern "C" int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void*
   tl_reg = PkReg();
   tl_reg.prec = p->precision; tl_reg.st = st;
   const int nW = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
-  tl_reg.describe(p->w1, H1, K1, w.pk_w1);
-  tl_reg.describe(p->w2, H2, H1, w.pk_w2);
+  tl_reg.describe_mlp(p->w1, H1, K1, w.pk_w1);
+  tl_reg.describe_mlp(p->w2, H2, H1, w.pk_w2);
   tl_reg.describe(p->bil_w, (long long)nW * D, D, w.pk_bil);
   const PackDst pkC = tl_reg.dst(w.C, B, K1, w.pk_C);
+  if (tl_reg.mlp16()) tl_reg.describe_mlp(w.C, B, K1, w.pk16_C);
   const PackDst pkX = tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm);
-  tl_reg.describe(w.A1, B, H1, w.pk_A1);
-  tl_reg.describe(w.dH1, B, H1, w.pk_dH1);      // valid after an fbn_backward on this workspace (mlp1_dgrad / mlp1_wgrad)
+  tl_reg.describe_mlp(w.A1, B, H1, w.pk_A1);
+  tl_reg.describe_mlp(w.dH1, B, H1, w.pk_dH1);      // valid after an fbn_backward on this workspace (mlp1_dgrad / mlp1_wgrad)
   const std::string s(stage);
   cudaEvent_t e0, e1;
   FBN_CHECK_CUDA(cudaEventCreate(&e0));
@@ -911,7 +953,8 @@ extern "C" int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void*
     if (flush) FBN_CHECK_CUDA(cudaMemsetAsync(flush, it, flush_bytes, st));
     FBN_CHECK_CUDA(cudaEventRecord(e0, st));
     if (s == "bil_gemm") RC(bilinear_transform_fwd(p, w, st));
-    else if (s == "bil_pairs") RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, pkC, st));
+    else if (s == "bil_pairs") RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, tl_reg.mlp16() ? PackDst() : pkC, st));
+    else if (s == "pack_c") RC(tl_reg.pack_mlp(w.C, B, K1, tl_reg.mlp16() ? w.pk16_C : w.pk_C, active_mask()));   // f16x3: amax + split of the MLP input
     else if (s == "embed") RC(run_embed_fwd(p, b, w, 1, st, pkC, pkX));
     else if (s == "mlp1") {
       GemmArgs g1;

@@ -198,6 +198,7 @@ struct Workspace {
   // tcgen05 operands packed once per step (tf32 hi|lo or bf16), natural layout
   void* pk_C; void* pk_A1; void* pk_dH2; void* pk_dH1; void* pk_dT; void* pk_dy; void* pk_xmm;
   void* pk_w1; void* pk_w2; void* pk_bil; void* pk_mmw;
+  void* pk16_C;      // f16x3: the live MLP-input row as fp16 hi|lo (pk_C then holds the tf32 copy of the field blocks only)
   size_t total_bytes;
 };
 

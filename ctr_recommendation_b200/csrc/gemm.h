@@ -5,12 +5,14 @@
 
 namespace fbn {
 
-// An operand already converted to the tcgen05 format (tf32 hi|lo split or bf16) in its natural row-major layout.
+// An operand already converted to the tcgen05 format (tf32 hi|lo split, fp16 hi|lo split under one scale, or bf16) in its natural
+// row-major layout.
 struct Packed {
   void* data = nullptr;      // hi part (or the bf16 copy); (rows, pitch) elements
   long long pitch = 0;       // elements per row (multiple of 8)
   long long lo_off = 0;      // element offset of the lo part (tf32x3)
   long long rows = 0, cols = 0;
+  float* scale = nullptr;    // f16x3: device record {s, 1/s, amax} of the tensor's power-of-two scale (written by the pack pass)
   Packed view_cols(long long col0, int esz) const {   // column-block view (same pitch / lo_off)
     Packed p = *this;
     p.data = static_cast<char*>(data) + col0 * esz;
@@ -48,7 +50,7 @@ int gemm_tc(const GemmArgs& g, int precision, void* scratch, size_t scratch_byte
 bool gemm_tc_supported(const GemmArgs& g, int precision);
 size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precision);
 size_t packed_bytes(long long rows, long long cols, int precision);
-Packed packed_describe(void* region, long long rows, long long cols);
+Packed packed_describe(void* region, long long rows, long long cols, int precision = -1);
 int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
                  Packed* out, cudaStream_t st);
 int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);

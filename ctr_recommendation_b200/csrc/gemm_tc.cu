@@ -10,6 +10,16 @@
 //                     128-byte row [hi as bf16 x32 | lo as bf16 x32]: the same 128B-swizzled K-major tile as the fp32 lo part,
 //                     the bf16 MMAs address the two halves by the ordinary in-row descriptor advance.  K-major operands only.
 //
+//   FBN_PREC_F16X3  : fp32-grade result from three kind::f16 (fp16) passes at the bf16 rate -- half the tensor time AND half the
+//                     operand bytes of tf32x3.  Each operand tensor carries ONE power-of-two scale s (amax * s in [2^14, 2^15)):
+//                     x_h = fp16_rn(s x), x_l = fp16_rn(s x - x_h), i.e. the same 22 operand bits as the tf32 split (fp16 and tf32
+//                     both keep 11 significand bits); D = (Ah*Bh + Ah*Bl + Al*Bh) / (sa sb), the division being two exact
+//                     multiplications by powers of two in the epilogue.  Elements more than 2^28 below the tensor's amax lose
+//                     relative (not absolute) precision: their error is <= 2^-25 / s, i.e. <= 2^-39 of amax
+//                     (tools/split_precision_sim.py: logits 7.6e-7, worst gradient 6e-6 -- the same as tf32x3 and as fp32 itself,
+//                     and unchanged when the scale is off by a factor of 2^12).  The amax pass makes the scale exact and the
+//                     result independent of anything but the operand values (no state carried between calls).
+//
 // Structure (one 128x128 output tile per CTA, 192 threads):
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d (128B swizzle) into a 3..6 stage smem ring
 //   warp 1      : MMA issuer    -- one elected thread issues tcgen05.mma, tcgen05.commit frees the stage
@@ -25,6 +35,7 @@
 // weight-gradient TN) maps onto this one kernel and a packed tensor is shared by all GEMMs that read it.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -44,6 +55,9 @@ struct TcArgs {
   // batched launch (blockIdx.z = batch * splits + split): per-batch TMA coordinate offsets and output stride
   int a_bc = 0, a_br = 0, b_bc = 0, b_br = 0;
   long long strideC = 0;
+  // FBN_PREC_F16X3: device pointers to the operands' inverse scales (1 / s, a power of two), applied in the epilogue
+  const float* inv_sa = nullptr;
+  const float* inv_sb = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -114,6 +128,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_m
 }
 
 constexpr bool is32(int mode) { return mode == FBN_PREC_TF32X3 || mode == FBN_PREC_TF32X2; }   // 4-byte operand parts
+constexpr bool two_part(int mode) { return is32(mode) || mode == FBN_PREC_F16X3; }             // hi + lo tiles: 64 KB per stage
 
 template <int MODE>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -151,8 +166,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 constexpr int EPI_PITCH = 132;                      // floats per staged row (+4 pad)
 constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH * 4;  // 16.5 KB per epilogue warp
 
+// s0 / s1: inverse operand scales of FBN_PREC_F16X3 (exact powers of two, applied one after the other so that their product can
+// never leave the fp32 range on its own); 1 for the other modes.
 __device__ __forceinline__ void epilogue_store(const float (&acc)[128], float* stage, int lane, long long row0, long long M,
-                                               float* cbase, long long ldc, const float* bias, int accumulate) {
+                                               float* cbase, long long ldc, const float* bias, int accumulate, float s0 = 1.f,
+                                               float s1 = 1.f) {
 #pragma unroll
   for (int j = 0; j < 128; j += 4)
     *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -161,7 +179,7 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[128], float* s
 #pragma unroll 4
   for (int r = 0; r < 32; ++r) {
     if (row0 + r >= M) break;
-    float4 o = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + 4 * lane) + bv;
+    float4 o = (*reinterpret_cast<const float4*>(stage + r * EPI_PITCH + 4 * lane) * s0) * s1 + bv;
     float* cp = cbase + (long long)r * ldc + 4 * lane;
     if (accumulate) o += *reinterpret_cast<const float4*>(cp);
     st4(cp, o);
@@ -177,14 +195,15 @@ struct TcCfg {
   static constexpr int BK = 128 / ESZ;                                   // k-block: 32 (tf32) / 64 (bf16) elements
   static constexpr int UK = 32 / ESZ;                                    // K per tcgen05.mma: 8 / 16
   static constexpr int EPB = 128 / ESZ;                                  // elements per 128-byte swizzle row
-  static constexpr int NPART = is32(MODE) ? 2 : 1;                       // hi + lo (tf32x3) / hi + [hi|lo as bf16] (tf32x2)
+  static constexpr int NPART = two_part(MODE) ? 2 : 1;                   // hi + lo (tf32x3, f16x3) / hi + [hi|lo as bf16] (tf32x2)
   static constexpr int TILE_BYTES = TC_BM * 128;                         // 128 x BK (K-major) == BK x 128 (MN-major)
   static constexpr int BOX_MN_BYTES = BK * 128;                          // one MN-major box: BK rows x 128 bytes
   static constexpr int STAGE_BYTES = 2 * NPART * TILE_BYTES;
-  static constexpr int STAGES = is32(MODE) ? 3 : 6;
+  static constexpr int STAGES = two_part(MODE) ? 3 : 6;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int NBAR = 2 * STAGES + 4;
-  static constexpr int FMT = is32(MODE) ? 2 : 1;
+  static constexpr int FMT = is32(MODE) ? 2 : (MODE == FBN_PREC_F16X3 ? 0 : 1);      // UMMA format: F16 = 0, BF16 = 1, TF32 = 2
+  static constexpr bool SCALED = MODE == FBN_PREC_F16X3;
   // k-blocks per TMEM chunk.  tf32x2 issues 8 MMAs per k-block instead of 12: 6 k-blocks keep the 48 accumulations per chunk (same
   // truncation error) and give the epilogue warps as long to fold a chunk as before (MLP-1 forward GEMM, B = 65536: 460 us with 4,
   // 441 us with 6; tf32x3: 517 us).  The gain stays well below the 1/3 fewer MMAs because operand delivery, not the tensor pipe, then
@@ -196,10 +215,10 @@ struct TcCfg {
 template <int MODE>
 __device__ __forceinline__ void issue_kstep(uint32_t tacc, uint64_t a_p0, uint64_t b_p0, uint64_t a_p1, uint64_t b_p1, uint64_t adv_a,
                                             uint64_t adv_b, int k, uint32_t idesc, uint32_t idesc_bf16, uint32_t acc) {
-  if (MODE == FBN_PREC_TF32X3) {
-    umma<FBN_PREC_TF32X3>(tacc, a_p1 + k * adv_a, b_p0 + k * adv_b, idesc, acc);      // small terms first
-    umma<FBN_PREC_TF32X3>(tacc, a_p0 + k * adv_a, b_p1 + k * adv_b, idesc, 1u);
-    umma<FBN_PREC_TF32X3>(tacc, a_p0 + k * adv_a, b_p0 + k * adv_b, idesc, 1u);
+  if (MODE == FBN_PREC_TF32X3 || MODE == FBN_PREC_F16X3) {
+    umma<MODE>(tacc, a_p1 + k * adv_a, b_p0 + k * adv_b, idesc, acc);      // small terms first
+    umma<MODE>(tacc, a_p0 + k * adv_a, b_p1 + k * adv_b, idesc, 1u);
+    umma<MODE>(tacc, a_p0 + k * adv_a, b_p0 + k * adv_b, idesc, 1u);
   } else if (MODE == FBN_PREC_TF32X2) {
     // K-major only: a k-step covers 8 tf32 = 32 bytes of the hi row.  The bf16 corrections run at 16 elements per MMA, i.e. once per
     // two tf32 k-steps: part-1 row = [hi_bf16 x32 (bytes 0..63) | lo_bf16 x32 (bytes 64..127)], 16 bf16 = 32 bytes = 2 x (16-byte units).
@@ -343,7 +362,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else {
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 == output rows m0 + 32*(w%4) + lane
     const int q = warp & 3;
-    const long long row = (long long)m0 + q * 32 + lane;
+    float s0 = 1.f, s1 = 1.f;
+    if (Cfg::SCALED) {
+      if (g.inv_sa) s0 = __ldg(g.inv_sa);
+      if (g.inv_sb) s1 = __ldg(g.inv_sb);
+    }
     float acc[TC_BN];
 #pragma unroll
     for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
@@ -366,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const long long row0 = (long long)m0 + q * 32;
       float* cbase = g.C + (long long)bi * g.strideC + (long long)sp * g.strideSplit + row0 * g.ldc + n0;
       epilogue_store(acc, reinterpret_cast<float*>(smem + (warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
-                     g.bias ? g.bias + n0 : nullptr, g.accumulate);
+                     g.bias ? g.bias + n0 : nullptr, g.accumulate, s0, s1);
     }
   }
   tc_fence_before();
@@ -387,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 struct TcpCfg {
-  static constexpr int STAGES = is32(MODE) ? 2 : 4;
+  static constexpr int STAGES = two_part(MODE) ? 2 : 4;
   static constexpr int STAGE_BYTES = TcCfg<MODE>::STAGE_BYTES;
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int NBAR = 2 * STAGES + 4;
@@ -547,6 +570,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
   } else {
     const int q = warp & 3;
     float* stage = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);
+    float s0 = 1.f, s1 = 1.f;
+    if (Cfg::SCALED) {
+      if (g.inv_sa) s0 = __ldg(g.inv_sa);
+      if (g.inv_sb) s1 = __ldg(g.inv_sb);
+    }
     int chunk = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const TileInfo ti = tile_info<MODE>(g, t, nN, nZ, kblocks, per);
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
       }
       const long long row0 = (long long)ti.m0 + q * 32;
       float* cbase = g.C + (long long)ti.bi * g.strideC + (long long)ti.sp * g.strideSplit + row0 * g.ldc + ti.n0;
-      epilogue_store(acc, stage, lane, row0, g.M, cbase, g.ldc, g.bias ? g.bias + ti.n0 : nullptr, g.accumulate);
+      epilogue_store(acc, stage, lane, row0, g.M, cbase, g.ldc, g.bias ? g.bias + ti.n0 : nullptr, g.accumulate, s0, s1);
       __syncwarp();        // the staging rows are reused by the next tile
     }
   }
@@ -777,7 +805,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const long long row = (long long)m0 + q * 32 + lane;
+    float s0 = 1.f, s1 = 1.f;
+    if (Cfg::SCALED) {
+      if (g.inv_sa) s0 = __ldg(g.inv_sa);
+      if (g.inv_sb) s1 = __ldg(g.inv_sb);
+    }
     float acc[128];
 #pragma unroll
     for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -802,7 +834,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
       const long long row0 = (long long)m0 + q * 32;
       float* cbase = g.C + (long long)sp * g.strideSplit + row0 * g.ldc + ncol0;
       epilogue_store(acc, reinterpret_cast<float*>(smem + (warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
-                     g.bias ? g.bias + ncol0 : nullptr, g.accumulate);
+                     g.bias ? g.bias + ncol0 : nullptr, g.accumulate, s0, s1);
     }
   }
   tc_fence_before();
@@ -838,7 +870,8 @@ struct Tc2pArgs {
 constexpr int EPI2_WARP_FLOATS = 32 * 32;
 
 __device__ __forceinline__ void epilogue_store_sw(const float (&acc)[128], float* stage, int lane, long long row0, long long M,
-                                                  float* cbase, long long ldc, const float* bias, int accumulate) {
+                                                  float* cbase, long long ldc, const float* bias, int accumulate, float s0 = 1.f,
+                                                  float s1 = 1.f) {
   const int rr = lane >> 3, cc = lane & 7;
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
@@ -852,7 +885,7 @@ __device__ __forceinline__ void epilogue_store_sw(const float (&acc)[128], float
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + rr;
       if (row0 + r < M) {
-        float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((cc ^ (r & 7)) << 2)) + bv;
+        float4 o = (*reinterpret_cast<const float4*>(stage + r * 32 + ((cc ^ (r & 7)) << 2)) * s0) * s1 + bv;
         float* cp = cbase + (long long)r * ldc + q4 * 32 + cc * 4;
         if (accumulate) o += *reinterpret_cast<const float4*>(cp);
         st4(cp, o);
@@ -1032,6 +1065,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* stage = reinterpret_cast<float*>(epi) + (warp - 2) * EPI2_WARP_FLOATS;
+    float s0 = 1.f, s1 = 1.f;
+    if (Cfg::SCALED) {
+      if (g.inv_sa) s0 = __ldg(g.inv_sa);
+      if (g.inv_sb) s1 = __ldg(g.inv_sb);
+    }
     const uint32_t tempty_leader0 = mapa_u32(smem_u32(tempty), 0);
     int chunk = 0;
     for (long long t = cid; t < p.ntiles; t += ncl) {
@@ -1059,7 +1097,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
         if (ncol0 < g.N) {
           const long long row0 = (long long)ti.m0 + (long long)rank * 128 + q * 32;
           float* cbase = g.C + (long long)ti.sp * g.strideSplit + row0 * g.ldc + ncol0;
-          epilogue_store_sw(acc, stage, lane, row0, g.M, cbase, g.ldc, g.bias ? g.bias + ncol0 : nullptr, g.accumulate);
+          epilogue_store_sw(acc, stage, lane, row0, g.M, cbase, g.ldc, g.bias ? g.bias + ncol0 : nullptr, g.accumulate, s0, s1);
         }
       }
     }
@@ -1124,6 +1162,96 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long ld, lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// FBN_PREC_F16X3 operands: one power-of-two scale per tensor.
+//   pass 1 (amax_partial_kernel): per-block maxima of |x| over the converted columns -> tail[F16_REC_FLOATS + block]
+//   pass 2 (pack_f16x3_kernel)  : every block folds the partial maxima (max is order-independent: deterministic, no atomics, nothing
+//                                 to re-arm), derives s = 2^(14 - floor(log2 amax)) and writes hi = fp16_rn(s x) at dst, lo =
+//                                 fp16_rn(s x - hi) at dst + lo_off; block 0 records {s, 1/s, amax} in tail[0..2] for the GEMM epilogues.
+// ------------------------------------------------------------------------------------------------
+constexpr int F16_REC_FLOATS = 16;          // scale record: [0] = s, [1] = 1 / s, [2] = amax
+constexpr int F16_AMAX_BLOCKS = 1024;       // partial maxima that follow the record
+
+__device__ __forceinline__ float f16x3_scale(float amax) {
+  // amax * s in [2^14, 2^15) (fp16 overflows at 65504); an all-zero or non-finite tensor is left unscaled; the exponent is clamped so
+  // that s and 1/s are normal fp32 numbers (only a tensor with amax < 2^-106 is scaled less than ideally)
+  const unsigned bits = __float_as_uint(amax);
+  const int e = (int)((bits >> 23) & 0xffu) - 127;
+  if (bits == 0u || e == 128) return 1.f;
+  const int k = max(-120, min(120, 14 - e));
+  return __uint_as_float((unsigned)(k + 127) << 23);
+}
+
+__global__ void __launch_bounds__(256) amax_partial_kernel(const float* __restrict__ src, long long ld, long long R, long long K,
+                                                           long long Kp, unsigned long long colmask, float* __restrict__ tail) {
+  const long long q = Kp / 4;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * q; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / q, c = (i % q) * 4;
+    if (colmask != ~0ull && !((colmask >> (c / 128)) & 1ull)) continue;
+    if (c + 3 < K) {
+      const float4 v = ld4(src + r * ld + c);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    } else {
+      for (long long j = c; j < K; ++j) m = fmaxf(m, fabsf(src[r * ld + j]));
+    }
+  }
+  // NaN inputs: fmaxf drops them here, the packed values (and every product) still carry them
+  __shared__ float sm[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    tail[F16_REC_FLOATS + blockIdx.x] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_f16x3_kernel(const float* __restrict__ src, long long ld, long long R, long long K,
+                                                         long long Kp, __half* __restrict__ dst, long long lo_off,
+                                                         unsigned long long colmask, float* __restrict__ tail, int npartial) {
+  __shared__ float sm[8];
+  __shared__ float s_scale;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < npartial; i += 256) m = fmaxf(m, tail[F16_REC_FLOATS + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    const float sc = f16x3_scale(m);
+    s_scale = sc;
+    if (blockIdx.x == 0) { tail[0] = sc; tail[1] = 1.0f / sc; tail[2] = m; }
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  const long long q = Kp / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * q; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / q, c = (i % q) * 4;
+    if (colmask != ~0ull && !((colmask >> (c / 128)) & 1ull)) continue;
+    float4 v = f4(0.f);
+    if (c + 3 < K) v = ld4s(src + r * ld + c);
+    else {
+      if (c < K) v.x = src[r * ld + c];
+      if (c + 1 < K) v.y = src[r * ld + c + 1];
+      if (c + 2 < K) v.z = src[r * ld + c + 2];
+    }
+    v = v * sc;
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 oh, ol;
+    oh.x = *reinterpret_cast<const uint32_t*>(&h0); oh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ol.x = *reinterpret_cast<const uint32_t*>(&l0); ol.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(dst + r * Kp + c) = oh;
+    *reinterpret_cast<uint2*>(dst + lo_off + r * Kp + c) = ol;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1154,7 +1282,7 @@ static int make_map(CUtensorMap* m, int mode, const void* base, long long rows, 
   cuuint32_t box[2] = {epb, mn_major ? epb : 128u};   // MN-major: BK == epb rows of K
   cuuint32_t estr[2] = {1, 1};
   FBN_REQUIRE(aligned16(base) && (pitch * esz) % 16 == 0, FBN_ERR_ALIGN, "tcgen05 operand is not 16-byte aligned");
-  CUresult r = enc(m, is32(mode) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = enc(m, is32(mode) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (mode == FBN_PREC_F16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    (mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1167,25 +1295,39 @@ static long long round_up(long long x, long long m) { return (x + m - 1) / m * m
 
 size_t packed_bytes(long long rows, long long cols, int precision) {
   const long long pitch = round_up(cols, precision == FBN_PREC_TF32X2 ? 32 : 8);
+  if (precision == FBN_PREC_F16X3)      // hi | lo fp16 + the scale record and the partial maxima of the amax pass
+    return (size_t)(rows * pitch * 4) + 1024 + (size_t)(F16_REC_FLOATS + F16_AMAX_BLOCKS) * sizeof(float);
   return (size_t)(rows * pitch * (is32(precision) ? 8 : 2)) + 1024;
 }
 
-Packed packed_describe(void* region, long long rows, long long cols) {
+Packed packed_describe(void* region, long long rows, long long cols, int precision) {
   Packed p;
   p.data = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(region) + 1023) & ~uintptr_t(1023));
   p.pitch = round_up(cols, 8);
   p.lo_off = rows * p.pitch;
   p.rows = rows; p.cols = cols;
+  if (precision == FBN_PREC_F16X3) p.scale = reinterpret_cast<float*>(static_cast<char*>(p.data) + (size_t)rows * p.pitch * 4);
   return p;
 }
 
 // converts src (rows x cols fp32, ld) into operand format at dst (1024-byte aligned inside the caller's region)
 int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
                  Packed* out, cudaStream_t st) {
-  FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16 || precision == FBN_PREC_TF32X2, FBN_ERR_ARG,
-              "pack_operand: bad precision");
+  FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16 || precision == FBN_PREC_TF32X2 || precision == FBN_PREC_F16X3,
+              FBN_ERR_ARG, "pack_operand: bad precision");
   FBN_REQUIRE(aligned16(src) && ld % 4 == 0, FBN_ERR_ALIGN, "pack_operand: source must be 16-byte aligned with ld %% 4 == 0");
-  *out = packed_describe(dst, rows, cols);
+  *out = packed_describe(dst, rows, cols, precision);
+  if (precision == FBN_PREC_F16X3) {
+    const long long n4 = rows * (out->pitch / 4);
+    const int nb1 = (int)std::max<long long>(1, std::min<long long>(cdiv(n4, 256 * 4), std::min(F16_AMAX_BLOCKS, 4 * num_sms())));
+    amax_partial_kernel<<<nb1, 256, 0, st>>>(src, ld, rows, cols, out->pitch, colmask, out->scale);
+    FBN_CHECK_LAUNCH();
+    const int nb2 = (int)std::max<long long>(1, std::min<long long>(cdiv(n4, 256), 16LL * num_sms()));
+    pack_f16x3_kernel<<<nb2, 256, 0, st>>>(src, ld, rows, cols, out->pitch, static_cast<__half*>(out->data), out->lo_off, colmask,
+                                           out->scale, nb1);
+    FBN_CHECK_LAUNCH();
+    return FBN_OK;
+  }
   if (precision == FBN_PREC_TF32X2) {          // whole 32-element k-blocks per row (the interleaved bf16 part needs them)
     out->pitch = round_up(cols, 32);
     out->lo_off = rows * out->pitch;
@@ -1212,7 +1354,8 @@ size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precisio
 bool gemm_tc_supported(const GemmArgs& g, int precision) {
   if (precision == FBN_PREC_TF32X2)   // K-major x K-major only, no pre-packed operands of another format
     return g.a_t == 0 && g.b_t != 0 && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch == 1;
-  return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16) && g.N % 128 == 0 && g.ldc % 4 == 0 && g.batch >= 1;
+  return (precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16 || precision == FBN_PREC_F16X3) && g.N % 128 == 0 && g.ldc % 4 == 0 &&
+         g.batch >= 1;
 }
 
 // fbn_set_option("tc_persistent", v): 1 = every single-CTA launch runs the persistent tile loop (epilogue of tile i overlapped with
@@ -1331,6 +1474,7 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
       t.C = g.C; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
       t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
       t.a_bc = (int)a_bc; t.a_br = (int)a_br; t.b_bc = (int)b_bc; t.b_br = (int)b_br; t.strideC = g.strideC;
+      if (Cfg::SCALED) { t.inv_sa = g.pkA.scale ? g.pkA.scale + 1 : nullptr; t.inv_sb = g.pkB.scale ? g.pkB.scale + 1 : nullptr; }
       dim3 grid((unsigned)(g.N / TC_BN), (unsigned)cdiv(g.M, TC_BM), (unsigned)(g.splits * g.batch));
       // short K, many tiles (the bilinear transforms / their data gradients): the tile loop hides the epilogue
       const bool persist = g.K <= 256 && g.splits == 1 && (long long)grid.x * grid.y * grid.z >= 2LL * num_sms();
@@ -1376,6 +1520,10 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     TcArgs t;
     t.C = g.C + bi * g.strideC; t.bias = g.bias; t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc; t.splits = g.splits;
     t.strideSplit = g.strideSplit; t.kmask = g.kmask; t.nmask = g.nmask; t.accumulate = g.accumulate;
+    if (Cfg::SCALED) {
+      FBN_REQUIRE(pa.scale && pb.scale, FBN_ERR_ARG, "tcgen05 GEMM (f16x3): a pre-packed operand carries no scale record");
+      t.inv_sa = pa.scale + 1; t.inv_sb = pb.scale + 1;
+    }
     int rc;
     // CTA pairs (256 x 256 tiles, half the L2 traffic per MMA) once they can fill most of the 148 SMs; small problems
     // keep the 128 x 128 single-CTA tiles (4x as many CTAs)
@@ -1449,10 +1597,11 @@ static int gemm_tc_x2(const GemmArgs& g, void* scratch, size_t scratch_bytes, cu
 
 int gemm_tc(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   FBN_REQUIRE(gemm_tc_supported(g, precision), FBN_ERR_SHAPE,
-              "tcgen05 GEMM: unsupported shape / layout (N %lld must be a multiple of 128; tf32x2 takes a_t = 0, b_t = 1 only)", g.N);
+              "tcgen05 GEMM: unsupported shape / layout / precision (N %lld must be a multiple of 128; tf32x2 takes a_t = 0, b_t = 1 only)", g.N);
   if (g.M <= 0) return FBN_OK;
   if (precision == FBN_PREC_TF32X2) return gemm_tc_x2(g, scratch, scratch_bytes, st);
   if (precision == FBN_PREC_TF32X3) return gemm_tc_mode<FBN_PREC_TF32X3>(g, scratch, scratch_bytes, st);
+  if (precision == FBN_PREC_F16X3) return gemm_tc_mode<FBN_PREC_F16X3>(g, scratch, scratch_bytes, st);
   return gemm_tc_mode<FBN_PREC_BF16>(g, scratch, scratch_bytes, st);
 }
 

@@ -225,7 +225,7 @@ class GeneralFiBiNET(nn.Module):
         e0, e2 = self.senet.excitation[0], self.senet.excitation[2]
         R = self.senet.reduced_size
         btype = _lib.BILINEAR_TYPES[self.bilinear.bilinear_type]
-        prec = _lib.PRECISIONS[self.precision]
+        prec = _lib.PRECISIONS["tf32x3" if self.precision == "f16x3" else self.precision]   # short-K bilinear GEMMs: see _lib.PRECISIONS
         _lib.check(lib.fbn_fields_gather(_lib.ptr(self.emb.weight), _lib.ptr(self.field_desc), _lib.ptr(ids), idt, B, F, self.id_cols,
                                          _lib.ptr(buf["X"]), _lib.ptr(buf["cnt"]), _lib.ptr(buf["flag"]), st), "fbn_fields_gather")
         _lib.check(lib.fbn_senet_fwd(_lib.ptr(buf["X"]), _lib.ptr(e0.weight), _lib.ptr(e0.bias), _lib.ptr(e2.weight), _lib.ptr(e2.bias),
@@ -270,7 +270,7 @@ class GeneralFiBiNET(nn.Module):
         e0, e2 = self.senet.excitation[0], self.senet.excitation[2]
         R = self.senet.reduced_size
         btype = _lib.BILINEAR_TYPES[self.bilinear.bilinear_type]
-        prec = _lib.PRECISIONS[self.precision]
+        prec = _lib.PRECISIONS["tf32x3" if self.precision == "f16x3" else self.precision]
         m = self.mlp
         new = lambda t: torch.empty_like(t, memory_format=torch.contiguous_format)
         g_w1, g_b1, g_g1, g_be1 = new(m[0].weight), new(m[0].bias), new(m[1].weight), new(m[1].bias)

@@ -123,7 +123,7 @@ class MM_FiBiNET(nn.Module):
     """Drop-in for the reference MM_FiBiNET (src/model_fibinet.py:91-199).
 
     ``feature_map`` is accepted and ignored like in the reference; when it is a dict it may carry
-    B200-side options (the reference's callers pass None):  {"precision": "fp32"|"tf32x3"|"bf16",
+    B200-side options (the reference's callers pass None):  {"precision": "fp32"|"tf32x3"|"f16x3"|"bf16",
     "bilinear_type": "all"|"each"|"interaction", "dropout": float, "table_sharding": "row", "item_rows": V,
     "shard_rank": r, "shard_world": N}.  With ``table_sharding="row"`` the item table is partitioned by ``id % N`` over the
     N ranks of the process group (see sharded.py): ``item_emb`` then holds this rank's (ceil(V/N),128) slice and training

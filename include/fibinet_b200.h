@@ -45,9 +45,15 @@ enum {
   FBN_PREC_FP32 = 0,   /* fp32 FMA (SIMT) -- exact-order reference mode */
   FBN_PREC_TF32X3 = 1, /* tcgen05 kind::tf32, 3-pass split operands, fp32 accumulate in TMEM */
   FBN_PREC_BF16 = 2,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM */
-  FBN_PREC_TF32X2 = 3  /* fbn_gemm only, K-major x K-major operands (a_t = 0, b_t = 1, K % 32 == 0): Ah*Bh as kind::tf32 plus the two
+  FBN_PREC_TF32X2 = 3, /* fbn_gemm only, K-major x K-major operands (a_t = 0, b_t = 1, K % 32 == 0): Ah*Bh as kind::tf32 plus the two
                           correction terms Al*Bh + Ah*Bl as kind::f16 bf16 MMAs -- 2 tensor-pass equivalents instead of 3,
                           ~1.4e-6 relative error; MLP-1 forward shape 517 -> 441 us.  Building block; the model path does not use it yet. */
+  FBN_PREC_F16X3 = 4   /* fp32-grade result from three kind::f16 (fp16) passes: every operand tensor is scaled by ONE power of two
+                          (amax -> [2^14, 2^15), found by an amax pass), split into fp16 hi | lo (the same 22 operand bits as the
+                          tf32 split) and multiplied at the bf16 rate with half the operand bytes of tf32x3; the epilogue undoes
+                          the scales exactly.  In the model path the long-K GEMMs (the MLP tower: forward, data- and
+                          weight-gradient) run in this mode, the short-K ones (bilinear transforms, item_emb_d128 projection)
+                          keep FBN_PREC_TF32X3. */
 };
 
 enum { FBN_BILINEAR_ALL = 0, FBN_BILINEAR_EACH = 1, FBN_BILINEAR_INTERACTION = 2 };

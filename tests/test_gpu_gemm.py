@@ -23,12 +23,13 @@ def test_sgemm_layouts(a_t, b_t, M, N, K):
     assert err <= 2e-6, err
 
 
-@pytest.mark.parametrize("precision,tol", [("tf32x3", 3e-6), ("bf16", 6e-3)])
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 3e-6), ("f16x3", 3e-6), ("bf16", 6e-3)])
 @pytest.mark.parametrize("a_t,b_t", [(False, True), (False, False), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 512, 2688), (4096, 256, 512), (128, 128, 1000), (512, 2688, 300)])
 def test_tcgen05_gemm_layouts(precision, tol, a_t, b_t, M, N, K):
     """tcgen05 path (TMA -> smem -> tcgen05.mma -> TMEM -> tcgen05.ld) against an fp64 matmul of the same fp32 inputs.
-    tf32x3 must be fp32-grade; bf16 carries 8-bit mantissa operands."""
+    tf32x3 and f16x3 (three fp16 passes under one power-of-two scale per operand) must be fp32-grade; bf16 carries 8-bit
+    mantissa operands."""
     from ctr_recommendation_b200.functional import gemm
     g = torch.Generator(device="cuda").manual_seed(2)
     A = torch.randn(M, K, device="cuda", generator=g)
@@ -54,7 +55,7 @@ def knobs():
 
 
 @pytest.mark.parametrize("pair,persistent,pair_persistent", [(1, 0, 1), (1, 0, 0), (0, -1, 1), (0, 1, 1), (1, 1, 1)])
-@pytest.mark.parametrize("precision,tol", [("tf32x3", 3e-6), ("bf16", 6e-3)])
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 3e-6), ("f16x3", 3e-6), ("bf16", 6e-3)])
 @pytest.mark.parametrize("a_t,b_t,M,N,K", [(False, True, 40000, 256, 512), (False, False, 40000, 512, 256), (False, False, 39000, 128, 128),
                                            (True, False, 512, 384, 5000), (False, True, 300, 512, 2688),
                                            (False, False, 20001, 2688, 512),      # 21 column blocks: the last pair tile is half dead
@@ -80,7 +81,7 @@ def test_tcgen05_kernel_variants(knobs, pair, persistent, pair_persistent, preci
     assert err <= tol, err
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3", "bf16"])
 def test_model_step_identical_under_kernel_variants(knobs, precision):
     """The train forward/backward of a batch large enough for the persistent-kernel heuristic (B = 40000: 4 x 313 bilinear tiles)
     gives the same probabilities and gradients whichever GEMM kernel variant runs (same MMA order per tile -> bitwise)."""
@@ -100,11 +101,43 @@ def test_model_step_identical_under_kernel_variants(knobs, precision):
         outs.append((y.detach().clone(), {k: torch.from_numpy(v) for k, v in named_grads(model).items()}))
         del model
     for y, g in outs[1:]:
-        assert torch.allclose(y, outs[0][0], rtol=0, atol=2e-6 if precision == "tf32x3" else 2e-3)
+        assert torch.allclose(y, outs[0][0], rtol=0, atol=2e-6 if precision != "bf16" else 2e-3)
         for k in g:
             ref = outs[0][1][k]
             err = (g[k] - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
-            assert err <= (1e-5 if precision == "tf32x3" else 5e-2), (k, err)
+            assert err <= (1e-5 if precision != "bf16" else 5e-2), (k, err)
+
+
+@pytest.mark.parametrize("a_scale,b_scale", [(1.0, 1.0), (3e-9, 0.04), (7e4, 2e-6), (1e-30, 1e20)])
+@pytest.mark.parametrize("a_t,b_t,M,N,K", [(False, True, 1000, 512, 2688), (True, False, 512, 640, 9000), (False, False, 20000, 512, 256)])
+def test_f16x3_scales(a_t, b_t, M, N, K, a_scale, b_scale):
+    """FBN_PREC_F16X3 on operands far outside the fp16 range (gradient-sized, weight-sized, huge): the per-tensor power-of-two
+    scale found by the amax pass keeps the result fp32-grade, and a block of columns 10^4 times smaller than the rest of its
+    tensor (the pair blocks of the MLP input next to the LayerNorm field) is still resolved to 1e-5 of ITS OWN magnitude in a
+    weight-gradient-shaped product."""
+    from ctr_recommendation_b200.functional import gemm
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g) * a_scale
+    Bm = torch.randn(K, N, device="cuda", generator=g) * b_scale
+    Bm[:, : N // 2] *= 1e-4                                   # half of the output columns come from a much smaller block
+    ref = A.double() @ Bm.double()
+    a_in = A.t().contiguous() if a_t else A
+    b_in = Bm.t().contiguous() if b_t else Bm
+    out = gemm(a_in, b_in, None, a_t=a_t, b_t=b_t, precision="f16x3").double()
+    torch.cuda.synchronize()
+    for cols in (slice(0, N // 2), slice(N // 2, N)):
+        err = (out[:, cols] - ref[:, cols]).abs().max().item() / ref[:, cols].abs().max().item()
+        assert err <= (1e-5 if cols.start == 0 else 3e-6), (cols, err)
+
+
+def test_f16x3_zero_operand():
+    """an all-zero operand (amax = 0) is left unscaled and gives an exact zero product + bias"""
+    from ctr_recommendation_b200.functional import gemm
+    A = torch.zeros(256, 128, device="cuda")
+    W = torch.randn(128, 128, device="cuda")
+    bias = torch.randn(128, device="cuda")
+    out = gemm(A, W, bias, a_t=False, b_t=True, precision="f16x3")
+    assert torch.equal(out, bias.expand(256, 128))
 
 
 @pytest.mark.parametrize("persistent", [-1, 1])

@@ -60,14 +60,14 @@ def _oracle_under_gpu_gates(model, P, ids, labels, B, tol, masks=None, dropout=0
 
 
 CASES = [("fp32", 8, 300, "all", 0.0), ("tf32x3", 8, 300, "all", 0.25), ("tf32x3", 8, 257, "each", 0.0), ("tf32x3", 6, 200, "interaction", 0.25),
-         ("tf32x3", 40, 256, "all", 0.0), ("bf16", 8, 300, "all", 0.0)]
+         ("tf32x3", 40, 256, "all", 0.0), ("bf16", 8, 300, "all", 0.0), ("f16x3", 8, 300, "all", 0.25), ("f16x3", 40, 256, "all", 0.0)]
 
 
 @pytest.mark.parametrize("precision,F,B,btype,dropout", CASES)
 def test_general_model_vs_oracle(precision, F, B, btype, dropout):
     from ctr_recommendation_b200 import GeneralFiBiNET, build_model
     vocab = 57
-    tol = {"fp32": 1e-5, "tf32x3": 1e-5, "bf16": 1e-2}[precision]
+    tol = {"fp32": 1e-5, "tf32x3": 1e-5, "f16x3": 1e-5, "bf16": 1e-2}[precision]
     P = _round32(gen.make_params(F, D, vocab, (512, 256), btype, reduction_ratio=2, seed=11))
     rng = np.random.default_rng(7)
     ids = rng.integers(0, vocab, (B, F))

@@ -21,7 +21,7 @@ def gpu():
 
 
 BF16_GRAD_L2 = 0.12
-PREC_TOL = {"fp32": TOL, "tf32x3": TOL, "bf16": 1e-2}   # north_star: fp32 1e-5 relative, bf16 paths 1e-2
+PREC_TOL = {"fp32": TOL, "tf32x3": TOL, "f16x3": TOL, "bf16": 1e-2}   # north_star: fp32 1e-5 relative, bf16 paths 1e-2
 
 
 @pytest.mark.parametrize("precision", list(PREC_TOL))
@@ -325,7 +325,8 @@ def test_full_size_properties(gpu, B):
 # (precision, B, id distribution): the reference's own batch 4096 (BASELINE config 1) and batches large enough for the CTA-pair
 # tcgen05 kernel (gemm_tc2_kernel engages from 120 pair CTAs: MLP-1 at B >= 7680) to run INSIDE the model
 FULL_CASES = [("fp32", 4096, "zipf"), ("tf32x3", 4096, "uniform"), ("tf32x3", 4096, "zipf"), ("tf32x3", 16384, "zipf"),
-              ("tf32x3", 40960, "uniform"), ("bf16", 16384, "zipf")]
+              ("tf32x3", 40960, "uniform"), ("bf16", 16384, "zipf"),
+              ("f16x3", 4096, "zipf"), ("f16x3", 16384, "zipf"), ("f16x3", 40960, "uniform")]
 
 
 @pytest.mark.parametrize("precision,B,id_dist", FULL_CASES)
@@ -417,7 +418,7 @@ def test_resident_mm_table_matches_batch_vectors(gpu):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "f16x3"])
 def test_train_step_engine_matches_module_path(gpu, precision):
     """engine.TrainStep (CUDA-graph replay of the loop body, fused BCE) == the autograd module path + FusedAdam,
     and graph replay == the same launches issued eagerly (bitwise)."""
