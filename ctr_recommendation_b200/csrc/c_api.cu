@@ -195,10 +195,16 @@ struct PkReg {
   // the same for a tensor only the MLP GEMMs read: in f16x3 mode the producer writes fp32 only and the caller follows up with
   // after_mlp() once the tensor is complete
   PackDst dst_mlp(const float* src, long long rows, long long cols, void* region) {
-    return mlp16() ? PackDst() : dst(src, rows, cols, region);
+    if (!mlp16()) return dst(src, rows, cols, region);
+    PackDst d;          // mode 0: fp32 only, plus the per-block maxima the split pass needs
+    d.tail = packed_describe(region, rows, cols, FBN_PREC_F16X3).scale;
+    return d;
   }
-  int after_mlp(const float* src, long long rows, long long cols, void* region, unsigned long long colmask = ~0ull) {
-    return mlp16() ? pack_mlp(src, rows, cols, region, colmask) : FBN_OK;
+  int after_mlp(const float* src, long long rows, long long cols, void* region) {
+    if (!mlp16()) return FBN_OK;
+    describe(src, rows, cols, region, FBN_PREC_F16X3);
+    Packed tmp;
+    return pack_operand(src, cols, rows, cols, FBN_PREC_F16X3, region, ~0ull, &tmp, st, /*producer_amax=*/true);
   }
   Packed find(const float* p, int fmt) const {
     for (int i = 0; i < ne; ++i)
@@ -372,6 +378,16 @@ static int bilinear_transform_fwd(const fbn_params_t* p, Workspace& w, cudaStrea
   return FBN_OK;
 }
 
+// Hadamard pairs -> the MLP input in GEMM operand format.  tf32x3 / bf16: the pair blocks join the field blocks the gather kernel
+// already wrote into pk_C.  f16x3: the whole live row is written as fp16 hi|lo under one scale into pk16_C (pk_C keeps the tf32
+// copy of the field blocks for the short-K bilinear GEMMs).
+static int pairs_into_mlp_input(const fbn_params_t* p, Workspace& w, const PackDst& pkC, cudaStream_t st) {
+  if (!tl_reg.mlp16()) return bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, w.B, pkC, st);
+  tl_reg.describe_mlp(w.C, w.B, K1, w.pk16_C);
+  const Packed pk = packed_describe(w.pk16_C, w.B, K1, FBN_PREC_F16X3);
+  return bilinear_pairs_mlp16(p->bilinear_type, w.C, w.T, w.B, pk.data, pk.lo_off, pk.scale, st);
+}
+
 // The item_emb_d128 projection (ref :106) runs on the tensor cores BEFORE the gather kernel when the batch carries the vectors:
 // one short-K GEMM  Y[B,128] = item_mm[B,128] x mm_w^T + mm_b  (persistent tile loop), whose operand copy of item_mm is the one
 // the mm_proj.0.weight gradient reads later.  The gather kernel then needs neither W in shared memory nor its SIMT projection loop
@@ -447,8 +463,7 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   STAGE("fwd:embed+senet (join weight packing)");
   RC(bilinear_transform_fwd(p, w, st));
   STAGE("fwd:bilinear transforms");
-  RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, tl_reg.mlp16() ? PackDst() : pkC, st));   // the pair blocks feed the MLP only
-  RC(tl_reg.after_mlp(w.C, B, K1, w.pk16_C, active_mask()));
+  RC(pairs_into_mlp_input(p, w, pkC, st));
   STAGE("fwd:bilinear pairs");
 
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
@@ -953,8 +968,7 @@ extern "C" int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void*
     if (flush) FBN_CHECK_CUDA(cudaMemsetAsync(flush, it, flush_bytes, st));
     FBN_CHECK_CUDA(cudaEventRecord(e0, st));
     if (s == "bil_gemm") RC(bilinear_transform_fwd(p, w, st));
-    else if (s == "bil_pairs") RC(bilinear_pairs_fwd(p->bilinear_type, w.C, w.T, B, tl_reg.mlp16() ? PackDst() : pkC, st));
-    else if (s == "pack_c") RC(tl_reg.pack_mlp(w.C, B, K1, tl_reg.mlp16() ? w.pk16_C : w.pk_C, active_mask()));   // f16x3: amax + split of the MLP input
+    else if (s == "bil_pairs") RC(pairs_into_mlp_input(p, w, pkC, st));
     else if (s == "embed") RC(run_embed_fwd(p, b, w, 1, st, pkC, pkX));
     else if (s == "mlp1") {
       GemmArgs g1;

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libfibinet_b200 (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -109,6 +110,78 @@ __device__ __forceinline__ void store_packed4(void* base, long long lo_off, int 
     *reinterpret_cast<uint2*>(d + e) = o;
   }
 }
+
+// ---- FBN_PREC_F16X3 operand format (gemm_tc.cu) -----------------------------------------------------------------------------
+// A packed tensor is followed by a small float record ("tail"): [0] = s (the tensor's power-of-two scale), [1] = 1 / s, [2] = amax,
+// [4] = number of partial maxima, [F16_REC_FLOATS + i] = partial maximum i of |x| (written by an amax pass or, block by block, by
+// the kernel that produces the tensor).  max is order-independent, so the scale is a deterministic function of the values alone.
+constexpr int F16_REC_FLOATS = 16;
+constexpr int F16_AMAX_BLOCKS = 1024;
+
+__device__ __forceinline__ float f16x3_scale(float amax) {
+  // amax * s in [2^14, 2^15) (fp16 overflows at 65504); an all-zero or non-finite tensor is left unscaled; the exponent is clamped so
+  // that s and 1/s are normal fp32 numbers (only a tensor with amax < 2^-106 is scaled less than ideally)
+  const unsigned bits = __float_as_uint(amax);
+  const int e = (int)((bits >> 23) & 0xffu) - 127;
+  if (bits == 0u || e == 128) return 1.f;
+  const int k = max(-120, min(120, 14 - e));
+  return __uint_as_float((unsigned)(k + 127) << 23);
+}
+
+// max over a 256-thread block (every thread must call); the result is valid in thread 0
+__device__ __forceinline__ float block_max_256(float m) {
+  __shared__ float sm_bmax[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm_bmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm_bmax[w]);
+  }
+  __syncthreads();      // the scratch may be reused by a second call
+  return m;
+}
+
+// a producer kernel (256 threads per block, at most F16_AMAX_BLOCKS blocks) publishes its block's maximum of |values written|
+__device__ __forceinline__ void f16x3_publish_amax(float m, float* tail) {
+  m = block_max_256(m);
+  if (threadIdx.x == 0) {
+    tail[F16_REC_FLOATS + blockIdx.x] = m;
+    if (blockIdx.x == 0) tail[4] = (float)gridDim.x;
+  }
+}
+
+// every block of a pack kernel: fold the partial maxima into the tensor's scale (block 0 records it for the GEMM epilogues).
+// npartial < 0: the count the producer left in tail[4].
+__device__ __forceinline__ float f16x3_block_scale(float* tail, int npartial) {
+  __shared__ float s_scale;
+  if (npartial < 0) npartial = (int)tail[4];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < npartial; i += 256) m = fmaxf(m, tail[F16_REC_FLOATS + i]);
+  m = block_max_256(m);
+  if (threadIdx.x == 0) {
+    const float sc = f16x3_scale(m);
+    s_scale = sc;
+    if (blockIdx.x == 0) { tail[0] = sc; tail[1] = 1.0f / sc; tail[2] = m; }
+  }
+  __syncthreads();
+  return s_scale;
+}
+
+// 4 consecutive values -> hi = fp16_rn(s x) at element e, lo = fp16_rn(s x - hi) at e + lo_off
+__device__ __forceinline__ void store_f16x3_4(__half* dst, long long lo_off, long long e, float4 v, float sc) {
+  v = v * sc;
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  uint2 oh, ol;
+  oh.x = *reinterpret_cast<const uint32_t*>(&h0); oh.y = *reinterpret_cast<const uint32_t*>(&h1);
+  ol.x = *reinterpret_cast<const uint32_t*>(&l0); ol.y = *reinterpret_cast<const uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(dst + e) = oh;
+  *reinterpret_cast<uint2*>(dst + lo_off + e) = ol;
+}
+__device__ __forceinline__ float amax4(const float4& v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); }
 
 // tensor.long() on the reference's index columns (src/model_fibinet.py:140-143): truncation toward
 // zero for floating inputs; exact for |id| < 2^53 (float64) as the loader delivers them.

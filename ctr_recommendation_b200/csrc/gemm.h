@@ -51,8 +51,10 @@ bool gemm_tc_supported(const GemmArgs& g, int precision);
 size_t gemm_tc_scratch_bytes(long long M, long long N, long long K, int precision);
 size_t packed_bytes(long long rows, long long cols, int precision);
 Packed packed_describe(void* region, long long rows, long long cols, int precision = -1);
+// producer_amax (f16x3 only): the kernel that wrote `src` already published its partial maxima into the region's record
+// (PackDst::tail), so the amax pass is skipped
 int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
-                 Packed* out, cudaStream_t st);
+                 Packed* out, cudaStream_t st, bool producer_amax = false);
 int gemm(const GemmArgs& g, int precision, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 }  // namespace fbn

@@ -1163,24 +1163,13 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long ld, lo
 
 // ------------------------------------------------------------------------------------------------
 // FBN_PREC_F16X3 operands: one power-of-two scale per tensor.
-//   pass 1 (amax_partial_kernel): per-block maxima of |x| over the converted columns -> tail[F16_REC_FLOATS + block]
+//   pass 1 (amax_partial_kernel): per-block maxima of |x| over the converted columns -> tail[F16_REC_FLOATS + block].  Skipped when
+//                                 the kernel that produced the tensor already published them (PackDst::tail, `producer_amax`).
 //   pass 2 (pack_f16x3_kernel)  : every block folds the partial maxima (max is order-independent: deterministic, no atomics, nothing
 //                                 to re-arm), derives s = 2^(14 - floor(log2 amax)) and writes hi = fp16_rn(s x) at dst, lo =
 //                                 fp16_rn(s x - hi) at dst + lo_off; block 0 records {s, 1/s, amax} in tail[0..2] for the GEMM epilogues.
+// (layout of the record and the device helpers: common.cuh)
 // ------------------------------------------------------------------------------------------------
-constexpr int F16_REC_FLOATS = 16;          // scale record: [0] = s, [1] = 1 / s, [2] = amax
-constexpr int F16_AMAX_BLOCKS = 1024;       // partial maxima that follow the record
-
-__device__ __forceinline__ float f16x3_scale(float amax) {
-  // amax * s in [2^14, 2^15) (fp16 overflows at 65504); an all-zero or non-finite tensor is left unscaled; the exponent is clamped so
-  // that s and 1/s are normal fp32 numbers (only a tensor with amax < 2^-106 is scaled less than ideally)
-  const unsigned bits = __float_as_uint(amax);
-  const int e = (int)((bits >> 23) & 0xffu) - 127;
-  if (bits == 0u || e == 128) return 1.f;
-  const int k = max(-120, min(120, 14 - e));
-  return __uint_as_float((unsigned)(k + 127) << 23);
-}
-
 __global__ void __launch_bounds__(256) amax_partial_kernel(const float* __restrict__ src, long long ld, long long R, long long K,
                                                            long long Kp, unsigned long long colmask, float* __restrict__ tail) {
   const long long q = Kp / 4;
@@ -1188,46 +1177,18 @@ __global__ void __launch_bounds__(256) amax_partial_kernel(const float* __restri
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * q; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / q, c = (i % q) * 4;
     if (colmask != ~0ull && !((colmask >> (c / 128)) & 1ull)) continue;
-    if (c + 3 < K) {
-      const float4 v = ld4(src + r * ld + c);
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    } else {
+    if (c + 3 < K) m = fmaxf(m, amax4(ld4(src + r * ld + c)));
+    else
       for (long long j = c; j < K; ++j) m = fmaxf(m, fabsf(src[r * ld + j]));
-    }
   }
   // NaN inputs: fmaxf drops them here, the packed values (and every product) still carry them
-  __shared__ float sm[8];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
-    tail[F16_REC_FLOATS + blockIdx.x] = m;
-  }
+  f16x3_publish_amax(m, tail);
 }
 
 __global__ void __launch_bounds__(256) pack_f16x3_kernel(const float* __restrict__ src, long long ld, long long R, long long K,
                                                          long long Kp, __half* __restrict__ dst, long long lo_off,
                                                          unsigned long long colmask, float* __restrict__ tail, int npartial) {
-  __shared__ float sm[8];
-  __shared__ float s_scale;
-  float m = 0.f;
-  for (int i = threadIdx.x; i < npartial; i += 256) m = fmaxf(m, tail[F16_REC_FLOATS + i]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
-    const float sc = f16x3_scale(m);
-    s_scale = sc;
-    if (blockIdx.x == 0) { tail[0] = sc; tail[1] = 1.0f / sc; tail[2] = m; }
-  }
-  __syncthreads();
-  const float sc = s_scale;
+  const float sc = f16x3_block_scale(tail, npartial);
   const long long q = Kp / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * q; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / q, c = (i % q) * 4;
@@ -1239,15 +1200,7 @@ __global__ void __launch_bounds__(256) pack_f16x3_kernel(const float* __restrict
       if (c + 1 < K) v.y = src[r * ld + c + 1];
       if (c + 2 < K) v.z = src[r * ld + c + 2];
     }
-    v = v * sc;
-    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
-    uint2 oh, ol;
-    oh.x = *reinterpret_cast<const uint32_t*>(&h0); oh.y = *reinterpret_cast<const uint32_t*>(&h1);
-    ol.x = *reinterpret_cast<const uint32_t*>(&l0); ol.y = *reinterpret_cast<const uint32_t*>(&l1);
-    *reinterpret_cast<uint2*>(dst + r * Kp + c) = oh;
-    *reinterpret_cast<uint2*>(dst + lo_off + r * Kp + c) = ol;
+    store_f16x3_4(dst, lo_off, r * Kp + c, v, sc);
   }
 }
 
@@ -1312,16 +1265,19 @@ Packed packed_describe(void* region, long long rows, long long cols, int precisi
 
 // converts src (rows x cols fp32, ld) into operand format at dst (1024-byte aligned inside the caller's region)
 int pack_operand(const float* src, long long ld, long long rows, long long cols, int precision, void* dst, unsigned long long colmask,
-                 Packed* out, cudaStream_t st) {
+                 Packed* out, cudaStream_t st, bool producer_amax) {
   FBN_REQUIRE(precision == FBN_PREC_TF32X3 || precision == FBN_PREC_BF16 || precision == FBN_PREC_TF32X2 || precision == FBN_PREC_F16X3,
               FBN_ERR_ARG, "pack_operand: bad precision");
   FBN_REQUIRE(aligned16(src) && ld % 4 == 0, FBN_ERR_ALIGN, "pack_operand: source must be 16-byte aligned with ld %% 4 == 0");
   *out = packed_describe(dst, rows, cols, precision);
   if (precision == FBN_PREC_F16X3) {
     const long long n4 = rows * (out->pitch / 4);
-    const int nb1 = (int)std::max<long long>(1, std::min<long long>(cdiv(n4, 256 * 4), std::min(F16_AMAX_BLOCKS, 4 * num_sms())));
-    amax_partial_kernel<<<nb1, 256, 0, st>>>(src, ld, rows, cols, out->pitch, colmask, out->scale);
-    FBN_CHECK_LAUNCH();
+    int nb1 = -1;       // producer_amax: the count is in the record
+    if (!producer_amax) {
+      nb1 = (int)std::max<long long>(1, std::min<long long>(cdiv(n4, 256 * 4), std::min(F16_AMAX_BLOCKS, 4 * num_sms())));
+      amax_partial_kernel<<<nb1, 256, 0, st>>>(src, ld, rows, cols, out->pitch, colmask, out->scale);
+      FBN_CHECK_LAUNCH();
+    }
     const int nb2 = (int)std::max<long long>(1, std::min<long long>(cdiv(n4, 256), 16LL * num_sms()));
     pack_f16x3_kernel<<<nb2, 256, 0, st>>>(src, ld, rows, cols, out->pitch, static_cast<__half*>(out->data), out->lo_off, colmask,
                                            out->scale, nb1);

@@ -242,19 +242,23 @@ __global__ void bn_act_kernel(const float* __restrict__ H, const float* __restri
                               const float* __restrict__ g, const float* __restrict__ b, long long B, int N, DropArgs d,
                               float* __restrict__ A, PackDst pk) {
   const long long total4 = B * N / 4;
+  float amax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4;
     const int c = (int)(e % N);
     const float4 y = bn_relu_drop4(ld4s(H + e), ld4(mean + c), ld4(rstd + c), ld4(g + c), ld4(b + c), d, e, d.mask);
     st4(A + e, y);
     if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, e, y);     // pitch == N
+    amax = fmaxf(amax, amax4(y));
   }
+  if (pk.tail) f16x3_publish_amax(amax, pk.tail);
 }
 
 int bn_act(const float* H, const float* mean, const float* rstd, const float* g, const float* b, long long B, int N,
            const DropArgs& d, float* A, PackDst pk, cudaStream_t st) {
   const long long total4 = B * N / 4;
   int blocks = (int)std::min<long long>((total4 + 255) / 256, 8LL * num_sms());
+  if (pk.tail) blocks = std::min(blocks, F16_AMAX_BLOCKS);
   bn_act_kernel<<<std::max(blocks, 1), 256, 0, st>>>(H, mean, rstd, g, b, B, N, d, A, pk);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
@@ -367,6 +371,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dA, const float* _
                                     float* __restrict__ dH, PackDst pk) {
   const long long total4 = B * N / 4;
   const float invB = 1.0f / (float)B;
+  float amax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4;
     const int c = (int)(e % N);
@@ -387,7 +392,9 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dA, const float* _
     }
     st4(dH + e, out);
     if (pk.mode) store_packed4(pk.base, pk.lo_off, pk.mode, e, out);
+    amax = fmaxf(amax, amax4(out));
   }
+  if (pk.tail) f16x3_publish_amax(amax, pk.tail);
 }
 
 int bn_bwd_apply(const float* dA, const float* dlogit, const float* w3, const float* A, const float* Hd, const float* mean,
@@ -395,6 +402,7 @@ int bn_bwd_apply(const float* dA, const float* dlogit, const float* w3, const fl
                  int train, float* dH, PackDst pk, cudaStream_t st) {
   const long long total4 = B * N / 4;
   int blocks = (int)std::min<long long>((total4 + 255) / 256, 8LL * num_sms());
+  if (pk.tail) blocks = std::min(blocks, F16_AMAX_BLOCKS);
   bn_bwd_apply_kernel<<<std::max(blocks, 1), 256, 0, st>>>(dA, dlogit, w3, A, Hd, mean, rstd, g, dgamma, dbeta, B, N, scale, train,
                                                            dH, pk);
   FBN_CHECK_LAUNCH();
@@ -449,6 +457,65 @@ int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, PackDst 
   else bilinear_pairs_fwd_kernel<FBN_BILINEAR_INTERACTION><<<blocks, 256, 0, st>>>(C, T, B, pk);
   FBN_CHECK_LAUNCH();
   return FBN_OK;
+}
+
+// FBN_PREC_F16X3: the whole live MLP-input row (fields 1..5 and the 10 live pairs) as fp16 hi|lo under ONE scale.  The scale needs
+// the maximum over values this very stage computes, so it runs twice: PACK = false only reduces max |v|, max |pair| per block
+// (reads 4.5 KB / sample, writes nothing), PACK = true recomputes the products and writes the 15 split blocks (7.7 KB / sample).
+// The fp32 pair blocks are never materialised (as in the other tcgen05 modes), and there is no separate pass over C.
+template <int TYPE, bool PACK>
+__global__ void __launch_bounds__(256) bilinear_pairs_mlp16_kernel(const float* __restrict__ C, const float* __restrict__ T, long long B,
+                                                                   __half* __restrict__ dst, long long lo_off, float* __restrict__ tail) {
+  constexpr int nT = TYPE == FBN_BILINEAR_INTERACTION ? 10 : 4;
+  float sc = 1.f;
+  if (PACK) sc = f16x3_block_scale(tail, -1);
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float amax = 0.f;
+  for (long long b = warp; b < B; b += nwarps) {
+    const float* crow = C + b * K1 + 4 * lane;
+    float4 v[NF], t[nT];
+#pragma unroll
+    for (int f = 1; f < NF; ++f) v[f] = ld4s(crow + f * D);
+#pragma unroll
+    for (int k = 0; k < nT; ++k) t[k] = ld4s(T + b * (nT * D) + k * D + 4 * lane);
+    const long long e0 = b * K1 + 4 * lane;
+#pragma unroll
+    for (int f = 1; f < NF; ++f) {
+      if (PACK) store_f16x3_4(dst, lo_off, e0 + f * D, v[f], sc);
+      else amax = fmaxf(amax, amax4(v[f]));
+    }
+#pragma unroll
+    for (int i = 1; i < NF; ++i)
+#pragma unroll
+      for (int j = i + 1; j < NF; ++j) {
+        float4 p;
+        if (TYPE == FBN_BILINEAR_ALL) p = v[i] * t[j - 2];
+        else if (TYPE == FBN_BILINEAR_EACH) p = t[i - 1] * v[j];
+        else p = t[active_q(i, j)] * v[j];
+        if (PACK) store_f16x3_4(dst, lo_off, e0 + pair_block(i, j) * D, p, sc);
+        else amax = fmaxf(amax, amax4(p));
+      }
+  }
+  if (!PACK) f16x3_publish_amax(amax, tail);
+}
+
+template <int TYPE>
+static int launch_pairs_mlp16(const float* C, const float* T, long long B, void* dst16, long long lo_off, float* tail, cudaStream_t st) {
+  int blocks = (int)std::min<long long>((B + 7) / 8, 8LL * num_sms());
+  blocks = std::max(blocks, 1);
+  bilinear_pairs_mlp16_kernel<TYPE, false><<<std::min(blocks, F16_AMAX_BLOCKS), 256, 0, st>>>(C, T, B, nullptr, 0, tail);
+  FBN_CHECK_LAUNCH();
+  bilinear_pairs_mlp16_kernel<TYPE, true><<<blocks, 256, 0, st>>>(C, T, B, static_cast<__half*>(dst16), lo_off, tail);
+  FBN_CHECK_LAUNCH();
+  return FBN_OK;
+}
+
+int bilinear_pairs_mlp16(int type, const float* C, const float* T, long long B, void* dst16, long long lo_off, float* tail, cudaStream_t st) {
+  if (type == FBN_BILINEAR_ALL) return launch_pairs_mlp16<FBN_BILINEAR_ALL>(C, T, B, dst16, lo_off, tail, st);
+  if (type == FBN_BILINEAR_EACH) return launch_pairs_mlp16<FBN_BILINEAR_EACH>(C, T, B, dst16, lo_off, tail, st);
+  return launch_pairs_mlp16<FBN_BILINEAR_INTERACTION>(C, T, B, dst16, lo_off, tail, st);
 }
 
 // dT_t = sum_q dP_q * (other operand) ; dV_f = dC_f + sum_q dP_q * T  (the W^T term is added by a GEMM)

@@ -12,6 +12,9 @@ struct PackDst {
   void* base = nullptr;
   long long pitch = 0, lo_off = 0;
   int mode = 0;
+  // f16x3: the tensor is split AFTER it is complete (its scale needs the maximum of |x|); the producer only publishes its
+  // per-block maxima into the record that follows the packed region (common.cuh), launched with at most F16_AMAX_BLOCKS blocks
+  float* tail = nullptr;
 };
 
 struct DropArgs {
@@ -40,6 +43,10 @@ int bn_bwd_apply(const float* dA, const float* dlogit, const float* w3, const fl
                  const float* rstd, const float* g, const float* dgamma, const float* dbeta, long long B, int N, float scale,
                  int train, float* dH, PackDst pk, cudaStream_t st);
 int bilinear_pairs_fwd(int type, float* C, const float* T, long long B, PackDst pk, cudaStream_t st);
+// f16x3: the MLP input as fp16 hi|lo under one scale, written in one go from the field blocks of C and the transforms T -- an amax
+// pass (no writes) and a split pass that recomputes the pair products, so the fp32 pair blocks never exist (dst16: hi part,
+// lo part lo_off halves later, pitch K1; tail: the region's record)
+int bilinear_pairs_mlp16(int type, const float* C, const float* T, long long B, void* dst16, long long lo_off, float* tail, cudaStream_t st);
 int bilinear_pairs_bwd(int type, const float* C, const float* T, const float* dC, long long B, float* dT, float* dV, PackDst pk,
                        cudaStream_t st);
 int reduce_splits(const float* partial, int parts, long long M, long long N, long long part_stride, unsigned long long nmask, float* out,
