@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("FBN_BENCH_BATCH", "65536")),
                     help="per-GPU batch (BASELINE config 2 sweeps 1K-64K; 65536 is its largest point)")
-    ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "f16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FBN_BENCH_PRECISION", "f16x3"), choices=["fp32", "tf32x3", "f16x3", "bf16"])
     ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows per CPU-baseline step (0 = the per-GPU batch itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -11,7 +11,7 @@ field list, every FLOP in libfibinet_b200.so:
 ``build_model(feature_map, model_cfg)`` returns it when ``feature_map`` carries a field list:
 
     feature_map = {"fields": [("user_id", 20000), ("item_id", 91718), ("likes_level", 11), ...],      # (name, vocabulary)
-                   "bilinear_type": "all" | "each" | "interaction", "senet_reduction": 2, "dropout": 0.2, "precision": "tf32x3"}
+                   "bilinear_type": "all" | "each" | "interaction", "senet_reduction": 2, "dropout": 0.2, "precision": "f16x3"}
 
 A field may also be a dict -- what the reference's commented-out tag lookup (src/dataloader.py:100-102), its unused ``user_emb``
 (src/model_fibinet.py:101,152) and its shared tables (:155-156,159,167) need:
@@ -62,7 +62,7 @@ class _GeneralFn(torch.autograd.Function):
 
 class GeneralFiBiNET(nn.Module):
     def __init__(self, fields: Sequence[Tuple[str, int]], model_cfg: dict | None = None, bilinear_type: str = "all",
-                 senet_reduction: int = 2, dropout: float = 0.2, precision: str = "tf32x3"):
+                 senet_reduction: int = 2, dropout: float = 0.2, precision: str = "f16x3"):
         super().__init__()
         model_cfg = model_cfg or {}
         if int(model_cfg.get("embedding_dim", D)) != D:

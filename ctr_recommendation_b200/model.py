@@ -495,5 +495,5 @@ def build_model(feature_map, model_cfg):
         fm = feature_map
         return GeneralFiBiNET(fields, model_cfg, bilinear_type=fm.get("bilinear_type", "all"),
                               senet_reduction=int(fm.get("senet_reduction", 2)), dropout=float(fm.get("dropout", 0.2)),
-                              precision=fm.get("precision", "tf32x3"))
+                              precision=fm.get("precision", "f16x3"))
     return MM_FiBiNET(feature_map, model_cfg)

@@ -45,7 +45,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
 
-    model = build_model({"precision": model_cfg.get("precision", "tf32x3")}, model_cfg)
+    model = build_model({"precision": model_cfg.get("precision", "f16x3")}, model_cfg)
     ckpt = "../checkpoints/FiBiNET_best.pth"
     if not os.path.exists(ckpt):
         ckpt = "checkpoints/FiBiNET_best.pth"

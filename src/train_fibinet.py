@@ -99,7 +99,7 @@ def main():
     valid_loader = MMCTRDataLoader(None, dataset_cfg["valid_data"], dataset_cfg["item_info"], batch_size=batch_size, shuffle=False,
                                    num_workers=workers, max_len=max_len, with_mm=False, pin_memory=True)
 
-    fm = {"precision": model_cfg.get("precision", "tf32x3")}
+    fm = {"precision": model_cfg.get("precision", "f16x3")}
     row_sharded = str(model_cfg.get("table_sharding", "")).lower() == "row"   # B200 extra: item table partitioned by id % world
     if row_sharded:
         fm["table_sharding"] = "row"

@@ -183,8 +183,8 @@ def test_fused_adagrad_vs_oracle(gpu, wd, engine):
     assert moved.size > 0
 
 
-@pytest.mark.parametrize("schedule", ["partial", "full", "wgrad"])
-def test_phased_backward_equals_single_call(gpu, schedule):
+@pytest.mark.parametrize("schedule,precision", [("partial", "tf32x3"), ("full", "tf32x3"), ("wgrad", "tf32x3"), ("full", "f16x3"), ("wgrad", "f16x3")])
+def test_phased_backward_equals_single_call(gpu, schedule, precision):
     """fbn_backward_phase (the schedules the data-parallel engine interleaves with its gradient all-reduces: CHAIN [+ LEAF1 beside it],
     then the remaining leaves) produces bit-identical gradients, weights and moments to the single fbn_backward call -- same kernels,
     same per-tensor summation order; run here on one GPU without the collectives.  With SMs reserved for a collective the split-K
@@ -195,7 +195,7 @@ def test_phased_backward_equals_single_call(gpu, schedule):
     pool = [synth.make_batch(seed=1300 + s, batch=B, id_dist="zipf", index_dtype=np.float64, edge_cases=False) for s in range(3)]
     finals = []
     for phased, reserve in ((False, 0), (True, 0), (True, 8)):
-        model = gpu["make_model"](train=True, precision="tf32x3")
+        model = gpu["make_model"](train=True, precision=precision)
         opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
         eng = TrainStep(model, opt, B, 20, idx_dtype=torch.float64, overlap=schedule, reserve_sms=reserve, phased_single=phased)
         assert eng._phased_single == phased
@@ -210,7 +210,7 @@ def test_phased_backward_equals_single_call(gpu, schedule):
     for k in finals[0]:
         assert np.array_equal(finals[0][k], finals[1][k]), k
     # one step with 8 SMs reserved: same gradients up to the split-K summation order
-    model = gpu["make_model"](train=True, precision="tf32x3")
+    model = gpu["make_model"](train=True, precision=precision)
     opt = FusedAdam(model, lr=1e-3, weight_decay=1e-5)
     eng = TrainStep(model, opt, B, 20, idx_dtype=torch.float64)
     eng(_pinned(pool[0][0]), torch.from_numpy(pool[0][1]).pin_memory())

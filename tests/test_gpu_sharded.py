@@ -195,12 +195,12 @@ def _plain_model(env, precision="fp32", dropout=0.0):
     return m.cuda().train()
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_sharded_trainstep_matches_replicated_bitwise(env, graph):
+@pytest.mark.parametrize("graph,precision", [(False, "fp32"), (True, "fp32"), (True, "f16x3")])
+def test_sharded_trainstep_matches_replicated_bitwise(env, graph, precision):
     from ctr_recommendation_b200 import FusedAdam
     from ctr_recommendation_b200.engine import ShardedTrainStep, TrainStep
     B, steps = 512, 3
-    a, b = _plain_model(env), _sharded_model(env)
+    a, b = _plain_model(env, precision), _sharded_model(env, precision)
     oa, ob = FusedAdam(a, lr=1e-3, weight_decay=1e-5), FusedAdam(b, lr=1e-3, weight_decay=1e-5)
     ea = TrainStep(a, oa, B, 20, idx_dtype=torch.float64, graph=graph)
     eb = ShardedTrainStep(b, ob, B, 20, idx_dtype=torch.float64, graph=graph)

@@ -29,7 +29,7 @@ def make(precision):
 def main():
     rank, local, world = fdist.init_from_env()
     torch.cuda.set_device(local)
-    precision = "tf32x3"
+    precision = os.environ.get("FBN_PRECISION", "f16x3")
     # global batch sizes: even split, uneven tail (rank shards of different size: loss weights B_r / B), and a tail so small that
     # torch's scatter chunking leaves the last rank WITHOUT rows (it joins the collectives with zero gradients)
     sizes = [1024, 1023, world - 1] if world > 1 else [1024, 1023]

@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--batch", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--precision", default="f16x3")
     args = ap.parse_args()
     rank, local, world = fdist.init_from_env()
     torch.cuda.set_device(local)
