@@ -1146,12 +1146,13 @@ extern "C" int fbn_time_gemm(const float* A, const float* Bm, float* C, int64_t 
   return FBN_OK;
 }
 
-namespace fbn { void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); void set_tc_reserve_sms(int n); void set_col_chunk_mult(int m); }
+namespace fbn { void set_f16_persist_k(int k); void set_tc_pair(int on); void set_tc_persistent(int on); void set_tc_pair_persistent(int on); void set_tc_reserve_sms(int n); void set_col_chunk_mult(int m); }
 
 // runtime knobs: "tc_pair" = 1 (default) use CTA-pair (cta_group::2) tiles for large tcgen05 GEMMs, 0 = single-CTA tiles
 extern "C" int fbn_set_option(const char* name, int value) {
   FBN_REQUIRE(name != nullptr, FBN_ERR_ARG, "fbn_set_option: null name");
   if (strcmp(name, "tc_pair") == 0) { fbn::set_tc_pair(value); return FBN_OK; }
+  if (strcmp(name, "f16_persist_k") == 0) { fbn::set_f16_persist_k(value); return FBN_OK; }
   if (strcmp(name, "tc_pair_persistent") == 0) { fbn::set_tc_pair_persistent(value); return FBN_OK; }
   if (strcmp(name, "ext_proj") == 0) { g_ext_proj = value; return FBN_OK; }
   if (strcmp(name, "col_chunk_mult") == 0) { fbn::set_col_chunk_mult(value); return FBN_OK; }

@@ -1394,6 +1394,8 @@ static int launch_tc2p(const TcMaps& maps, const TcArgs& t, cudaStream_t st) {
   return FBN_OK;
 }
 
+static int g_f16_persist_k = 0;   // 0: the tf32x3 rule
+void set_f16_persist_k(int k) { g_f16_persist_k = k; }
 static int g_tc_pair = 1;   // 0: always use the 1-CTA kernel (fbn_set_option("tc_pair", 0))
 void set_tc_pair(int on) { g_tc_pair = on; }
 static int g_tc_pair_persistent = 1;   // 0: one 256 x 256 tile per cluster (fbn_set_option("tc_pair_persistent", 0)), for A/B runs
@@ -1487,8 +1489,10 @@ static int gemm_tc_mode(const GemmArgs& g, void* scratch, size_t scratch_bytes, 
     // one bf16 pass with K <= 512 is epilogue-bound: the persistent single-CTA tile loop beats the pair kernel there
     const long long single_tiles = cdiv(g.M, TC_BM) * (g.N / TC_BN);
     // (and a short-K, 128-wide tf32x3 GEMM -- the item_emb_d128 projection -- cannot pair at all: the tile loop hides its epilogue too)
+    // f16x3 (three passes at the bf16 rate) sits between the two: fbn_set_option("f16_persist_k", K) moves its threshold (A/B runs)
     const bool persist = g.splits == 1 && single_tiles >= 2LL * num_sms() &&
-                         (MODE == FBN_PREC_BF16 ? g.K <= 512 : (g.K <= 256 && g.N == TC_BN));
+                         (MODE == FBN_PREC_BF16 ? g.K <= 512
+                                                : (MODE == FBN_PREC_F16X3 && g_f16_persist_k > 0 ? g.K <= g_f16_persist_k : (g.K <= 256 && g.N == TC_BN)));
     if (g_tc_pair && !use_persistent(persist) && g.M > 128 && g.N >= 256 && pair_ctas >= 120) {
       if (g_tc_pair_persistent && g.N / 128 <= 64) {
         if (a_mn && b_mn) rc = launch_tc2p<MODE, true, true>(maps, t, st);
