@@ -166,23 +166,44 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 constexpr int EPI_PITCH = 132;                      // floats per staged row (+4 pad)
 constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH * 4;  // 16.5 KB per epilogue warp
 
+// shared-memory accesses of the staging buffer as explicit ld/st.shared: through a generic pointer the compiler emitted LD.E / ST.E
+// and, not knowing that they cannot alias the global stores of the same loop, kept every staged read behind the previous row's
+// store (ncu source view of the MLP-1 data gradient: 31 % of all stall samples sat on those generic loads)
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
 // s0 / s1: inverse operand scales of FBN_PREC_F16X3 (exact powers of two, applied one after the other so that their product can
-// never leave the fp32 range on its own); 1 for the other modes.
-__device__ __forceinline__ void epilogue_store(const float (&acc)[128], float* stage, int lane, long long row0, long long M,
+// never leave the fp32 range on its own); 1 for the other modes.  stage: shared-space byte address of this warp's staging rows.
+__device__ __forceinline__ void epilogue_store(const float (&acc)[128], uint32_t stage, int lane, long long row0, long long M,
                                                float* cbase, long long ldc, const float* bias, int accumulate, float s0 = 1.f,
                                                float s1 = 1.f) {
 #pragma unroll
   for (int j = 0; j < 128; j += 4)
-    *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    sts128(stage + (uint32_t)(lane * EPI_PITCH + j) * 4u, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
   __syncwarp();
   const float4 bv = bias ? ld4(bias + 4 * lane) : f4(0.f);
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    if (row0 + r >= M) break;
-    float4 o = (*reinterpret_cast<const float4*>(stage + r * EPI_PITCH + 4 * lane) * s0) * s1 + bv;
-    float* cp = cbase + (long long)r * ldc + 4 * lane;
-    if (accumulate) o += *reinterpret_cast<const float4*>(cp);
-    st4(cp, o);
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {       // eight staged rows first, then their eight global stores
+    if (row0 + r0 >= M) break;
+    float4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = lds128(stage + (uint32_t)((r0 + i) * EPI_PITCH + 4 * lane) * 4u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + i;
+      if (row0 + r < M) {
+        float4 x = (o[i] * s0) * s1 + bv;
+        float* cp = cbase + (long long)r * ldc + 4 * lane;
+        if (accumulate) x += *reinterpret_cast<const float4*>(cp);
+        st4(cp, x);
+      }
+    }
   }
 }
 
@@ -388,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     {
       const long long row0 = (long long)m0 + q * 32;
       float* cbase = g.C + (long long)bi * g.strideC + (long long)sp * g.strideSplit + row0 * g.ldc + n0;
-      epilogue_store(acc, reinterpret_cast<float*>(smem + (warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
+      epilogue_store(acc, smem_u32(smem) + (uint32_t)((warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
                      g.bias ? g.bias + n0 : nullptr, g.accumulate, s0, s1);
     }
   }
@@ -569,7 +590,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcp_kernel(const __grid_co
     }
   } else {
     const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);
+    const uint32_t stage = smem_u32(epi) + (uint32_t)((warp - 2) * EPI_WARP_BYTES);
     float s0 = 1.f, s1 = 1.f;
     if (Cfg::SCALED) {
       if (g.inv_sa) s0 = __ldg(g.inv_sa);
@@ -833,7 +854,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
     if (col_on) {
       const long long row0 = (long long)m0 + q * 32;
       float* cbase = g.C + (long long)sp * g.strideSplit + row0 * g.ldc + ncol0;
-      epilogue_store(acc, reinterpret_cast<float*>(smem + (warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
+      epilogue_store(acc, smem_u32(smem) + (uint32_t)((warp - 2) * EPI_WARP_BYTES), lane, row0, g.M, cbase, g.ldc,
                      g.bias ? g.bias + ncol0 : nullptr, g.accumulate, s0, s1);
     }
   }
@@ -869,7 +890,8 @@ struct Tc2pArgs {
 
 constexpr int EPI2_WARP_FLOATS = 32 * 32;
 
-__device__ __forceinline__ void epilogue_store_sw(const float (&acc)[128], float* stage, int lane, long long row0, long long M,
+// stage: shared-space byte address of this warp's 4 KB (32 rows x 32 floats, 16-byte chunks XOR-swizzled by the row)
+__device__ __forceinline__ void epilogue_store_sw(const float (&acc)[128], uint32_t stage, int lane, long long row0, long long M,
                                                   float* cbase, long long ldc, const float* bias, int accumulate, float s0 = 1.f,
                                                   float s1 = 1.f) {
   const int rr = lane >> 3, cc = lane & 7;
@@ -877,18 +899,24 @@ __device__ __forceinline__ void epilogue_store_sw(const float (&acc)[128], float
   for (int q4 = 0; q4 < 4; ++q4) {
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4)
-      *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
-          make_float4(acc[q4 * 32 + c4 * 4], acc[q4 * 32 + c4 * 4 + 1], acc[q4 * 32 + c4 * 4 + 2], acc[q4 * 32 + c4 * 4 + 3]);
+      sts128(stage + (uint32_t)(lane * 32 + ((c4 ^ (lane & 7)) << 2)) * 4u,
+             make_float4(acc[q4 * 32 + c4 * 4], acc[q4 * 32 + c4 * 4 + 1], acc[q4 * 32 + c4 * 4 + 2], acc[q4 * 32 + c4 * 4 + 3]));
     __syncwarp();
     const float4 bv = bias ? ld4(bias + q4 * 32 + cc * 4) : f4(0.f);
+    float4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {       // all eight staged rows first, then the eight global stores
+      const int r = i * 4 + rr;
+      o[i] = lds128(stage + (uint32_t)(r * 32 + ((cc ^ (r & 7)) << 2)) * 4u);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + rr;
       if (row0 + r < M) {
-        float4 o = (*reinterpret_cast<const float4*>(stage + r * 32 + ((cc ^ (r & 7)) << 2)) * s0) * s1 + bv;
+        float4 x = (o[i] * s0) * s1 + bv;
         float* cp = cbase + (long long)r * ldc + q4 * 32 + cc * 4;
-        if (accumulate) o += *reinterpret_cast<const float4*>(cp);
-        st4(cp, o);
+        if (accumulate) x += *reinterpret_cast<const float4*>(cp);
+        st4(cp, x);
       }
     }
     __syncwarp();
@@ -955,7 +983,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b, 1);
-      mbar_init(tempty + b, 2 * 256);
+      mbar_init(tempty + b, 2 * 8);       // one arrival per epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1064,7 +1092,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    float* stage = reinterpret_cast<float*>(epi) + (warp - 2) * EPI2_WARP_FLOATS;
+    const uint32_t stage = smem_u32(epi) + (uint32_t)((warp - 2) * EPI2_WARP_FLOATS * 4);
     float s0 = 1.f, s1 = 1.f;
     if (Cfg::SCALED) {
       if (g.inv_sa) s0 = __ldg(g.inv_sa);
@@ -1089,8 +1117,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
         }
+        // tcgen05.wait::ld is warp-collective: once it has returned the whole warp's slice of the accumulator is in registers,
+        // so ONE remote arrival per warp releases the buffer (16 per chunk on the leader's barrier instead of 512)
         tc_fence_before();
-        mbar_arrive_cluster(tempty_leader0 + (uint32_t)(buf * 8));
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader0 + (uint32_t)(buf * 8));
       }
       if (half == 0 || ti.hasB) {
         const int ncol0 = (half == 0 ? ti.nbA : ti.nbB) * 128;
