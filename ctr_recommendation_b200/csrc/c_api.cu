@@ -319,7 +319,7 @@ extern "C" size_t fbn_workspace_offset(int64_t batch, int64_t seq_len, int64_t i
 // stream and events are created on the first non-capturing call.
 struct SideCtx {
   cudaStream_t s = nullptr;
-  cudaEvent_t fork_ev[6], join_ev;
+  cudaEvent_t fork_ev[6], join_ev, mark_ev;
   int dev = -1;
   bool ok = false;
 };
@@ -337,6 +337,7 @@ static bool side_ready(cudaStream_t main) {
   if (cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
   for (auto& e : g_side.fork_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&g_side.mark_ev, cudaEventDisableTiming);
   g_side.dev = dev; g_side.ok = true;
   return true;
 }
@@ -346,6 +347,9 @@ static int side_fork(cudaStream_t main, int slot) {
   FBN_CHECK_CUDA(cudaStreamWaitEvent(g_side.s, g_side.fork_ev[slot], 0));
   return FBN_OK;
 }
+// a point on the side stream the caller's stream can wait for BEFORE the final join (everything issued on the side stream so far)
+static int side_mark() { FBN_CHECK_CUDA(cudaEventRecord(g_side.mark_ev, g_side.s)); return FBN_OK; }
+static int side_wait_mark(cudaStream_t main) { FBN_CHECK_CUDA(cudaStreamWaitEvent(main, g_side.mark_ev, 0)); return FBN_OK; }
 static int side_join(cudaStream_t main) {
   FBN_CHECK_CUDA(cudaEventRecord(g_side.join_ev, g_side.s));
   FBN_CHECK_CUDA(cudaStreamWaitEvent(main, g_side.join_ev, 0));
@@ -448,10 +452,13 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   const int nW = p->bilinear_type == FBN_BILINEAR_ALL ? 1 : (p->bilinear_type == FBN_BILINEAR_EACH ? NF - 1 : FBN_PAIRS);
   // the weights are converted on the side stream while the gather kernel runs
   const bool parf = tl_reg.on() && side_ready(st);
+  // (the bilinear weight first: the transforms wait only for it -- `mark` -- while the MLP weights, which in f16x3 take an amax
+  // and a split pass each, keep converting beside the transforms and the pair stage; the MLP-1 GEMM joins the side stream)
   if (parf) { RC(side_fork(st, 4)); tl_reg.st = g_side.s; }
+  RC(tl_reg.pack(p->bil_w, (long long)nW * D, D, w.pk_bil));
+  if (parf) RC(side_mark());
   RC(tl_reg.pack_mlp(p->w1, H1, K1, w.pk_w1, active_mask()));
   RC(tl_reg.pack_mlp(p->w2, H2, H1, w.pk_w2));
-  RC(tl_reg.pack(p->bil_w, (long long)nW * D, D, w.pk_bil));
   tl_reg.st = st;
 
   // activations are converted to the operand format by the kernels that produce them (no separate pack pass)
@@ -459,12 +466,13 @@ extern "C" int fbn_forward(const fbn_params_t* p, const fbn_batch_t* b, void* ws
   STAGE("fwd:start");
   RC(run_embed_fwd(p, b, w, 1, st, pkC, tl_reg.dst(b->item_mm ? b->item_mm : w.xmm, B, D, w.pk_xmm)));
   (void)fmask;
-  if (parf) RC(side_join(st));
-  STAGE("fwd:embed+senet (join weight packing)");
+  if (parf) RC(side_wait_mark(st));
+  STAGE("fwd:embed+senet (bilinear weight ready)");
   RC(bilinear_transform_fwd(p, w, st));
   STAGE("fwd:bilinear transforms");
   RC(pairs_into_mlp_input(p, w, pkC, st));
-  STAGE("fwd:bilinear pairs");
+  if (parf) RC(side_join(st));
+  STAGE("fwd:bilinear pairs (join MLP weight packing)");
 
   float* mean1 = w.bn; float* rstd1 = w.bn + H1; float* mean2 = w.bn + 2 * H1; float* rstd2 = w.bn + 2 * H1 + H2;
   GemmArgs g1;
@@ -504,11 +512,16 @@ static int pick_splits_pair(long long M, long long N, long long K, unsigned long
   const long long clusters = cdiv(M, 256) * cdiv(nlive, 2);
   const long long kblocks = std::max<long long>(1, cdiv(K, 32));
   const long long slots = std::max(1, (num_sms() - tc_reserved_sms()) / 2);   // clusters that can run at once
+  // cost in k-block times of a 256 x 256 tile (~1.3 us measured): waves x k-blocks per split, plus the fixed-order reduction of the
+  // partials (1.6 us per split for the 512 x 1920 MLP-1 gradient, proportional to the output size).  At K = 65536 the second
+  // term is noise and the split that fills whole waves wins (9 for MLP-1: 144 tiles = 2 waves of 74); at the reference's batch
+  // 4096 it is what matters (9 splits: 2 x 8 + 11 = 27 units; 4 splits: 16 + 5 = 21).
+  const double red = 1.25 * (double)(M * nlive * 128) / (512.0 * 1920.0);
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= 32; ++s) {
     if ((size_t)s * M * N > max_floats || cdiv(kblocks, s) < 4) break;
-    const double cost = (double)cdiv(clusters * s, slots) / s + 0.002 * s;   // waves per unit of K work (+ a little for the reduce)
+    const double cost = (double)cdiv(clusters * s, slots) * (double)cdiv(cdiv(K, 64), s) + red * s;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
