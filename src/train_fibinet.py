@@ -145,10 +145,16 @@ def main():
     best_path = "../checkpoints/FiBiNET_best.pth"
     # Resume (the reference only ever saves the best weights and cannot continue a run): after every epoch rank 0
     # writes the full training state -- weights, Adam moments + step, scheduler, dropout-stream counters, loader RNG -- and
-    # FBN_RESUME=1 continues from it bit for bit.  Not offered for a row-sharded table (its moments live on the owning ranks).
-    last_path = "../checkpoints/FiBiNET_last.pth"
+    # FBN_RESUME=1 continues from it bit for bit.  With a row-sharded table every rank writes its own file (its slice of the table
+    # and of the Adam moments live only there; the dense state is replicated) and a run resumes on the same number of ranks.
+    last_path = f"../checkpoints/FiBiNET_last.rank{rank}of{world}.pth" if row_sharded else "../checkpoints/FiBiNET_last.pth"
     start_epoch = 0
-    if os.environ.get("FBN_RESUME") == "1" and os.path.exists(last_path) and not row_sharded:
+    have_last = os.path.exists(last_path)
+    if row_sharded and world > 1:      # all ranks or none
+        flag = torch.tensor([1 if have_last else 0], device=device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        have_last = bool(flag.item())
+    if os.environ.get("FBN_RESUME") == "1" and have_last:
         state = torch.load(last_path, map_location="cpu", weights_only=True)     # tensors + plain Python values only
         model.load_state_dict(state["model"])
         optimizer.load_state_dict(state["optimizer"])
@@ -210,7 +216,7 @@ def main():
                 if rank == 0:
                     torch.save(sd, best_path)
                     log(f"[ckpt] new best -> {best_path}")
-        if rank == 0 and not row_sharded:
+        if rank == 0 or row_sharded:
             torch.cuda.synchronize()
             # tensors and plain values only (loads with weights_only=True); written beside the old file and renamed over it, so a
             # crash during the save never leaves a truncated resume file

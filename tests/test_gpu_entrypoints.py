@@ -68,9 +68,12 @@ def _run_train(cwd, env_extra):
     return r.stdout
 
 
-def test_resume_continues_bit_for_bit(tmp_path):
+@pytest.mark.parametrize("table_sharding", [None, "row"])
+def test_resume_continues_bit_for_bit(tmp_path, table_sharding):
     """SURVEY 8f-3: FiBiNET_last.pth carries weights, Adam moments + step, scheduler, dropout-stream counters and the loader RNG;
-    1 epoch + FBN_RESUME=1 for the remaining 2 ends in exactly the state of an uninterrupted 3-epoch run (dropout is ON)."""
+    1 epoch + FBN_RESUME=1 for the remaining 2 ends in exactly the state of an uninterrupted 3-epoch run (dropout is ON).  With a
+    row-sharded table every rank keeps its own resume file (one rank here: the table slice is the whole table)."""
+    last = "FiBiNET_last.rank0of1.pth" if table_sharding else "FiBiNET_last.pth"
     states = {}
     for tag in ("straight", "resumed"):
         root = tmp_path / tag
@@ -79,6 +82,8 @@ def test_resume_continues_bit_for_bit(tmp_path):
                         "--test", "10"], check=True, capture_output=True)
         cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "fibinet_config.yaml")))
         cfg[cfg["base_expid"]].update(epochs=3, batch_size=512)
+        if table_sharding:
+            cfg[cfg["base_expid"]]["table_sharding"] = table_sharding
         (root / "config").mkdir()
         yaml.safe_dump(cfg, open(root / "config" / "fibinet_config.yaml", "w"))
         cwd = root / "src"
@@ -90,8 +95,8 @@ def test_resume_continues_bit_for_bit(tmp_path):
             assert "stopping after epoch 1" in out
             out = _run_train(cwd, {"FBN_RESUME": "1"})
             assert "continuing at epoch 2" in out
-        assert not os.path.exists(root / "checkpoints" / "FiBiNET_last.pth.tmp")          # written beside, renamed over
-        states[tag] = torch.load(root / "checkpoints" / "FiBiNET_last.pth", map_location="cpu", weights_only=True)   # plain values + tensors only
+        assert not os.path.exists(root / "checkpoints" / (last + ".tmp"))          # written beside, renamed over
+        states[tag] = torch.load(root / "checkpoints" / last, map_location="cpu", weights_only=True)   # plain values + tensors only
     a, b = states["straight"], states["resumed"]
     # 1500 rows at batch 512 = 2 full steps + a 476-row tail per epoch: ONE dropout stream shared by both engines -> 9 steps
     assert a["epoch"] == b["epoch"] == 3 and a["dropout_counter"] == b["dropout_counter"] == 9
