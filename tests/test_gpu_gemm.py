@@ -130,6 +130,52 @@ def test_f16x3_scales(a_t, b_t, M, N, K, a_scale, b_scale):
         assert err <= (1e-5 if cols.start == 0 else 3e-6), (cols, err)
 
 
+def test_f16x3_pack_bits_match_restatement():
+    """The operand format itself, byte for byte: after an fbn_gemm call in f16x3 the scratch holds both packed operands --
+    [hi (rows, pitch) fp16 | lo | record {s, 1/s, amax, ...}] at the next 1024-byte boundary -- and they must equal the numpy
+    restatement (oracle/f16x3_numpy.py: amax -> power-of-two scale, hi = rn(s x), lo = rn(s x - hi)) bit for bit, zero padding
+    included; the product agrees with the restatement's exact-product sum to accumulation rounding."""
+    import ctypes as C
+    from ctr_recommendation_b200 import _lib
+    from oracle import f16x3_numpy as F
+    lib = _lib.load()
+    M, N, K = 300, 128, 204                                   # K % 8 != 0: 4 zero padding columns per row
+    pitch = (K + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(M, K, device="cuda", generator=g) * 3e-5  # gradient-sized
+    A[:, :16] *= 1e-5                                         # a block near the fp16 subnormal floor after scaling
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05  # nn.Linear weight (N, K)
+    Cm = torch.empty(M, N, device="cuda")
+    prec = _lib.PRECISIONS["f16x3"]
+    nbytes = lib.fbn_gemm_scratch_bytes(M, N, K, prec)
+    scratch = torch.zeros(nbytes + 1024, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.fbn_gemm(_lib.ptr(A), _lib.ptr(W), None, _lib.ptr(Cm), M, N, K, K, K, N, 0, 1, prec, _lib.ptr(scratch), nbytes,
+                            _lib.stream_ptr()), "fbn_gemm")
+    torch.cuda.synchronize()
+    raw = scratch.cpu().numpy()
+    base = scratch.data_ptr()
+
+    def region(start, rows):
+        off = start + (-(base + start)) % 1024
+        hi = raw[off: off + rows * pitch * 2].view(np.float16).reshape(rows, pitch)
+        lo = raw[off + rows * pitch * 2: off + rows * pitch * 4].view(np.float16).reshape(rows, pitch)
+        rec = raw[off + rows * pitch * 4: off + rows * pitch * 4 + 16].view(np.float32)
+        return hi, lo, rec
+
+    region_bytes = lambda rows: rows * pitch * 4 + 1024 + (16 + 1024) * 4      # packed_bytes(rows, K, f16x3)
+    for name, x, start, rows in (("A", A, 0, M), ("W", W, region_bytes(M), N)):
+        xn = x.cpu().numpy()
+        hi, lo, rec = region(start, rows)
+        ohi, olo, s = F.split(xn)
+        assert rec[0] == np.float32(s) and rec[1] == np.float32(1.0 / s) and rec[2] == np.abs(xn).max(), (name, rec[:3], s)
+        assert np.array_equal(hi[:, :K].view(np.uint16), ohi.view(np.uint16)), name
+        assert np.array_equal(lo[:, :K].view(np.uint16), olo.view(np.uint16)), name
+        assert not hi[:, K:].view(np.uint16).any() and not lo[:, K:].view(np.uint16).any(), name
+    ref = F.matmul(A.cpu().numpy(), W.cpu().numpy().T)
+    got = Cm.cpu().numpy()
+    assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-6
+
+
 def test_f16x3_zero_operand():
     """an all-zero operand (amax = 0) is left unscaled and gives an exact zero product + bias"""
     from ctr_recommendation_b200.functional import gemm
