@@ -384,7 +384,8 @@ int fbn_time_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N
                   int precision, void* scratch, size_t scratch_bytes, void* flush, size_t flush_bytes, int iters, float* ms_out,
                   fbn_stream_t stream);
 /* Benchmark helper: mean CUDA-event duration (ms) of one stage of the forward pass exactly as fbn_forward launches it, after a
- * complete fbn_forward on the same workspace: "embed", "bil_gemm", "bil_pairs", "mlp1".  `flush` is overwritten before
+ * complete fbn_forward on the same workspace: "embed", "bil_gemm", "bil_pairs" (f16x3: the amax + split passes that write the MLP input), "mlp1", "mlp1_dgrad", "mlp1_wgrad"
+ * (the last two after an fbn_backward).  `flush` is overwritten before
  * every timed launch (L2 eviction).  Synchronises the stream. */
 int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t ws_bytes, const char* stage, void* flush,
                    size_t flush_bytes, int iters, float* ms_out, fbn_stream_t stream);
@@ -393,7 +394,10 @@ int fbn_time_stage(const fbn_params_t* p, const fbn_batch_t* b, void* ws, size_t
 int fbn_stage_report(char* buf, size_t buf_bytes);
 /* runtime knobs: "tc_pair" (1 = CTA-pair 256x256 tcgen05 tiles for large GEMMs [default], 0 = single-CTA 128x128),
  * "tc_persistent" (0 = per-launch heuristic [default]: persistent tile loop for short-K / bf16 epilogue-bound GEMMs,
- * 1 = always, -1 = never), "stage_events" (see fbn_stage_report) */
+ * 1 = always, -1 = never), "tc_pair_persistent" (1 = the CTA pairs walk a tile list [default], 0 = one tile per cluster),
+ * "f16_persist_k" (K threshold below which an f16x3 GEMM takes the single-CTA persistent loop; 0 = the tf32x3 rule [default]),
+ * "tc_reserve_sms" (SMs the persistent GEMMs leave to a concurrent collective), "side_streams", "ext_proj", "col_chunk_mult",
+ * "stage_events" (see fbn_stage_report) */
 int fbn_set_option(const char* name, int value);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 uint64_t fbn_launch_count(void);
