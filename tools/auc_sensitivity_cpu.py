@@ -5,10 +5,11 @@ of the reference can be held to -- plus two arms whose every matmul is an exact 
 
     python tools/auc_sensitivity_cpu.py [steps] [arms, e.g. fp32,fp64,f16x3,tf32x3]
 
-Measured (B = 1024, 20000 validation rows, AUC against the fp64 oracle):
-    4 steps : fp32 1.3e-06   f16x3 4.7e-07   tf32x3 2.1e-07
-   40 steps : fp32 8.4e-04   f16x3 see profiles/r2c_auc_sensitivity_cpu.txt
-The split-operand arms sit inside the spread of the two plain restatements.
+Measured (B = 1024, 20000 validation rows, |AUC - AUC of the fp64 oracle|; profiles/r2c_auc_sensitivity_cpu.txt):
+    4 steps : fp32 1.4e-06   f16x3 3.1e-06   tf32x3 6.1e-06
+   40 steps : fp32 8.4e-04   f16x3 9.4e-05   tf32x3 2.4e-04
+The split-operand arms sit inside the spread of the two plain restatements (multi-step trajectories are chaotic at the 1e-4
+level, DESIGN.md section 2, finding 1).
 """
 import os
 import sys
