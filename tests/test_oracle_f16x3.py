@@ -46,3 +46,35 @@ def test_matmul_is_fp32_grade(a_scale, b_scale):
     assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-6
     plain = (a @ b)                                       # numpy's own fp32 product for scale
     assert np.abs(got - ref).max() <= 4 * max(np.abs(plain - ref).max(), 1e-7 * np.abs(ref).max())
+
+
+def test_model_level_emulation_is_fp32_grade():
+    """The whole FiBiNET train step of the numpy oracle with EVERY matmul (forward and backward) replaced by the exact emulation of
+    the f16x3 operand split (tools/split_precision_sim.py, the kernels' scale rule): logits and all gradients stay within the
+    north_star tolerance (1e-5 relative) of the fp64 oracle -- and so does the same step with every scale deliberately 2^-12 too
+    small.  bf16x3 (bf16 hi|lo, the other 3-pass candidate at the bf16 rate) does not."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import split_precision_sim as sim
+    from oracle import fibinet_numpy as O, synth
+    B = 512
+    P = synth.make_weights(7)
+    batch, labels = synth.make_batch(101, B, id_dist="zipf")
+    masks = synth.make_dropout_masks(5, B)
+    p64, c64 = O.forward({k: v.copy() for k, v in P.items()}, batch, train=True, masks=masks, dtype=np.float64, update_running=False)
+    _, dp64 = O.bce_loss(p64, labels, np.float64)
+    G64 = O.backward(P, c64, dp64)
+    gates = (c64["Y1"] > 0, c64["Y2"] > 0)      # a flipped ReLU decision is not an operand error (DESIGN.md section 2)
+    skip = ("mlp.0.bias", "mlp.4.bias")         # pre-BatchNorm biases: the exact gradient is 0
+    worst = {}
+    for scheme, shift in (("f16x3", 0), ("f16x3", 12), ("bf16x3", 0)):
+        sim.SHIFT = shift
+        try:
+            _, logit, G, _ = sim.run(P, batch, labels, masks, scheme, gates=gates)
+        finally:
+            sim.SHIFT = 0
+        worst[(scheme, shift)] = (sim.rel(logit, c64["logit"]), max(sim.rel(G[k], G64[k]) for k in G if k not in skip))
+    for key in (("f16x3", 0), ("f16x3", 12)):
+        assert worst[key][0] <= 2e-6 and worst[key][1] <= 1e-5, (key, worst[key])
+    assert worst[("bf16x3", 0)][1] > 1e-5, worst
